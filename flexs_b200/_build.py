@@ -1,0 +1,81 @@
+"""Builds ``flexs_b200/libflexs_b200.so`` (sm_100a only) with nvcc, in-tree.
+
+The library is a plain C-ABI shared object (include/flexs_b200.h); it links the CUDA runtime
+statically and nothing else, so it can be loaded next to torch or from any FFI.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+CSRC = PKG_DIR / "csrc"
+LIB_PATH = PKG_DIR / "libflexs_b200.so"
+
+SOURCES = ["api.cu", "encode.cu", "cnn_simple.cu", "cnn_tiled.cu", "cnn_umma.cu", "mlp.cu",
+           "topk.cu", "gen.cu", "train.cu"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+    "--expt-relaxed-constexpr",
+    "-Xptxas", "-v",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def needs_build() -> bool:
+    if not LIB_PATH.exists():
+        return True
+    lib_m = LIB_PATH.stat().st_mtime
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG_DIR.parent / "include" / "flexs_b200.h"]
+    return any(p.stat().st_mtime > lib_m for p in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile every CUDA source for sm_100a and link the shared library."""
+    if not force and not needs_build():
+        return LIB_PATH
+    obj_dir = CSRC / "build"
+    obj_dir.mkdir(exist_ok=True)
+    nvcc = _nvcc()
+    objs = []
+    procs = []
+    for src in SOURCES:
+        obj = obj_dir / (src[:-3] + ".o")
+        objs.append(str(obj))
+        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        procs.append((src, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    failed = False
+    for src, cmd, proc in procs:
+        out, _ = proc.communicate()
+        log.append(f"$ {' '.join(cmd)}\n{out}")
+        if proc.returncode != 0:
+            failed = True
+            sys.stderr.write(f"nvcc failed for {src}:\n{out}\n")
+    (obj_dir / "ptxas.log").write_text("\n".join(log))
+    if failed:
+        raise RuntimeError("flexs_b200: nvcc compilation failed (see stderr)")
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
+            "-cudart", "static", "-o", str(LIB_PATH), *objs]
+    res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout)
+        raise RuntimeError("flexs_b200: link failed")
+    if verbose:
+        print("\n".join(log))
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

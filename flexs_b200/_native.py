@@ -1,0 +1,236 @@
+"""ctypes binding of ``libflexs_b200.so`` (the C ABI declared in include/flexs_b200.h).
+
+This is the stub a maintainer of the reference would add next to
+``flexs/baselines/models/keras_model.py``.  There is NO fallback: if the
+shared library is missing, or no CUDA device is present, every compute call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_uint8, c_uint64, c_void_p
+from pathlib import Path
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+_LIB_PATH = Path(__file__).resolve().parent / "libflexs_b200.so"
+_lib: Optional[ctypes.CDLL] = None
+
+OK, EINVAL, ECUDA, EALPHABET = 0, -1, -2, -3
+VARIANT_AUTO, VARIANT_SIMPLE, VARIANT_TILED, VARIANT_UMMA = 0, 1, 2, 3
+VARIANT_NAMES = {0: "auto", 1: "simple", 2: "tiled_ffma", 3: "umma_tcgen05"}
+
+#: every symbol include/flexs_b200.h declares: (name, restype, argtypes)
+_SIGNATURES = [
+    ("flexs_abi_version", c_int, []),
+    ("flexs_last_error", c_char_p, []),
+    ("flexs_device_count", c_int, []),
+    ("flexs_cnn_create", c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_void_p)]),
+    ("flexs_mlp_create", c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_void_p)]),
+    ("flexs_model_destroy", None, [c_void_p]),
+    ("flexs_model_num_arrays", c_int, [c_void_p]),
+    ("flexs_model_array_size", c_int64, [c_void_p, c_int]),
+    ("flexs_model_set_weights", c_int, [c_void_p, c_int, POINTER(c_void_p)]),
+    ("flexs_model_get_weights", c_int, [c_void_p, c_int, POINTER(c_void_p)]),
+    ("flexs_model_set_variant", c_int, [c_void_p, c_int]),
+    ("flexs_model_active_variant", c_int, [c_void_p, c_int64]),
+    ("flexs_model_launch_count", c_int64, [c_void_p]),
+    ("flexs_encode_dev", c_int, [c_void_p, c_int64, c_char_p, c_int, c_void_p, c_void_p, c_void_p]),
+    ("flexs_model_forward_dev", c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    ("flexs_model_score_host", c_int, [c_void_p, c_void_p, c_int64, c_char_p, c_void_p, POINTER(c_int64)]),
+    ("flexs_topk_workspace_bytes", c_int64, [c_int64, c_int]),
+    ("flexs_topk_dev", c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    ("flexs_mutate_dev", c_int, [c_void_p, c_int64, c_int, c_int, c_float, c_uint64, c_uint64, c_void_p, c_void_p]),
+    ("flexs_argmax_decode_dev", c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
+    ("flexs_model_fit_dev", c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_uint64, c_void_p, c_void_p]),
+    ("flexs_model_train_step_dev", c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, POINTER(c_float), c_void_p]),
+]
+
+EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
+
+
+class NativeError(RuntimeError):
+    """A call into libflexs_b200 failed."""
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    """Load the shared library (once).  Raises loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise NativeError(
+                f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `python flexs_b200/_build.py`).  flexs_b200 has no CPU fallback."
+            )
+        handle = ctypes.CDLL(str(_LIB_PATH), mode=getattr(os, "RTLD_NOW", 2) | getattr(os, "RTLD_LOCAL", 0))
+        for name, restype, argtypes in _SIGNATURES:
+            fn = getattr(handle, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    """Turn a negative return code into the Python exception the reference would raise."""
+    if rc >= 0:
+        return
+    msg = lib().flexs_last_error().decode("utf-8", "replace")
+    if rc == EALPHABET:
+        raise ValueError(msg)  # str.index raises ValueError in the reference (sequence_utils.py:46)
+    if rc == EINVAL:
+        raise ValueError(f"{what}: {msg}" if what else msg)
+    raise NativeError(f"{what}: {msg}" if what else msg)
+
+
+def device_count() -> int:
+    n = lib().flexs_device_count()
+    return max(n, 0)
+
+
+def require_cuda() -> None:
+    n = lib().flexs_device_count()
+    if n <= 0:
+        raise NativeError("flexs_b200 needs a CUDA device (B200, sm_100a); none is visible and there is no CPU fallback")
+
+
+def _as_ptr_array(arrays: Sequence[np.ndarray]):
+    arr_t = c_void_p * len(arrays)
+    return arr_t(*[a.ctypes.data_as(c_void_p).value for a in arrays])
+
+
+class NativeModel:
+    """Owns one ``flexs_model_t*`` (a CNN or MLP surrogate with ``n_members`` weight sets)."""
+
+    def __init__(self, kind: str, *, seq_len: int, alphabet_size: int, hidden_size: int, num_filters: int = 0,
+                 kernel_size: int = 0, n_members: int = 1, device: int = 0):
+        require_cuda()
+        self.kind = kind
+        self.seq_len, self.alphabet_size, self.hidden_size = seq_len, alphabet_size, hidden_size
+        self.num_filters, self.kernel_size, self.n_members, self.device = num_filters, kernel_size, n_members, device
+        handle = c_void_p()
+        if kind == "cnn":
+            rc = lib().flexs_cnn_create(device, seq_len, alphabet_size, num_filters, hidden_size, kernel_size,
+                                        n_members, ctypes.byref(handle))
+        elif kind == "mlp":
+            rc = lib().flexs_mlp_create(device, seq_len, alphabet_size, hidden_size, n_members, ctypes.byref(handle))
+        else:
+            raise ValueError(kind)
+        check(rc, f"create {kind}")
+        self._h = handle
+        self.array_sizes = [int(lib().flexs_model_array_size(self._h, i))
+                            for i in range(lib().flexs_model_num_arrays(self._h))]
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().flexs_model_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover - interpreter shutdown ordering
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- weights -------------------------------------------------------------------------
+    def set_weights(self, weights: Sequence[np.ndarray], member: int = 0) -> None:
+        if len(weights) != len(self.array_sizes):
+            raise ValueError(f"expected {len(self.array_sizes)} arrays, got {len(weights)}")
+        flat = []
+        for w, size in zip(weights, self.array_sizes):
+            a = np.ascontiguousarray(np.asarray(w, dtype=np.float32)).reshape(-1)
+            if a.size != size:
+                raise ValueError(f"weight array has {a.size} elements, expected {size}")
+            flat.append(a)
+        check(lib().flexs_model_set_weights(self._h, member, _as_ptr_array(flat)), "set_weights")
+
+    def get_weights(self, member: int = 0) -> List[np.ndarray]:
+        flat = [np.empty(size, dtype=np.float32) for size in self.array_sizes]
+        check(lib().flexs_model_get_weights(self._h, member, _as_ptr_array(flat)), "get_weights")
+        return flat
+
+    # -- variants / counters ---------------------------------------------------------------
+    def set_variant(self, variant: int) -> None:
+        check(lib().flexs_model_set_variant(self._h, variant), "set_variant")
+
+    def active_variant(self, n: int = 1) -> int:
+        return int(lib().flexs_model_active_variant(self._h, n))
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().flexs_model_launch_count(self._h))
+
+    # -- forward ---------------------------------------------------------------------------
+    def forward_dev(self, d_idx: int, n: int, d_out: int, stream: int = 0) -> None:
+        """Enqueue scoring of ``uint8[n, L]`` at device address ``d_idx`` into ``float32[n]`` at ``d_out``."""
+        check(lib().flexs_model_forward_dev(self._h, c_void_p(d_idx), n, c_void_p(d_out), c_void_p(stream)), "forward")
+
+    def score_host(self, chars: np.ndarray, alphabet: str, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """``chars``: contiguous ``uint8[n, L]`` of residue CHARACTERS in host memory -> ``float32[n]``."""
+        if chars.dtype != np.uint8 or not chars.flags.c_contiguous:
+            raise ValueError("chars must be a C-contiguous uint8 array")
+        n = chars.shape[0] if chars.ndim == 2 else chars.size // max(self.seq_len, 1)
+        if chars.size != n * self.seq_len:
+            raise ValueError(f"expected sequences of length {self.seq_len}")
+        if out is None:
+            out = np.empty(n, dtype=np.float32)
+        bad = c_int64(-1)
+        alpha = alphabet if isinstance(alphabet, bytes) else alphabet.encode("latin-1")
+        rc = lib().flexs_model_score_host(self._h, chars.ctypes.data_as(c_void_p), n, alpha,
+                                          out.ctypes.data_as(c_void_p), ctypes.byref(bad))
+        if rc == EALPHABET:
+            pos = bad.value
+            raise ValueError(f"substring not found: character {chr(int(chars.reshape(-1)[pos]))!r} of sequence "
+                             f"{pos // self.seq_len} (position {pos % self.seq_len}) is not in alphabet {alphabet!r}")
+        check(rc, "score_host")
+        return out
+
+    # -- training --------------------------------------------------------------------------
+    def fit_dev(self, d_idx: int, d_labels: int, n: int, batch_size: int, epochs: int, seed: int,
+                stream: int = 0) -> np.ndarray:
+        losses = np.zeros(max(epochs, 1) * self.n_members, dtype=np.float32)
+        check(lib().flexs_model_fit_dev(self._h, c_void_p(d_idx), c_void_p(d_labels), n, batch_size, epochs,
+                                        c_uint64(seed), losses.ctypes.data_as(c_void_p), c_void_p(stream)), "fit")
+        return losses
+
+    def train_step_dev(self, member: int, d_idx: int, d_labels: int, n: int, d_mask: int = 0, stream: int = 0) -> float:
+        loss = c_float(0.0)
+        check(lib().flexs_model_train_step_dev(self._h, member, c_void_p(d_idx), c_void_p(d_labels), n,
+                                               c_void_p(d_mask), ctypes.byref(loss), c_void_p(stream)), "train_step")
+        return float(loss.value)
+
+
+# -- stateless kernels ------------------------------------------------------------------------
+def encode_dev(d_chars: int, n_bytes: int, alphabet: str, d_idx: int, d_status: int, stream: int = 0) -> None:
+    check(lib().flexs_encode_dev(c_void_p(d_chars), n_bytes, alphabet.encode("latin-1"), len(alphabet),
+                                 c_void_p(d_idx), c_void_p(d_status), c_void_p(stream)), "encode")
+
+
+def topk_workspace_bytes(n: int, k: int) -> int:
+    b = int(lib().flexs_topk_workspace_bytes(n, k))
+    if b < 0:
+        raise ValueError("k must be in [1, 4096]")
+    return b
+
+
+def topk_dev(d_scores: int, n: int, k: int, index_offset: int, d_index_map: int, d_top_scores: int, d_top_idx: int,
+             d_work: int, stream: int = 0) -> None:
+    check(lib().flexs_topk_dev(c_void_p(d_scores), n, k, index_offset, c_void_p(d_index_map), c_void_p(d_top_scores),
+                               c_void_p(d_top_idx), c_void_p(d_work), c_void_p(stream)), "topk")
+
+
+def mutate_dev(d_parents: int, n: int, seq_len: int, alphabet_size: int, mu: float, seed: int, subsequence: int,
+               d_children: int, stream: int = 0) -> None:
+    check(lib().flexs_mutate_dev(c_void_p(d_parents), n, seq_len, alphabet_size, c_float(mu), c_uint64(seed),
+                                 c_uint64(subsequence), c_void_p(d_children), c_void_p(stream)), "mutate")
+
+
+def argmax_decode_dev(d_x: int, n: int, seq_len: int, row_stride: int, alphabet_size: int, d_idx: int,
+                      stream: int = 0) -> None:
+    check(lib().flexs_argmax_decode_dev(c_void_p(d_x), n, seq_len, row_stride, alphabet_size, c_void_p(d_idx),
+                                        c_void_p(stream)), "argmax_decode")

@@ -1,0 +1,2 @@
+"""Explorers on the virtual-screen hot path (reference: flexs/baselines/explorers/)."""
+from flexs_b200.baselines.explorers.adalead import Adalead  # noqa: F401

@@ -1,0 +1,309 @@
+// C ABI of flexs_b200 (include/flexs_b200.h): model objects, weight I/O, dispatch and the
+// host-buffer scoring call.  No CPU compute path exists in this file or behind it.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+
+#include "common.cuh"
+
+namespace fx {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string &msg) { g_last_error = msg; }
+
+int cuda_fail(cudaError_t e, const char *what) {
+    g_last_error = std::string("CUDA error ") + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) +
+                   ") in " + what;
+    cudaGetLastError();  // clear sticky-less errors
+    return FLEXS_ECUDA;
+}
+
+CnnDims cnn_dims(const flexs_model *m) {
+    CnnDims d;
+    d.L = m->L; d.A = m->A; d.F = m->F; d.H = m->H; d.K = m->K; d.K3 = m->K3;
+    d.T = m->L - m->K + 1;
+    d.pl2 = (m->K - 1) / 2;  d.pr2 = (m->K - 1) - d.pl2;
+    d.pl3 = (m->K3 - 1) / 2; d.pr3 = (m->K3 - 1) - d.pl3;
+    return d;
+}
+
+CnnOffsets cnn_offsets(const flexs_model *m) {
+    CnnOffsets o;
+    const std::vector<int64_t> &p = m->arr_offs;
+    o.w1 = p[0]; o.b1 = p[1]; o.w2 = p[2]; o.b2 = p[3]; o.w3 = p[4]; o.b3 = p[5];
+    o.wd1 = p[6]; o.bd1 = p[7]; o.wd2 = p[8]; o.bd2 = p[9]; o.wd3 = p[10]; o.bd3 = p[11];
+    o.total = m->member_floats;
+    return o;
+}
+
+MlpOffsets mlp_offsets(const flexs_model *m) {
+    MlpOffsets o;
+    const std::vector<int64_t> &p = m->arr_offs;
+    o.w1 = p[0]; o.b1 = p[1]; o.w2 = p[2]; o.b2 = p[3]; o.w3 = p[4]; o.b3 = p[5];
+    o.w4 = p[6]; o.b4 = p[7];
+    o.total = m->member_floats;
+    return o;
+}
+
+static int finish_create(flexs_model *m) {
+    int64_t off = 0;
+    m->arr_offs.clear();
+    for (int64_t s : m->arr_sizes) {
+        m->arr_offs.push_back(off);
+        off += (s + 3) / 4 * 4;  // keep every array 16-byte aligned inside the block
+    }
+    m->member_floats = off;
+    int ndev = 0;
+    FX_CUDA(cudaGetDeviceCount(&ndev));
+    FX_REQUIRE(m->device >= 0 && m->device < ndev, "device index out of range");
+    FX_CUDA(cudaSetDevice(m->device));
+    FX_CUDA(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, m->device));
+    FX_CUDA(cudaDeviceGetAttribute(&m->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin,
+                                   m->device));
+    size_t bytes = sizeof(float) * m->member_floats * m->M;
+    FX_CUDA(cudaMalloc(&m->d_weights, bytes));
+    FX_CUDA(cudaMemset(m->d_weights, 0, bytes));
+    m->adam_step.assign(m->M, 0);
+    return FLEXS_OK;
+}
+
+}  // namespace fx
+
+using namespace fx;
+
+extern "C" {
+
+int flexs_abi_version(void) { return FLEXS_B200_ABI_VERSION; }
+
+const char *flexs_last_error(void) { return g_last_error.c_str(); }
+
+int flexs_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+    return n;
+}
+
+int flexs_cnn_create(int device, int seq_len, int alphabet_size, int num_filters, int hidden_size,
+                     int kernel_size, int n_members, flexs_model_t **out) {
+    FX_REQUIRE(out != nullptr, "out is null");
+    *out = nullptr;
+    FX_REQUIRE(alphabet_size >= 2 && alphabet_size <= 255, "alphabet_size must be in [2,255]");
+    FX_REQUIRE(kernel_size >= 1 && seq_len >= kernel_size,
+               "seq_len must be >= kernel_size (valid conv, cnn.py:25-32)");
+    FX_REQUIRE(num_filters >= 1 && hidden_size >= 1 && n_members >= 1, "bad sizes");
+    flexs_model *m = new flexs_model();
+    m->kind = FLEXS_KIND_CNN; m->device = device;
+    m->L = seq_len; m->A = alphabet_size; m->F = num_filters; m->H = hidden_size;
+    m->K = kernel_size; m->K3 = alphabet_size - 1; m->M = n_members;
+    const int64_t k = m->K, a = m->A, f = m->F, h = m->H, k3 = m->K3;
+    m->arr_sizes = {k * a * f, f, k * f * f, f, k3 * f * f, f, f * h, h, h * h, h, h, 1};
+    int rc = finish_create(m);
+    if (rc != FLEXS_OK) { flexs_model_destroy(m); return rc; }
+    *out = m;
+    return FLEXS_OK;
+}
+
+int flexs_mlp_create(int device, int seq_len, int alphabet_size, int hidden_size, int n_members,
+                     flexs_model_t **out) {
+    FX_REQUIRE(out != nullptr, "out is null");
+    *out = nullptr;
+    FX_REQUIRE(alphabet_size >= 2 && alphabet_size <= 255, "alphabet_size must be in [2,255]");
+    FX_REQUIRE(seq_len >= 1 && hidden_size >= 1 && n_members >= 1, "bad sizes");
+    flexs_model *m = new flexs_model();
+    m->kind = FLEXS_KIND_MLP; m->device = device;
+    m->L = seq_len; m->A = alphabet_size; m->H = hidden_size; m->M = n_members;
+    const int64_t d = (int64_t)m->L * m->A, h = m->H;
+    m->arr_sizes = {d * h, h, h * h, h, h * h, h, h, 1};
+    int rc = finish_create(m);
+    if (rc != FLEXS_OK) { flexs_model_destroy(m); return rc; }
+    *out = m;
+    return FLEXS_OK;
+}
+
+void flexs_model_destroy(flexs_model_t *m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaFree(m->d_weights);
+    cudaFree(m->d_umma_w);
+    cudaFree(m->d_adam_m);
+    cudaFree(m->d_adam_v);
+    cudaFree(m->train_ws);
+    for (int i = 0; i < 2; ++i) {
+        if (m->streams[i]) cudaStreamDestroy(m->streams[i]);
+        if (m->slot_done[i]) cudaEventDestroy(m->slot_done[i]);
+        cudaFreeHost(m->h_pin_chars[i]);
+        cudaFreeHost(m->h_pin_out[i]);
+        cudaFree(m->d_chars[i]);
+        cudaFree(m->d_idx[i]);
+        cudaFree(m->d_out[i]);
+    }
+    cudaFree(m->d_status);
+    cudaFreeHost(m->h_status);
+    delete m;
+}
+
+int flexs_model_num_arrays(const flexs_model_t *m) { return m ? (int)m->arr_sizes.size() : FLEXS_EINVAL; }
+
+int64_t flexs_model_array_size(const flexs_model_t *m, int i) {
+    if (!m || i < 0 || i >= (int)m->arr_sizes.size()) return FLEXS_EINVAL;
+    return m->arr_sizes[i];
+}
+
+int flexs_model_set_weights(flexs_model_t *m, int member, const float *const *h_arrays) {
+    FX_REQUIRE(m && h_arrays, "null argument");
+    FX_REQUIRE(member >= 0 && member < m->M, "member out of range");
+    FX_CUDA(cudaSetDevice(m->device));
+    float *base = m->d_weights + (int64_t)member * m->member_floats;
+    for (size_t i = 0; i < m->arr_sizes.size(); ++i) {
+        FX_REQUIRE(h_arrays[i] != nullptr, "null weight array");
+        FX_CUDA(cudaMemcpy(base + m->arr_offs[i], h_arrays[i], sizeof(float) * m->arr_sizes[i],
+                           cudaMemcpyHostToDevice));
+    }
+    m->umma_ready = false;
+    return FLEXS_OK;
+}
+
+int flexs_model_get_weights(flexs_model_t *m, int member, float *const *h_arrays) {
+    FX_REQUIRE(m && h_arrays, "null argument");
+    FX_REQUIRE(member >= 0 && member < m->M, "member out of range");
+    FX_CUDA(cudaSetDevice(m->device));
+    const float *base = m->d_weights + (int64_t)member * m->member_floats;
+    for (size_t i = 0; i < m->arr_sizes.size(); ++i) {
+        FX_REQUIRE(h_arrays[i] != nullptr, "null weight array");
+        FX_CUDA(cudaMemcpy(h_arrays[i], base + m->arr_offs[i], sizeof(float) * m->arr_sizes[i],
+                           cudaMemcpyDeviceToHost));
+    }
+    return FLEXS_OK;
+}
+
+int flexs_model_set_variant(flexs_model_t *m, int variant) {
+    FX_REQUIRE(m, "null model");
+    FX_REQUIRE(variant >= FLEXS_VARIANT_AUTO && variant <= FLEXS_VARIANT_UMMA, "unknown variant");
+    if (m->kind == FLEXS_KIND_CNN) {
+        if (variant == FLEXS_VARIANT_TILED) FX_REQUIRE(cnn_tiled_supported(m), "TILED variant needs F=32, k=5, A in {4,20}");
+        if (variant == FLEXS_VARIANT_UMMA) FX_REQUIRE(cnn_umma_supported(m), "UMMA variant not available for this shape");
+    } else {
+        FX_REQUIRE(variant == FLEXS_VARIANT_AUTO, "MLP has a single kernel");
+    }
+    m->variant = variant;
+    return FLEXS_OK;
+}
+
+int flexs_model_active_variant(const flexs_model_t *m, int64_t n) {
+    if (!m) return FLEXS_EINVAL;
+    (void)n;
+    if (m->kind != FLEXS_KIND_CNN) return FLEXS_VARIANT_AUTO;
+    if (m->variant != FLEXS_VARIANT_AUTO) return m->variant;
+    if (cnn_umma_supported(m)) return FLEXS_VARIANT_UMMA;
+    if (cnn_tiled_supported(m)) return FLEXS_VARIANT_TILED;
+    return FLEXS_VARIANT_SIMPLE;
+}
+
+int64_t flexs_model_launch_count(const flexs_model_t *m) { return m ? m->launches : FLEXS_EINVAL; }
+
+int flexs_encode_dev(const uint8_t *d_chars, int64_t n_bytes, const char *alphabet,
+                     int alphabet_size, uint8_t *d_idx, int64_t *d_status, void *stream) {
+    FX_REQUIRE(alphabet && alphabet_size >= 1 && alphabet_size <= 255, "bad alphabet");
+    FX_REQUIRE(n_bytes >= 0, "negative size");
+    FX_REQUIRE(d_status != nullptr, "d_status is null");
+    FX_REQUIRE(n_bytes == 0 || (d_chars && d_idx), "null buffer");
+    return launch_encode(d_chars, n_bytes, alphabet, alphabet_size, d_idx, d_status,
+                         (cudaStream_t)stream);
+}
+
+int flexs_model_forward_dev(flexs_model_t *m, const uint8_t *d_idx, int64_t n, float *d_out,
+                            void *stream) {
+    FX_REQUIRE(m, "null model");
+    FX_REQUIRE(n >= 0, "negative n");
+    if (n == 0) return FLEXS_OK;
+    FX_REQUIRE(d_idx && d_out, "null buffer");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (m->kind == FLEXS_KIND_MLP) return launch_mlp(m, d_idx, n, d_out, s);
+    switch (flexs_model_active_variant(m, n)) {
+        case FLEXS_VARIANT_UMMA: return launch_cnn_umma(m, d_idx, n, d_out, s);
+        case FLEXS_VARIANT_TILED: return launch_cnn_tiled(m, d_idx, n, d_out, s);
+        default: return launch_cnn_simple(m, d_idx, n, d_out, s);
+    }
+}
+
+// Host-buffer scoring: chunk the batch, and for each chunk H2D(chars) -> encode -> forward ->
+// D2H(scores), alternating between two slots/streams so copies overlap compute.
+static int ensure_host_staging(flexs_model *m) {
+    if (m->streams[0]) return FLEXS_OK;
+    // chunk sized so a slot's chars are ~8 MiB: large enough to amortise launches, small
+    // enough that the first copy does not serialise the pipeline.
+    int64_t chunk = (8ll << 20) / std::max(1, m->L);
+    chunk = std::max<int64_t>(1024, std::min<int64_t>(chunk, 1 << 20));
+    m->host_chunk = chunk;
+    for (int i = 0; i < 2; ++i) {
+        FX_CUDA(cudaStreamCreateWithFlags(&m->streams[i], cudaStreamNonBlocking));
+        FX_CUDA(cudaEventCreateWithFlags(&m->slot_done[i], cudaEventDisableTiming));
+        FX_CUDA(cudaMallocHost(&m->h_pin_chars[i], chunk * m->L));
+        FX_CUDA(cudaMallocHost(&m->h_pin_out[i], chunk * sizeof(float)));
+        FX_CUDA(cudaMalloc(&m->d_chars[i], chunk * m->L + 16));
+        FX_CUDA(cudaMalloc(&m->d_idx[i], chunk * m->L + 16));
+        FX_CUDA(cudaMalloc(&m->d_out[i], chunk * sizeof(float)));
+    }
+    FX_CUDA(cudaMalloc(&m->d_status, 4 * sizeof(int64_t)));
+    FX_CUDA(cudaMallocHost(&m->h_status, 4 * sizeof(int64_t)));
+    return FLEXS_OK;
+}
+
+int flexs_model_score_host(flexs_model_t *m, const char *h_chars, int64_t n, const char *alphabet,
+                           float *h_out, int64_t *bad_pos) {
+    FX_REQUIRE(m && alphabet, "null argument");
+    FX_REQUIRE(n >= 0, "negative n");
+    if (bad_pos) *bad_pos = -1;
+    if (n == 0) return FLEXS_OK;
+    FX_REQUIRE(h_chars && h_out, "null buffer");
+    FX_CUDA(cudaSetDevice(m->device));
+    int rc = ensure_host_staging(m);
+    if (rc != FLEXS_OK) return rc;
+    const int64_t chunk = m->host_chunk, L = m->L;
+    const int64_t nchunks = (n + chunk - 1) / chunk;
+    int64_t first_bad = std::numeric_limits<int64_t>::max();
+    // slot bookkeeping: what is in flight in each slot
+    int64_t inflight_start[2] = {-1, -1}, inflight_cnt[2] = {0, 0};
+    auto drain = [&](int slot) -> int {
+        if (inflight_start[slot] < 0) return FLEXS_OK;
+        FX_CUDA(cudaEventSynchronize(m->slot_done[slot]));
+        const int64_t *st = m->h_status + 2 * slot;
+        if (st[0] != 0) first_bad = std::min(first_bad, inflight_start[slot] * L + st[1]);
+        std::memcpy(h_out + inflight_start[slot], m->h_pin_out[slot], inflight_cnt[slot] * sizeof(float));
+        inflight_start[slot] = -1;
+        return FLEXS_OK;
+    };
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int slot = (int)(c & 1);
+        rc = drain(slot);
+        if (rc != FLEXS_OK) return rc;
+        const int64_t start = c * chunk, cnt = std::min(chunk, n - start);
+        cudaStream_t s = m->streams[slot];
+        std::memcpy(m->h_pin_chars[slot], h_chars + start * L, cnt * L);
+        FX_CUDA(cudaMemcpyAsync(m->d_chars[slot], m->h_pin_chars[slot], cnt * L, cudaMemcpyHostToDevice, s));
+        rc = launch_encode(m->d_chars[slot], cnt * L, alphabet, m->A, m->d_idx[slot], m->d_status + 2 * slot, s);
+        if (rc != FLEXS_OK) return rc;
+        m->launches += 1;
+        rc = flexs_model_forward_dev(m, m->d_idx[slot], cnt, m->d_out[slot], s);
+        if (rc != FLEXS_OK) return rc;
+        FX_CUDA(cudaMemcpyAsync(m->h_pin_out[slot], m->d_out[slot], cnt * sizeof(float), cudaMemcpyDeviceToHost, s));
+        FX_CUDA(cudaMemcpyAsync(m->h_status + 2 * slot, m->d_status + 2 * slot, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        FX_CUDA(cudaEventRecord(m->slot_done[slot], s));
+        inflight_start[slot] = start; inflight_cnt[slot] = cnt;
+    }
+    for (int slot = 0; slot < 2; ++slot) {
+        rc = drain(slot);
+        if (rc != FLEXS_OK) return rc;
+    }
+    if (first_bad != std::numeric_limits<int64_t>::max()) {
+        if (bad_pos) *bad_pos = first_bad;
+        set_error("character outside the alphabet at flat position " + std::to_string(first_bad));
+        return FLEXS_EALPHABET;
+    }
+    return FLEXS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,153 @@
+// Shared declarations for the flexs_b200 native library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/flexs_b200.h"
+
+namespace fx {
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what);
+
+#define FX_CUDA(call)                                            \
+    do {                                                         \
+        cudaError_t e__ = (call);                                \
+        if (e__ != cudaSuccess) return fx::cuda_fail(e__, #call); \
+    } while (0)
+
+#define FX_REQUIRE(cond, msg)           \
+    do {                                \
+        if (!(cond)) {                  \
+            fx::set_error(msg);         \
+            return FLEXS_EINVAL;        \
+        }                               \
+    } while (0)
+
+// Geometry of one CNN member (cnn.py:23-54) in the notation of DESIGN.md.
+struct CnnDims {
+    int L, A, F, H, K, K3, T;
+    int pl2, pr2, pl3, pr3;  // "same" padding of conv2 / conv3 (TF rule: left=(k-1)/2)
+};
+
+// Offsets (in floats) of the 12 Keras arrays inside one member's weight block.
+struct CnnOffsets {
+    int64_t w1, b1, w2, b2, w3, b3, wd1, bd1, wd2, bd2, wd3, bd3, total;
+};
+
+struct MlpOffsets {
+    int64_t w1, b1, w2, b2, w3, b3, w4, b4, total;
+};
+
+}  // namespace fx
+
+// Opaque model object behind the C ABI.
+struct flexs_model {
+    int kind = 0, device = 0;
+    int L = 0, A = 0, F = 0, H = 0, K = 0, K3 = 0, M = 1;
+    int variant = FLEXS_VARIANT_AUTO;
+    int sm_count = 148;
+    int max_smem_optin = 0;
+    int64_t launches = 0;
+
+    std::vector<int64_t> arr_sizes;  // per-member array element counts, Keras order
+    std::vector<int64_t> arr_offs;   // prefix offsets (floats) inside a member block
+    int64_t member_floats = 0;
+    float *d_weights = nullptr;      // [M][member_floats], Keras layout, fp32
+
+    // derived operand layouts (rebuilt by set_weights when a variant needs them)
+    void *d_umma_w = nullptr;        // bf16 hi/lo canonical-layout conv weights, all members
+    bool umma_ready = false;
+
+    // Adam state for K4 (same layout as d_weights) and the 1-based step counter per member
+    float *d_adam_m = nullptr, *d_adam_v = nullptr;
+    std::vector<int64_t> adam_step;
+    void *train_ws = nullptr;        // training workspace (activations + grads)
+    int64_t train_ws_bytes = 0;
+
+    // score_host staging: two slots of pinned host + device buffers and two streams
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    cudaEvent_t slot_done[2] = {nullptr, nullptr};
+    uint8_t *h_pin_chars[2] = {nullptr, nullptr};
+    float *h_pin_out[2] = {nullptr, nullptr};
+    uint8_t *d_chars[2] = {nullptr, nullptr};
+    uint8_t *d_idx[2] = {nullptr, nullptr};
+    float *d_out[2] = {nullptr, nullptr};
+    int64_t *d_status = nullptr;     // [2 slots][2]
+    int64_t *h_status = nullptr;     // pinned mirror
+    int64_t host_chunk = 0;          // sequences per staging slot
+};
+
+namespace fx {
+
+CnnDims cnn_dims(const flexs_model *m);
+CnnOffsets cnn_offsets(const flexs_model *m);
+MlpOffsets mlp_offsets(const flexs_model *m);
+
+// kernels' host launchers (each returns a FLEXS_* code and bumps m->launches)
+int launch_encode(const uint8_t *d_chars, int64_t n_bytes, const char *alphabet, int a,
+                  uint8_t *d_idx, int64_t *d_status, cudaStream_t s);
+int launch_cnn_simple(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s);
+int launch_cnn_tiled(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s);
+bool cnn_tiled_supported(const flexs_model *m);
+int launch_cnn_umma(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s);
+bool cnn_umma_supported(const flexs_model *m);
+int prepare_cnn_umma(flexs_model *m);
+int launch_mlp(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s);
+
+}  // namespace fx
+
+// ---- small device helpers shared by the kernels -------------------------------------------
+#ifdef __CUDACC__
+namespace fxd {
+
+// np.nan_to_num on float32 (keras_model.py:77): NaN -> 0, +-inf -> +-FLT_MAX
+__device__ __forceinline__ float nan_to_num(float x) {
+    if (x != x) return 0.f;
+    if (x > 3.4028234663852886e38f) return 3.4028234663852886e38f;
+    if (x < -3.4028234663852886e38f) return -3.4028234663852886e38f;
+    return x;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP) ----------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared bulk copy; dst/src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                         uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+}  // namespace fxd
+#endif

@@ -1,0 +1,169 @@
+/*
+ * flexs_b200 — C ABI of the B200-native virtual-screen hot path of FLEXS.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / numpy / Python types.
+ * The reference is pure Python, so the binding a maintainer adds is a ctypes stub
+ * (INTEGRATION.md shows it); flexs_b200/_native.py is that stub for this repo.
+ *
+ * Every entry point below names the reference interface it replaces (paths relative to
+ * the reference checkout, samsinai/FLEXS @ dd40916).
+ *
+ * Conventions
+ *   - Return value: 0 on success, a negative FLEXS_E* code on failure;
+ *     flexs_last_error() returns a thread-local message for the last failure.
+ *   - "d_" pointers are device pointers on the model's device; "h_" pointers are host
+ *     pointers.  `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *     Device entry points enqueue work on `stream` and return without synchronising.
+ *   - Sequences are residue-index arrays uint8[n, seq_len], row-major: the value is
+ *     alphabet.index(ch) (flexs/utils/sequence_utils.py:44-47).  The float one-hot of the
+ *     reference is never materialised.
+ *   - Weights cross the boundary in Keras get_weights() order and layout, fp32:
+ *       CNN (flexs/baselines/models/cnn.py:23-54), 12 arrays per member:
+ *         W1 (k,A,F) b1 (F) | W2 (k,F,F) b2 | W3 (A-1,F,F) b3 | Wd1 (F,H) bd1 | Wd2 (H,H) bd2 |
+ *         Wd3 (H,1) bd3 (1)
+ *       MLP (flexs/baselines/models/mlp.py:21-31), 8 arrays per member:
+ *         W1 (L*A,H) b1 | W2 (H,H) b2 | W3 (H,H) b3 | W4 (H,1) b4 (1)
+ *   - There is no CPU fallback anywhere behind this header: without a CUDA device every
+ *     compute entry point fails with FLEXS_ECUDA.
+ */
+#ifndef FLEXS_B200_H
+#define FLEXS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLEXS_B200_ABI_VERSION 1
+
+enum {
+    FLEXS_OK = 0,
+    FLEXS_EINVAL = -1,   /* bad argument (shape, null pointer, unsupported size)          */
+    FLEXS_ECUDA = -2,    /* CUDA runtime error (message in flexs_last_error)              */
+    FLEXS_EALPHABET = -3 /* a character outside the alphabet (reference: ValueError)      */
+};
+
+enum { FLEXS_KIND_CNN = 1, FLEXS_KIND_MLP = 2 };
+
+/* Kernel variant selection for flexs_model_set_variant (diagnostics / A-B measurements;
+ * AUTO is what the product uses). */
+enum {
+    FLEXS_VARIANT_AUTO = 0,
+    FLEXS_VARIANT_SIMPLE = 1, /* one CTA per sequence, any shape                          */
+    FLEXS_VARIANT_TILED = 2,  /* register-tiled FP32 FFMA, F == 32                        */
+    FLEXS_VARIANT_UMMA = 3    /* tcgen05 (3x bf16 split) convs, F == 32                   */
+};
+
+typedef struct flexs_model flexs_model_t;
+
+int flexs_abi_version(void);
+const char *flexs_last_error(void);
+
+/* Number of CUDA devices visible, or a negative error. */
+int flexs_device_count(void);
+
+/* ---- surrogate objects ---------------------------------------------------------------
+ * Replaces the construction of the Keras Sequential in cnn.py:23-54 / mlp.py:21-31.
+ * `n_members` > 1 builds the flexs.Ensemble of identical architectures
+ * (flexs/ensemble.py:21-40) whose default mean (ensemble.py:24) is applied in the
+ * kernel epilogue.  Weights start as zeros; call flexs_model_set_weights.             */
+int flexs_cnn_create(int device, int seq_len, int alphabet_size, int num_filters,
+                     int hidden_size, int kernel_size, int n_members, flexs_model_t **out);
+int flexs_mlp_create(int device, int seq_len, int alphabet_size, int hidden_size,
+                     int n_members, flexs_model_t **out);
+void flexs_model_destroy(flexs_model_t *m);
+
+/* Number of weight arrays per member (12 or 8) and the element count of array `i`.     */
+int flexs_model_num_arrays(const flexs_model_t *m);
+int64_t flexs_model_array_size(const flexs_model_t *m, int i);
+
+/* keras Model.set_weights / get_weights for one member (used by cbas_dbas.py:130-144 style
+ * cloning and by tools/export_keras_golden.py parity checks).  Host pointers, fp32.       */
+int flexs_model_set_weights(flexs_model_t *m, int member, const float *const *h_arrays);
+int flexs_model_get_weights(flexs_model_t *m, int member, float *const *h_arrays);
+
+int flexs_model_set_variant(flexs_model_t *m, int variant);
+/* Variant the next forward of `n` sequences will run (one of FLEXS_VARIANT_*).          */
+int flexs_model_active_variant(const flexs_model_t *m, int64_t n);
+/* Kernel launches issued by this model since creation (bench.py's gpu_launches claim).   */
+int64_t flexs_model_launch_count(const flexs_model_t *m);
+
+/* ---- K0: encode ----------------------------------------------------------------------
+ * Replaces string_to_one_hot (sequence_utils.py:32-47) as called per sequence at
+ * keras_model.py:53-56 and :70-73.  d_chars: n*seq_len raw bytes (one byte per residue
+ * character).  alphabet: `alphabet_size` bytes.  d_idx receives alphabet.index(ch).
+ * d_status (int64[2], device): [0] = number of bytes not in the alphabet, [1] = smallest
+ * flat position of such a byte (INT64_MAX if none).  The caller turns [0] != 0 into the
+ * reference's ValueError.                                                                */
+int flexs_encode_dev(const uint8_t *d_chars, int64_t n_bytes, const char *alphabet,
+                     int alphabet_size, uint8_t *d_idx, int64_t *d_status, void *stream);
+
+/* ---- K1/K2: forward ------------------------------------------------------------------
+ * Replaces KerasModel._fitness_function (keras_model.py:69-79) including squeeze(axis=1)
+ * and np.nan_to_num, and Ensemble._fitness_function's stack+mean (ensemble.py:54-59).
+ * d_idx uint8[n, seq_len] -> d_out float32[n].                                           */
+int flexs_model_forward_dev(flexs_model_t *m, const uint8_t *d_idx, int64_t n, float *d_out,
+                            void *stream);
+
+/* Same call with HOST buffers, the shape Landscape.get_fitness (landscape.py:29-45) has:
+ * h_chars = n*seq_len residue characters, h_out = n scores.  Copies are chunked and
+ * double-buffered over two streams inside the call; returns after h_out is complete.
+ * On FLEXS_EALPHABET *bad_pos (if non-null) is the flat offset of the first bad byte.    */
+int flexs_model_score_host(flexs_model_t *m, const char *h_chars, int64_t n,
+                           const char *alphabet, float *h_out, int64_t *bad_pos);
+
+/* ---- K3: selection -------------------------------------------------------------------
+ * Replaces the final ranking of propose_sequences: np.argsort(preds)[: -B : -1]
+ * (adalead.py:171-175, cbas_dbas.py:197-201, cmaes.py:117-122) and
+ * np.argsort(preds)[::-1][:B] (dyna_ppo.py:315-319).  Returns the k largest scores in
+ * descending order with their indices (+index_offset, for a shard of a larger batch);
+ * ties are broken by the LOWER index first (documented deviation: numpy's introsort
+ * leaves tie order unspecified).  NaN never appears (forward applies nan_to_num).
+ * The reported index of position p is d_index_map[p] when d_index_map is non-NULL (used to
+ * merge the all-gathered per-shard top-k lists of a multi-GPU screen), else p + index_offset.
+ * If n < k the tail is filled with (-inf, -1).  k <= 4096, n < 2^32.
+ * d_work: at least flexs_topk_workspace_bytes(n, k) bytes.                               */
+int64_t flexs_topk_workspace_bytes(int64_t n, int k);
+int flexs_topk_dev(const float *d_scores, int64_t n, int k, int64_t index_offset,
+                   const int64_t *d_index_map, float *d_top_scores, int64_t *d_top_idx,
+                   void *d_work, void *stream);
+
+/* ---- K5: candidate generation helpers -------------------------------------------------
+ * flexs_mutate_dev replaces generate_random_mutant (sequence_utils.py:87-108) applied to
+ * n parents at once: every residue is, with probability mu, replaced by a uniform draw
+ * from the alphabet (which may re-draw the same residue, as the reference does).
+ * RNG is Philox-4x32-10 keyed by (seed, flat position); the reference is unseeded, so
+ * parity is distributional (tests check rates), not bitwise.                            */
+int flexs_mutate_dev(const uint8_t *d_parents, int64_t n, int seq_len, int alphabet_size,
+                     float mu, uint64_t seed, uint64_t subsequence, uint8_t *d_children,
+                     void *stream);
+
+/* flexs_argmax_decode_dev replaces CMAES._soln_to_string (cmaes.py:61-67) and the decode in
+ * environments/dyna_ppo.py:144-147: d_x is [n, seq_len, row_stride] floats of which the
+ * first `alphabet_size` of each row are compared; first maximum wins (np.argmax).         */
+int flexs_argmax_decode_dev(const float *d_x, int64_t n, int seq_len, int row_stride,
+                            int alphabet_size, uint8_t *d_idx, void *stream);
+
+/* ---- K4: training --------------------------------------------------------------------
+ * Replaces keras Model.fit as called at keras_model.py:61-67 with the compile() of
+ * cnn.py:56 / mlp.py:33: MSE loss, Adam(1e-3, 0.9, 0.999, 1e-7), batch_size, epochs,
+ * shuffle every epoch, Dropout(0.25) active for the CNN (cnn.py:51).  Optimiser state
+ * persists in the model across calls, as it does in the reference (explorer.py:157-160).
+ * d_idx uint8[n, seq_len], d_labels float32[n].  h_losses (may be NULL) receives the
+ * mean loss of each epoch.  All members are trained (ensemble.py:42-52).                 */
+int flexs_model_fit_dev(flexs_model_t *m, const uint8_t *d_idx, const float *d_labels,
+                        int64_t n, int batch_size, int epochs, uint64_t seed,
+                        float *h_losses, void *stream);
+
+/* One optimiser step on exactly the given batch with a caller-supplied dropout mask
+ * (float32 [n, H] of 0/1, NULL = no dropout) — the unit the parity tests pin against
+ * oracle.cnn_loss_and_grads + adam_update.  Returns the batch loss in *h_loss.           */
+int flexs_model_train_step_dev(flexs_model_t *m, int member, const uint8_t *d_idx,
+                               const float *d_labels, int64_t n, const float *d_dropout_mask,
+                               float *h_loss, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLEXS_B200_H */
