@@ -1,0 +1,438 @@
+#!/usr/bin/env python
+"""bench.py — virtual-screen throughput of the B200-native FLEXS hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] ...     # the reference's CPU path
+
+Metric (BASELINE.json): sequences scored per second in a virtual screen.  One "step" = one pass of
+the hot path over one synthetic candidate batch per GPU: fused CNN forward (uint8 residue indices in
+HBM -> fp32 scores), per-shard top-k, and — for N > 1 — ONE NCCL all-gather of the per-shard top-k
+lists followed by the final merge on every rank.  Weak scaling: the per-GPU batch is fixed.
+
+Headline workload: the configuration the metric's target is quoted on in BASELINE.json's north_star
+("100-mer x 4-alphabet CNN surrogate"), canonical hyper-parameters F=32, H=100, k=5
+(paper_code/cloud/figure2a_data.py:19-30).  configs[1] (TF-binding 8-mer CNN, 1M candidates) and
+configs[2] (RNA 14-mer, Ensemble(3xCNN)) are measured in the same run and reported under
+"other_workloads".  Data: synthetic (iid uniform residues, fixed seeds), random-init weights.
+
+Output: ONE JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+METRIC = "sequences_scored_per_sec_virtual_screen"
+UNIT = "sequences/s"
+L_NS, A_NS, F_NS, H_NS, K_NS = 100, 4, 32, 100, 5
+PER_GPU_BATCH = 1 << 22          # 4,194,304 candidates per GPU per step (419 MB of uint8 > 126 MB L2)
+TOPK = 99                        # sequences_batch_size=100 -> the [: -B : -1] slice keeps B-1
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}   # B200_PROFILING.md fallback
+
+
+def flop_alg(L, A, F, H, K):
+    """conv1 as gather-add, everything else 2 flop per MAC."""
+    T, K3 = L - K + 1, A - 1
+    return T * F * K + 2 * (T * F * K * F + T * F * K3 * F + F * H + H * H + H)
+
+
+def load_peaks():
+    path = REPO / "MEASURED_PEAKS.json"
+    if path.exists():
+        try:
+            d = json.load(open(path))
+            flat = {}
+
+            def walk(x):
+                if isinstance(x, dict):
+                    for k, v in x.items():
+                        if isinstance(v, (int, float)):
+                            flat.setdefault(k, float(v))
+                        else:
+                            walk(v)
+            walk(d)
+            if "bf16_tflops" in flat and "hbm_gbs" in flat:
+                return {"hbm_gbs": flat["hbm_gbs"], "bf16_tflops": flat["bf16_tflops"],
+                        "bf16_tflops_sustained": flat.get("bf16_tflops_sustained")}, "measured"
+        except Exception:  # noqa: BLE001
+            pass
+    return dict(FALLBACK_PEAKS), "fallback"
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and clock-event reasons of one GPU through NVML during the timed region."""
+
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, torch_index: int):
+        super().__init__(daemon=True)
+        self.samples, self.reason_bits, self.max_mhz = [], 0, None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            import torch
+
+            pynvml.nvmlInit()
+            handle = None
+            try:
+                uuid = str(torch.cuda.get_device_properties(torch_index).uuid)
+                handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:  # noqa: BLE001
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                phys = int(vis.split(",")[torch_index]) if vis and vis.split(",")[torch_index].isdigit() else torch_index
+                handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._nv, self._h = pynvml, handle
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:  # noqa: BLE001
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(self._nv.nvmlDeviceGetClockInfo(self._h, self._nv.NVML_CLOCK_SM)))
+                try:
+                    bits = self._nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:  # noqa: BLE001
+                    bits = self._nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                self.reason_bits |= int(bits)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop_evt.wait(0.05)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        reasons = [name for bit, name in self.REASONS.items() if self.reason_bits & bit]
+        return {"sm_mhz": int(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+def make_weights(shapes, seed):
+    """Keras default init (glorot-uniform kernels, zero biases), numpy default_rng(seed)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for shp in shapes:
+        if len(shp) == 1:
+            out.append(np.zeros(shp, dtype=np.float32))
+        else:
+            rec = int(np.prod(shp[:-2])) if len(shp) > 2 else 1
+            lim = np.sqrt(6.0 / (rec * shp[-2] + rec * shp[-1]))
+            out.append(rng.uniform(-lim, lim, size=shp).astype(np.float32))
+    return out
+
+
+def cnn_shapes(L, A, F, H, K):
+    return [(K, A, F), (F,), (K, F, F), (F,), (A - 1, F, F), (F,), (F, H), (H,), (H, H), (H,), (H, 1), (1,)]
+
+
+class Screen:
+    """One rank's share of the virtual screen: forward + top-k (+ all-gather + merge)."""
+
+    def __init__(self, L, A, F, H, K, members, batch, rank, world, device):
+        import torch
+
+        from flexs_b200 import _native
+
+        self.torch, self.native = torch, _native
+        self.L, self.batch, self.rank, self.world, self.device = L, batch, rank, world, device
+        self.model = _native.NativeModel("cnn", seq_len=L, alphabet_size=A, num_filters=F, hidden_size=H,
+                                         kernel_size=K, n_members=members, device=device.index)
+        for mem in range(members):
+            self.model.set_weights(make_weights(cnn_shapes(L, A, F, H, K), mem), mem)
+        gen = torch.Generator(device=device)
+        gen.manual_seed(1234 + rank)
+        self.idx = torch.randint(0, A, (batch, L), dtype=torch.uint8, device=device, generator=gen)
+        self.scores = torch.empty(batch, dtype=torch.float32, device=device)
+        self.k = TOPK
+        self.ws = torch.empty(_native.topk_workspace_bytes(batch, self.k), dtype=torch.uint8, device=device)
+        self.top_s = torch.empty(self.k, dtype=torch.float32, device=device)
+        self.top_i = torch.empty(self.k, dtype=torch.int64, device=device)
+        if world > 1:
+            self.pack = torch.empty(2 * self.k, dtype=torch.int64, device=device)
+            self.gathered = torch.empty(world * 2 * self.k, dtype=torch.int64, device=device)
+            self.g_scores = torch.empty(world * self.k, dtype=torch.float32, device=device)
+            self.g_idx = torch.empty(world * self.k, dtype=torch.int64, device=device)
+            self.ws2 = torch.empty(_native.topk_workspace_bytes(world * self.k, self.k), dtype=torch.uint8, device=device)
+            self.fin_s = torch.empty(self.k, dtype=torch.float32, device=device)
+            self.fin_i = torch.empty(self.k, dtype=torch.int64, device=device)
+        self.fwd_ms = []
+        self.launches = 0
+
+    def step(self, time_forward=False):
+        torch, nat = self.torch, self.native
+        stream = torch.cuda.current_stream().cuda_stream
+        l0 = self.model.launch_count
+        if time_forward:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        self.model.forward_dev(self.idx.data_ptr(), self.batch, self.scores.data_ptr(), stream)
+        if time_forward:
+            e1.record()
+            self._pending = (e0, e1)
+        nat.topk_dev(self.scores.data_ptr(), self.batch, self.k, self.rank * self.batch, 0, self.top_s.data_ptr(),
+                     self.top_i.data_ptr(), self.ws.data_ptr(), stream)
+        self.launches += (self.model.launch_count - l0) + 11
+        if self.world > 1:
+            import torch.distributed as dist
+
+            self.pack[: self.k] = self.top_i
+            self.pack[self.k:] = self.top_s.view(torch.int32).to(torch.int64)
+            dist.all_gather_into_tensor(self.gathered, self.pack)   # the single collective of the path
+            g = self.gathered.view(self.world, 2, self.k)
+            self.g_idx.copy_(g[:, 0, :].reshape(-1))
+            self.g_scores.copy_(g[:, 1, :].reshape(-1).to(torch.int32).view(torch.float32))
+            nat.topk_dev(self.g_scores.data_ptr(), self.world * self.k, self.k, 0, self.g_idx.data_ptr(),
+                         self.fin_s.data_ptr(), self.fin_i.data_ptr(), self.ws2.data_ptr(), stream)
+            self.launches += 11
+
+    def collect_forward_time(self):
+        e0, e1 = self._pending
+        self.fwd_ms.append(e0.elapsed_time(e1))
+
+
+def timed_steps(screen, steps, warmup, world, device):
+    """W warm-up steps, then exactly K steps between barrier+synchronize, CUDA events, max over ranks."""
+    import torch
+
+    for _ in range(warmup):
+        screen.step()
+    torch.cuda.synchronize(device)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    sampler = ClockSampler(device.index)
+    sampler.start()
+    screen.launches = 0
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    pend = []
+    for _ in range(steps):
+        screen.step(time_forward=True)
+        pend.append(screen._pending)
+    end.record()
+    torch.cuda.synchronize(device)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    clocks = sampler.stop()
+    ms = start.elapsed_time(end)
+    screen.fwd_ms = [a.elapsed_time(b) for a, b in pend]
+    if world > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, clocks
+
+
+def measure_e2e(screen, L, A, steps, world, device):
+    """Same metric through the reference-facing call with HOST buffers: pinned residue characters in,
+    host scores out (flexs_model_score_host = what Model.get_fitness calls), copies inside the timing."""
+    import torch
+
+    alphabet = "TGCA"[:A] if A == 4 else "ILVAGMFYWEDQNHCRKSTP"[:A]
+    table = torch.tensor(list(alphabet.encode()), dtype=torch.uint8)
+    chars = table[screen.idx.cpu().long()].contiguous().pin_memory()
+    out = torch.empty(screen.batch, dtype=torch.float32).pin_memory()
+    chars_np, out_np = chars.numpy(), out.numpy()
+    screen.model.score_host(chars_np[:4096], alphabet)          # allocate staging, warm up
+    screen.model.score_host(chars_np, alphabet, out_np)
+    torch.cuda.synchronize(device)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    l0 = screen.model.launch_count
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        screen.model.score_host(chars_np, alphabet, out_np)
+    dt = time.perf_counter() - t0
+    launches = screen.model.launch_count - l0
+    if world > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([dt], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    # sanity: identical to the device-resident path
+    same = bool(np.array_equal(out_np, screen.scores.cpu().numpy()))
+    return {"value": world * screen.batch * steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(screen.batch * L),
+            "d2h_bytes_per_step": int(screen.batch * 4), "steps": steps, "matches_device_path": same,
+            "api": "flexs_model_score_host (Model.get_fitness)", "gpu_launches": int(launches)}
+
+
+def cpu_baseline(L, A, F, H, K, members=1, seconds_target=12.0):
+    """The oracle's plain-C restatement (OpenMP, all host cores) on a bounded sample of the workload."""
+    from oracle import c_oracle as co
+
+    ws = [make_weights(cnn_shapes(L, A, F, H, K), m) for m in range(members)]
+    rng = np.random.default_rng(99)
+    probe = rng.integers(0, A, size=(2048, L), dtype=np.uint8)
+    co.cnn_forward(probe[:64], ws, K)
+    t0 = time.perf_counter(); co.cnn_forward(probe, ws, K); rate = len(probe) / (time.perf_counter() - t0)
+    n = int(max(4096, min(rate * seconds_target, 2_000_000)))
+    idx = rng.integers(0, A, size=(n, L), dtype=np.uint8)
+    t0 = time.perf_counter(); co.cnn_forward(idx, ws, K); dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{n} synthetic {L}-mers (A={A}) through oracle/c/oracle.c (fp32, OpenMP static schedule), "
+                      f"forward only, {dt:.1f} s"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of get_fitness, restated (TensorFlow is
+    absent): Python-loop float64 one-hot per sequence (sequence_utils.py:32-47), np.array -> fp32
+    tensor (keras_model.py:70-75), predict in batches of 256 (keras_model.py:20,77) through
+    oneDNN-backed torch-CPU conv1d/linear standing in for TF's CPU kernels, squeeze, nan_to_num."""
+    if rank != 0:
+        return
+    from oracle import ref_path
+
+    model = ref_path.ReferenceCNN(L_NS, "TGCA", F_NS, H_NS, K_NS, make_weights(cnn_shapes(L_NS, A_NS, F_NS, H_NS, K_NS), 0))
+    n = 4096
+    rng = np.random.default_rng(1234)
+    seqs = ["".join("TGCA"[i] for i in row) for row in rng.integers(0, 4, size=(n, L_NS))]
+    for _ in range(args.warmup):
+        model.get_fitness(seqs[:512])
+    t0 = time.perf_counter()
+    enc_s = 0.0
+    for _ in range(args.steps):
+        model.get_fitness(seqs)
+        enc_s += model.last_encode_seconds
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "north_star_cnn_100x4", "seq_len": L_NS, "alphabet": 4, "num_filters": F_NS,
+                   "hidden": H_NS, "kernel_size": K_NS, "per_step_sample": n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": model.threads, "kind": "port",
+                         "sample": f"{n} sequences/step through the restated reference get_fitness "
+                                   f"(Python one-hot loop {100 * enc_s / dt:.0f}% of the time, then batch-256 predict on "
+                                   f"{model.threads} torch-CPU threads); TensorFlow itself is not installed"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="candidates per GPU per step")
+    ap.add_argument("--variant", default="auto", choices=["auto", "simple", "tiled", "umma"])
+    ap.add_argument("--skip-extras", action="store_true", help="skip cpu_baseline / e2e / other workloads")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+
+    from flexs_b200 import _native
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: flexs_b200 has no CPU fallback")
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    assert world == max(1, args.gpus) or world == 1, "launch N>1 through torch.distributed.run"
+
+    peaks, peak_src = load_peaks()
+    screen = Screen(L_NS, A_NS, F_NS, H_NS, K_NS, 1, args.batch, rank, world, device)
+    variant = {"auto": 0, "simple": 1, "tiled": 2, "umma": 3}[args.variant]
+    screen.model.set_variant(variant)
+    ms, clocks = timed_steps(screen, args.steps, args.warmup, world, device)
+    total_seqs = world * args.batch * args.steps
+    value = total_seqs / (ms / 1e3)
+    fwd_ms = float(np.mean(screen.fwd_ms))
+    fa = flop_alg(L_NS, A_NS, F_NS, H_NS, K_NS)
+    achieved_tf = fa * args.batch / (fwd_ms / 1e3) / 1e12
+    roofline = {
+        "bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+        "frac": achieved_tf / peaks["bf16_tflops"], "traffic": None, "peak_source": peak_src,
+        "kernel": _native.VARIANT_NAMES[screen.model.active_variant(args.batch)],
+        "kernel_ms": fwd_ms, "kernel_share_of_step": fwd_ms * args.steps / ms,
+        "flop_alg_per_seq": fa, "bytes_alg_per_seq": L_NS + 4,
+        "hbm_gbs_alg": (L_NS + 4) * args.batch / (fwd_ms / 1e3) / 1e9,
+        "hbm_frac": (L_NS + 4) * args.batch / (fwd_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
+        "fp32_ffma_peak_tflops_nominal": 148 * 128 * 2 * 1.965e9 / 1e12,
+        "note": "compute-bound path (1.55e4 flop/B): fraction is of the dense bf16 tensor peak; "
+                "algorithmic flops count each MAC once even when the kernel runs 3 split-bf16 passes",
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "north_star_cnn_100x4", "seq_len": L_NS, "alphabet": A_NS, "num_filters": F_NS,
+                   "hidden": H_NS, "kernel_size": K_NS, "per_gpu_batch": args.batch, "topk": TOPK,
+                   "parallelism": f"candidate-shard x{world}, one all-gather of per-shard top-k" if world > 1 else "single GPU",
+                   "l2_policy": f"inputs larger than L2 ({args.batch * L_NS / 1e6:.0f} MB of uint8 per GPU per step)"},
+        "clocks": clocks, "roofline": roofline, "gpu_launches": int(screen.launches),
+    }
+    if not args.skip_extras:
+        line["e2e"] = measure_e2e(screen, L_NS, A_NS, max(2, min(args.steps, 4)), world, device)
+        if rank == 0 and world == 1:
+            line["cpu_baseline"] = cpu_baseline(L_NS, A_NS, F_NS, H_NS, K_NS)
+        elif rank == 0:
+            line["cpu_baseline"] = None
+        others = {}
+        for tag, (L, A, members, batch) in {"tfbind8_cnn_1M (configs[1])": (8, 4, 1, 1 << 20),
+                                            "rna14_ens3cnn_1M (configs[2])": (14, 4, 3, 1 << 20)}.items():
+            sc = Screen(L, A, F_NS, H_NS, K_NS, members, batch, rank, world, device)
+            sc.model.set_variant(variant)
+            oms, _ = timed_steps(sc, max(3, args.steps), args.warmup, world, device)
+            st = max(3, args.steps)
+            others[tag] = {"value": world * batch * st / (oms / 1e3), "unit": UNIT, "ms_per_step": oms / st,
+                           "kernel_ms": float(np.mean(sc.fwd_ms)), "members": members,
+                           "achieved_tflops": members * flop_alg(L, A, F_NS, H_NS, K_NS) * batch / (np.mean(sc.fwd_ms) / 1e3) / 1e12,
+                           "note": "batch fits in L2 (input re-read from L2 between steps); compute-bound, so unaffected"}
+            del sc
+        line["other_workloads"] = others
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

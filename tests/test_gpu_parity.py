@@ -1,0 +1,423 @@
+"""GPU: parity of the CUDA path (through the C ABI) with the CPU oracle.
+
+Tolerance (north_star: 1e-4 relative): ``|gpu - ref| <= 1e-4 * max(|ref|, FLOOR)``
+with FLOOR = 1e-2 of the batch's score scale, because the final Dense(1) output may be arbitrarily
+close to zero.  Integer work (encode, decode, ranking) is compared bit-exact.
+"""
+import numpy as np
+import pytest
+
+from tests.conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from flexs_b200 import _native  # noqa: E402
+from flexs_b200.utils import sequence_utils as su  # noqa: E402
+from oracle import c_oracle as co  # noqa: E402
+from oracle import flexs_oracle as fo  # noqa: E402
+
+TOL = 1e-4
+
+
+def _floor(ref):
+    return max(1e-2 * float(np.abs(ref).max()), 1e-6)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    if not torch.cuda.is_available():
+        pytest.fail("gpu tests need a CUDA device; the CUDA path has no CPU fallback")
+
+
+def _device_forward(model, idx):
+    d_idx = torch.from_numpy(np.ascontiguousarray(idx)).cuda()
+    out = torch.empty(len(idx), dtype=torch.float32, device="cuda")
+    model.forward_dev(d_idx.data_ptr(), len(idx), out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def _variants(model):
+    vs = [_native.VARIANT_SIMPLE]
+    for v in (_native.VARIANT_TILED, _native.VARIANT_UMMA):
+        try:
+            model.set_variant(v)
+            vs.append(v)
+        except ValueError:
+            pass
+    model.set_variant(_native.VARIANT_AUTO)
+    return vs
+
+
+CNN_SHAPES = {
+    # tag: (L, A, F, H, K, N)
+    "test_shape": (3, 4, 1, 1, 2, 37),      # tests/test_models.py:56-63 of the reference (even k)
+    "tf8": (8, 4, 32, 100, 5, 1000),        # config 2
+    "rna14": (14, 4, 32, 100, 5, 777),      # config 3 member
+    "ns100": (100, 4, 32, 100, 5, 403),     # north-star shape
+    "aav90": (90, 20, 32, 100, 5, 150),     # AAV registry window
+    "gfp237": (237, 20, 32, 100, 5, 41),    # config 5
+    "gfp238": (238, 20, 32, 100, 5, 40),
+    "aav735": (735, 20, 32, 100, 5, 13),    # config 4
+    "minlen": (5, 4, 32, 100, 5, 65),       # L == k: a single conv position
+    "odd": (11, 7, 8, 10, 3, 50),           # generic shape only the simple kernel covers
+}
+
+
+@pytest.mark.parametrize("tag", list(CNN_SHAPES))
+@pytest.mark.parametrize("wname", ["glorot", "trained"])
+def test_cnn_forward_parity_all_variants(tag, wname):
+    L, A, F, H, K, n = CNN_SHAPES[tag]
+    shp = fo.CNNShape(L, A, F, H, K)
+    ws = (fo.glorot_weights if wname == "glorot" else fo.trained_like_weights)(shp.weight_shapes(), 11)
+    idx = np.random.default_rng(5).integers(0, A, size=(n, L), dtype=np.uint8)
+    ref = co.cnn_forward(idx, [ws], K)
+    if L <= 100:
+        ref64 = fo.cnn_forward(idx, ws, np.float64)
+        assert rel_err(ref, ref64, _floor(ref64)) < 2e-5
+        ref = ref64
+    m = _native.NativeModel("cnn", seq_len=L, alphabet_size=A, num_filters=F, hidden_size=H, kernel_size=K)
+    m.set_weights(ws)
+    for v in _variants(m):
+        m.set_variant(v)
+        got = _device_forward(m, idx)
+        assert rel_err(got, ref, _floor(ref)) < TOL, (tag, wname, _native.VARIANT_NAMES[v])
+    m.close()
+
+
+def test_cnn_forward_golden_vectors(golden):
+    g = golden("oracle_forward.npz")
+    for tag in ["test_shape", "tf8", "rna14", "ns100", "aav90", "gfp237", "gfp238", "aav735"]:
+        for wname, fn in (("glorot", fo.glorot_weights), ("trained", fo.trained_like_weights)):
+            L, A, F, H, K, wseed = [int(v) for v in g[f"{tag}_{wname}_cfg"]]
+            ws = fn(fo.CNNShape(L, A, F, H, K).weight_shapes(), wseed)
+            m = _native.NativeModel("cnn", seq_len=L, alphabet_size=A, num_filters=F, hidden_size=H, kernel_size=K)
+            m.set_weights(ws)
+            ref = g[f"{tag}_{wname}_y"]
+            for v in _variants(m):
+                m.set_variant(v)
+                got = _device_forward(m, g[f"{tag}_{wname}_idx"])
+                assert rel_err(got, ref, _floor(ref)) < TOL, (tag, wname, v)
+            m.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 5, 6, 63, 64, 65, 147, 148 * 5 + 3, 4099])
+def test_cnn_batch_sizes_and_tile_boundaries(n):
+    """Ragged batch sizes around the item/tile sizes of the tiled kernels (S=5 for 100-mers)."""
+    L, A = 100, 4
+    shp = fo.CNNShape(L, A, 32, 100, 5)
+    ws = fo.trained_like_weights(shp.weight_shapes(), 3)
+    idx = np.random.default_rng(n).integers(0, A, size=(n, L), dtype=np.uint8)
+    ref = co.cnn_forward(idx, [ws])
+    m = _native.NativeModel("cnn", seq_len=L, alphabet_size=A, num_filters=32, hidden_size=100, kernel_size=5)
+    m.set_weights(ws)
+    for v in _variants(m):
+        if v == _native.VARIANT_SIMPLE and n > 1000:
+            continue
+        m.set_variant(v)
+        assert rel_err(_device_forward(m, idx), ref, _floor(ref)) < TOL, (n, v)
+    m.close()
+
+
+def test_cnn_unaligned_device_pointer_and_empty_batch():
+    """The idx staging copy rounds to 16-byte boundaries itself; any device pointer must work."""
+    L, A, n = 100, 4, 333
+    ws = fo.trained_like_weights(fo.CNNShape(L, A, 32, 100, 5).weight_shapes(), 3)
+    idx = np.random.default_rng(0).integers(0, A, size=(n, L), dtype=np.uint8)
+    ref = co.cnn_forward(idx, [ws])
+    m = _native.NativeModel("cnn", seq_len=L, alphabet_size=A, num_filters=32, hidden_size=100, kernel_size=5)
+    m.set_weights(ws)
+    for off in (1, 7, 13):
+        buf = torch.zeros(n * L + 64, dtype=torch.uint8, device="cuda")
+        buf[off: off + n * L] = torch.from_numpy(idx.reshape(-1)).cuda()
+        out = torch.empty(n, dtype=torch.float32, device="cuda")
+        m.forward_dev(buf.data_ptr() + off, n, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert rel_err(out.cpu().numpy(), ref, _floor(ref)) < TOL
+    m.forward_dev(0, 0, 0, 0)  # n == 0 is a no-op
+    m.close()
+
+
+def test_cnn_full_size_properties():
+    """BASELINE-size batch (1M 8-mers; 2^18 100-mers): size-independent properties instead of a CPU
+    re-computation — permutation equivariance, duplicate rows score identically, a strided sample
+    matches the oracle, and the two kernel variants agree with each other everywhere."""
+    for L, n in ((8, 1 << 20), (100, 1 << 18)):
+        A = 4
+        ws = fo.trained_like_weights(fo.CNNShape(L, A, 32, 100, 5).weight_shapes(), 9)
+        rng = np.random.default_rng(L)
+        idx = rng.integers(0, A, size=(n, L), dtype=np.uint8)
+        idx[1::2] = idx[0::2]  # every odd row duplicates the row before it
+        m = _native.NativeModel("cnn", seq_len=L, alphabet_size=A, num_filters=32, hidden_size=100, kernel_size=5)
+        m.set_weights(ws)
+        base = _device_forward(m, idx)
+        np.testing.assert_array_equal(base[1::2], base[0::2])
+        perm = rng.permutation(n)
+        np.testing.assert_array_equal(_device_forward(m, idx[perm]), base[perm])
+        sample = np.arange(0, n, 997)
+        ref = co.cnn_forward(idx[sample], [ws])
+        assert rel_err(base[sample], ref, _floor(ref)) < TOL
+        vs = _variants(m)
+        if len(vs) > 2:
+            m.set_variant(vs[1])
+            other = _device_forward(m, idx)
+            assert rel_err(other, base, _floor(base)) < TOL
+        m.close()
+
+
+@pytest.mark.parametrize("members", [2, 3])
+def test_ensemble_mean_fused(members):
+    """Ensemble of CNNs in one launch == np.mean over the members' oracle scores (ensemble.py:54-59)."""
+    L, A, n = 14, 4, 500
+    shp = fo.CNNShape(L, A, 32, 100, 5)
+    wss = [fo.trained_like_weights(shp.weight_shapes(), 20 + i) for i in range(members)]
+    idx = np.random.default_rng(1).integers(0, A, size=(n, L), dtype=np.uint8)
+    per_member = [fo.nan_to_num_f32(fo.cnn_forward(idx, ws, np.float64)) for ws in wss]
+    ref = fo.ensemble_mean(per_member)
+    assert ref.dtype == np.float32
+    np.testing.assert_allclose(co.cnn_forward(idx, wss), ref, rtol=0, atol=2e-6)
+    m = _native.NativeModel("cnn", seq_len=L, alphabet_size=A, num_filters=32, hidden_size=100, kernel_size=5,
+                            n_members=members)
+    for i, ws in enumerate(wss):
+        m.set_weights(ws, i)
+    for v in _variants(m):
+        m.set_variant(v)
+        assert rel_err(_device_forward(m, idx), ref, _floor(ref)) < TOL, v
+    # get_weights returns what was set, member by member, in Keras order
+    for i, ws in enumerate(wss):
+        for a, b in zip(m.get_weights(i), ws):
+            np.testing.assert_array_equal(a, b.reshape(-1))
+    m.close()
+
+
+@pytest.mark.parametrize("L,A,H,n", [(8, 4, 100, 1000), (3, 4, 1, 5), (14, 4, 200, 130), (90, 20, 100, 77)])
+def test_mlp_forward_parity(L, A, H, n):
+    ms = fo.MLPShape(L, A, H)
+    ws = fo.trained_like_weights(ms.weight_shapes(), 4)
+    idx = np.random.default_rng(2).integers(0, A, size=(n, L), dtype=np.uint8)
+    ref = fo.mlp_forward(idx, ws, np.float64)
+    m = _native.NativeModel("mlp", seq_len=L, alphabet_size=A, hidden_size=H)
+    m.set_weights(ws)
+    assert rel_err(_device_forward(m, idx), ref, _floor(ref)) < TOL
+    m.close()
+    # ensemble of MLPs
+    ws2 = fo.trained_like_weights(ms.weight_shapes(), 5)
+    m2 = _native.NativeModel("mlp", seq_len=L, alphabet_size=A, hidden_size=H, n_members=2)
+    m2.set_weights(ws, 0); m2.set_weights(ws2, 1)
+    ref2 = fo.ensemble_mean([fo.nan_to_num_f32(ref), fo.nan_to_num_f32(fo.mlp_forward(idx, ws2, np.float64))])
+    assert rel_err(_device_forward(m2, idx), ref2, _floor(ref2)) < TOL
+    m2.close()
+
+
+def test_nan_to_num_epilogue():
+    """keras_model.py:77: NaN -> 0, +-inf -> +-float32 max."""
+    L, A = 8, 4
+    shp = fo.CNNShape(L, A, 32, 100, 5)
+    idx = np.zeros((4, L), dtype=np.uint8)
+    for bias, want in ((np.inf, np.finfo(np.float32).max), (-np.inf, np.finfo(np.float32).min), (np.nan, 0.0)):
+        ws = fo.glorot_weights(shp.weight_shapes(), 0)
+        ws[11] = np.array([bias], dtype=np.float32)
+        m = _native.NativeModel("cnn", seq_len=L, alphabet_size=A, num_filters=32, hidden_size=100, kernel_size=5)
+        m.set_weights(ws)
+        for v in _variants(m):
+            m.set_variant(v)
+            np.testing.assert_array_equal(_device_forward(m, idx), np.full(4, want, dtype=np.float32))
+        m.close()
+
+
+# ------------------------------------------------------------------------------------ encode
+def test_encode_kernel_bit_exact(golden):
+    g = golden("ref_encode_decode.json")
+    for name, case in g["encode"].items():
+        chars = su.sequences_to_char_array(case["seqs"])
+        d_chars = torch.from_numpy(chars).cuda()
+        d_idx = torch.empty_like(d_chars)
+        status = torch.zeros(2, dtype=torch.int64, device="cuda")
+        _native.encode_dev(d_chars.data_ptr(), chars.size, case["alphabet"], d_idx.data_ptr(), status.data_ptr())
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(d_idx.cpu().numpy(), np.array(case["idx"], dtype=np.uint8), err_msg=name)
+        assert status[0].item() == 0
+
+
+def test_encode_kernel_large_unaligned_and_bad_chars():
+    rng = np.random.default_rng(0)
+    alphabet = su.AAS
+    n_bytes = 1_000_003
+    idx = rng.integers(0, 20, size=n_bytes, dtype=np.uint8)
+    chars = np.frombuffer(alphabet.encode(), dtype=np.uint8)[idx].copy()
+    bad_positions = [17, 999_999, 123_456]
+    for p in bad_positions:
+        chars[p] = ord("X")
+    for off in (0, 3):
+        buf = torch.zeros(n_bytes + 32, dtype=torch.uint8, device="cuda")
+        buf[off: off + n_bytes] = torch.from_numpy(chars).cuda()
+        out = torch.zeros(n_bytes + 32, dtype=torch.uint8, device="cuda")
+        status = torch.zeros(2, dtype=torch.int64, device="cuda")
+        _native.encode_dev(buf.data_ptr() + off, n_bytes, alphabet, out.data_ptr() + off, status.data_ptr())
+        torch.cuda.synchronize()
+        got = out[off: off + n_bytes].cpu().numpy()
+        mask = np.ones(n_bytes, dtype=bool); mask[bad_positions] = False
+        np.testing.assert_array_equal(got[mask], idx[mask])
+        assert status.tolist() == [3, 17]
+
+
+def test_score_host_strings_and_value_error():
+    """The reference-facing call: list[str] / ndarray[str] in, float32 ndarray out; a character
+    outside the alphabet raises ValueError like str.index (sequence_utils.py:46)."""
+    import flexs_b200 as flexs
+
+    L = 14
+    cnn = flexs.baselines.models.CNN(L, 32, 100, su.RNAA, seed=3)
+    ws = fo.trained_like_weights(fo.CNNShape(L, 4, 32, 100, 5).weight_shapes(), 2)
+    cnn.set_weights(ws)
+    seqs = su.generate_random_sequences(L, 3000, su.RNAA)
+    ref = fo.get_fitness_cnn(seqs, su.RNAA, ws, np.float64)
+    for container in (seqs, np.array(seqs), su.encode_sequences(seqs, su.RNAA)):
+        got = cnn.get_fitness(container)
+        assert isinstance(got, np.ndarray) and got.dtype == np.float32 and got.shape == (3000,)
+        assert rel_err(got, ref, _floor(ref)) < TOL
+    assert cnn.cost == 9000
+    with pytest.raises(ValueError):
+        cnn.get_fitness(seqs[:5] + ["UGCAUGCAUGCAUX"])
+    with pytest.raises(ValueError):
+        cnn.get_fitness(["UGCA"])  # wrong length
+    assert cnn.get_fitness([]).shape == (0,)
+    for a, b in zip(cnn.get_weights(), ws):
+        np.testing.assert_array_equal(a, b)
+    # device-resident entry used by the explorers
+    d = torch.from_numpy(su.encode_sequences(seqs, su.RNAA)).cuda()
+    got = cnn.get_fitness_device(d).cpu().numpy()
+    assert rel_err(got, ref, _floor(ref)) < TOL
+
+
+def test_score_host_multi_chunk_pipeline():
+    """More sequences than one staging slot holds: chunks alternate between the two streams."""
+    import flexs_b200 as flexs
+
+    L, n = 100, 200_000
+    cnn = flexs.baselines.models.CNN(L, 32, 100, su.DNAA, seed=1)
+    idx = np.random.default_rng(0).integers(0, 4, size=(n, L), dtype=np.uint8)
+    chars = np.frombuffer(su.DNAA.encode(), dtype=np.uint8)[idx]
+    got = cnn.native.score_host(np.ascontiguousarray(chars), su.DNAA)
+    d = torch.from_numpy(idx).cuda()
+    want = cnn._score_device(d).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+    chars = chars.copy(); chars[150_000, 7] = ord("N")
+    with pytest.raises(ValueError, match="150000"):
+        cnn.native.score_host(np.ascontiguousarray(chars), su.DNAA)
+
+
+def test_fused_ensemble_drop_in_and_costs():
+    import flexs_b200 as flexs
+
+    L = 14
+    members = [flexs.baselines.models.CNN(L, 32, 100, su.RNAA, seed=i) for i in range(3)]
+    ens = flexs.Ensemble(members)
+    seqs = su.generate_random_sequences(L, 257, su.RNAA)
+    got = ens.get_fitness(seqs)
+    ref = fo.ensemble_mean([fo.get_fitness_cnn(seqs, su.RNAA, m.get_weights(), np.float64) for m in members])
+    assert got.dtype == np.float32 and rel_err(got, ref, _floor(ref)) < TOL
+    assert ens.cost == 257 and [m.cost for m in members] == [257] * 3
+    # the generic path (custom reducer) gives the same numbers through M separate launches
+    ens2 = flexs.Ensemble(members, combine_with=lambda s: np.mean(s, axis=1))
+    assert rel_err(ens2.get_fitness(seqs), ref, _floor(ref)) < TOL
+    # weights changed on a member -> fused copy refreshes
+    members[1].set_weights(fo.trained_like_weights(fo.CNNShape(L, 4, 32, 100, 5).weight_shapes(), 99))
+    ref = fo.ensemble_mean([fo.get_fitness_cnn(seqs, su.RNAA, m.get_weights(), np.float64) for m in members])
+    assert rel_err(ens.get_fitness(seqs), ref, _floor(ref)) < TOL
+
+
+# ------------------------------------------------------------------------------------ top-k
+def _topk(scores, k, offset=0, index_map=None):
+    d = torch.from_numpy(scores).cuda()
+    ws = torch.empty(_native.topk_workspace_bytes(len(scores), k), dtype=torch.uint8, device="cuda")
+    ts = torch.empty(k, dtype=torch.float32, device="cuda")
+    ti = torch.empty(k, dtype=torch.int64, device="cuda")
+    dm = torch.from_numpy(index_map).cuda() if index_map is not None else None
+    _native.topk_dev(d.data_ptr(), len(scores), k, offset, dm.data_ptr() if dm is not None else 0, ts.data_ptr(),
+                     ti.data_ptr(), ws.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return ts.cpu().numpy(), ti.cpu().numpy()
+
+
+def test_topk_matches_reference_slices(golden):
+    g = golden("ref_topk_slices.json")
+    preds = np.array(g["preds"], dtype=np.float32)
+    for b in (2, 5, 100, 499, 500):
+        ts, ti = _topk(preds, b - 1)      # adalead.py:173: B-1 items
+        np.testing.assert_array_equal(ti, g[f"bm1_{b}"])
+        np.testing.assert_array_equal(ts, preds[g[f"bm1_{b}"]])
+        ts, ti = _topk(preds, b)          # dyna_ppo.py:317: B items
+        np.testing.assert_array_equal(ti, g[f"b_{b}"])
+    ts, ti = _topk(preds, 600)            # k > n: tail is (-inf, -1)
+    np.testing.assert_array_equal(ti[:500], g["b_600"])
+    assert (ti[500:] == -1).all() and np.isneginf(ts[500:]).all()
+
+
+@pytest.mark.parametrize("n,k", [(1, 1), (1000, 1), (4097, 100), (1 << 20, 99), (3_000_001, 1000), (5000, 4096)])
+def test_topk_random_ties_and_scale(n, k):
+    rng = np.random.default_rng(n)
+    # coarse values -> many ties; negative values, zeros and -0.0 included
+    scores = (rng.integers(-50, 50, size=n) / 8.0).astype(np.float32)
+    scores[rng.integers(0, n, size=min(n, 10))] = -0.0
+    ts, ti = _topk(scores, k, offset=1000)
+    keff = min(n, k)
+    order = np.lexsort((np.arange(n), -scores.astype(np.float64)))[:keff]  # score desc, index asc
+    np.testing.assert_array_equal(ti[:keff] - 1000, order)
+    np.testing.assert_array_equal(ts[:keff], scores[order] + 0.0)
+
+
+def test_topk_index_map():
+    scores = np.array([0.5, 2.0, 2.0, -1.0, 7.0], dtype=np.float32)
+    imap = np.array([40, 10, 11, 99, 5], dtype=np.int64)
+    ts, ti = _topk(scores, 3, index_map=imap)
+    np.testing.assert_array_equal(ti, [5, 10, 11])
+    np.testing.assert_array_equal(ts, [7.0, 2.0, 2.0])
+
+
+# ------------------------------------------------------------------------------------ K5
+def test_argmax_decode_bit_exact(golden):
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(300, 14, 5)).round(1).astype(np.float32)  # ties; last column = mask channel
+    d = torch.from_numpy(x).cuda()
+    out = torch.empty((300, 14), dtype=torch.uint8, device="cuda")
+    _native.argmax_decode_dev(d.data_ptr(), 300, 14, 5, 4, out.data_ptr())
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy(), np.argmax(x[:, :, :4], axis=2))
+    for case in golden("ref_encode_decode.json")["decode"]:
+        xx = np.array(case["x"], dtype=np.float32)
+        d = torch.from_numpy(xx).cuda()
+        out = torch.empty(xx.shape[:2], dtype=torch.uint8, device="cuda")
+        _native.argmax_decode_dev(d.data_ptr(), xx.shape[0], xx.shape[1], xx.shape[2], xx.shape[2], out.data_ptr())
+        torch.cuda.synchronize()
+        assert list(su.decode_indices(out.cpu().numpy(), case["alphabet"])) == case["strings"]
+
+
+def test_mutate_rates_and_determinism():
+    """generate_random_mutant semantics (sequence_utils.py:87-108), distributional: each residue is
+    redrawn with probability mu, uniformly over the WHOLE alphabet (so it changes w.p. mu*(A-1)/A)."""
+    n, L, A = 20000, 100, 4
+    parents = np.random.default_rng(0).integers(0, A, size=(n, L), dtype=np.uint8)
+    d = torch.from_numpy(parents).cuda()
+    out = torch.empty_like(d)
+    for mu in (0.0, 1.0 / L, 0.2, 1.0):
+        _native.mutate_dev(d.data_ptr(), n, L, A, mu, 1234, 0, out.data_ptr())
+        torch.cuda.synchronize()
+        child = out.cpu().numpy()
+        assert child.max() < A
+        changed = (child != parents).mean()
+        expect = mu * (A - 1) / A
+        assert abs(changed - expect) < 5 * np.sqrt(max(expect, 1e-9) / (n * L)) + 1e-9, (mu, changed, expect)
+        if mu == 1.0:
+            counts = np.bincount(child.reshape(-1), minlength=A) / child.size
+            assert np.abs(counts - 1 / A).max() < 2e-3
+    out2 = torch.empty_like(d)
+    _native.mutate_dev(d.data_ptr(), n, L, A, 0.2, 1234, 0, out.data_ptr())
+    _native.mutate_dev(d.data_ptr(), n, L, A, 0.2, 1234, 0, out2.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+    _native.mutate_dev(d.data_ptr(), n, L, A, 0.2, 1234, 1, out2.data_ptr())
+    torch.cuda.synchronize()
+    assert not torch.equal(out, out2)
