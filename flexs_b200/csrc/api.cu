@@ -128,6 +128,8 @@ void flexs_model_destroy(flexs_model_t *m) {
     cudaSetDevice(m->device);
     cudaFree(m->d_weights);
     cudaFree(m->d_umma_w);
+    cudaFree(m->d_umma2_w);
+    cudaFree(m->d_flag);
     cudaFree(m->d_adam_m);
     cudaFree(m->d_adam_v);
     cudaFree(m->train_ws);
@@ -163,6 +165,7 @@ int flexs_model_set_weights(flexs_model_t *m, int member, const float *const *h_
                            cudaMemcpyHostToDevice));
     }
     m->umma_ready = false;
+    m->umma2_ready = false;
     return FLEXS_OK;
 }
 

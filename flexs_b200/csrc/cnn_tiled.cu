@@ -18,6 +18,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "dense_head.cuh"
 
 namespace {
 
@@ -31,6 +32,7 @@ struct TiledParams {
     const uint8_t *idx;
     float *out;
     const float *weights;
+    const int *gate;  // optional: run only if *gate != 0
     int64_t n, n_items, member_floats;
     fx::CnnDims d;
     fx::CnnOffsets o;
@@ -41,6 +43,7 @@ struct TiledParams {
     int sbcap;   // feature slots batched for the dense head (multiple of 8)
     int sbp;     // slot pitch of the dense buffers = sbcap + 4
     int idx_slot;  // bytes per idx staging slot
+    int stage;     // dense head stages Wd1/Wd2 in shared memory
 };
 
 struct Smem {
@@ -139,80 +142,10 @@ __device__ __forceinline__ void issue_idx_load(const TiledParams &p, const Smem 
     fxd::bulk_g2s(sm.idx[buf], reinterpret_cast<const void *>(a0), bytes, &sm.mbar[buf]);
 }
 
-// dense head on the batched features: featT[32][sbp] -> out[slot_seq[slot]]
-__device__ void dense_flush(const TiledParams &p, const Smem &sm, const float *__restrict__ w, int nslots,
-                            int mem) {
-    const int tid = threadIdx.x, H = p.d.H, sbp = p.sbp;
-    const int HP = (H + 31) & ~31;
-    const int nsg = (nslots + 7) >> 3;
-    float *d1T = sm.h1;                    // [H][sbp]
-    float *d2T = sm.h1 + (size_t)H * sbp;  // [H][sbp]
-    const float *wd1 = w + p.o.wd1, *bd1 = w + p.o.bd1, *wd2 = w + p.o.wd2, *bd2 = w + p.o.bd2;
-    const float *wd3 = w + p.o.wd3, *bd3 = w + p.o.bd3;
-    __syncthreads();
-    for (int wk = tid; wk < HP * nsg; wk += NT) {
-        const int o = wk % HP, sg = wk / HP;
-        if (o >= H) continue;
-        float acc[8];
-        const float b = __ldg(bd1 + o);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = b;
-#pragma unroll 4
-        for (int g = 0; g < F; ++g) {
-            const float wv = __ldg(wd1 + (size_t)g * H + o);
-            const float4 x0 = *reinterpret_cast<const float4 *>(sm.featT + (size_t)g * sbp + sg * 8);
-            const float4 x1 = *reinterpret_cast<const float4 *>(sm.featT + (size_t)g * sbp + sg * 8 + 4);
-            acc[0] = fmaf(wv, x0.x, acc[0]); acc[1] = fmaf(wv, x0.y, acc[1]);
-            acc[2] = fmaf(wv, x0.z, acc[2]); acc[3] = fmaf(wv, x0.w, acc[3]);
-            acc[4] = fmaf(wv, x1.x, acc[4]); acc[5] = fmaf(wv, x1.y, acc[5]);
-            acc[6] = fmaf(wv, x1.z, acc[6]); acc[7] = fmaf(wv, x1.w, acc[7]);
-        }
-        float4 r0 = make_float4(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
-        float4 r1 = make_float4(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f), fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
-        *reinterpret_cast<float4 *>(d1T + (size_t)o * sbp + sg * 8) = r0;
-        *reinterpret_cast<float4 *>(d1T + (size_t)o * sbp + sg * 8 + 4) = r1;
-    }
-    __syncthreads();
-    for (int wk = tid; wk < HP * nsg; wk += NT) {
-        const int o = wk % HP, sg = wk / HP;
-        if (o >= H) continue;
-        float acc[8];
-        const float b = __ldg(bd2 + o);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = b;
-#pragma unroll 4
-        for (int g = 0; g < H; ++g) {
-            const float wv = __ldg(wd2 + (size_t)g * H + o);
-            const float4 x0 = *reinterpret_cast<const float4 *>(d1T + (size_t)g * sbp + sg * 8);
-            const float4 x1 = *reinterpret_cast<const float4 *>(d1T + (size_t)g * sbp + sg * 8 + 4);
-            acc[0] = fmaf(wv, x0.x, acc[0]); acc[1] = fmaf(wv, x0.y, acc[1]);
-            acc[2] = fmaf(wv, x0.z, acc[2]); acc[3] = fmaf(wv, x0.w, acc[3]);
-            acc[4] = fmaf(wv, x1.x, acc[4]); acc[5] = fmaf(wv, x1.y, acc[5]);
-            acc[6] = fmaf(wv, x1.z, acc[6]); acc[7] = fmaf(wv, x1.w, acc[7]);
-        }
-        float4 r0 = make_float4(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
-        float4 r1 = make_float4(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f), fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
-        *reinterpret_cast<float4 *>(d2T + (size_t)o * sbp + sg * 8) = r0;
-        *reinterpret_cast<float4 *>(d2T + (size_t)o * sbp + sg * 8 + 4) = r1;
-    }
-    __syncthreads();
-    for (int slot = tid; slot < nslots; slot += NT) {
-        float acc = 0.f;
-#pragma unroll 4
-        for (int g = 0; g < H; ++g) acc = fmaf(d2T[(size_t)g * sbp + slot], __ldg(wd3 + g), acc);
-        const float y = fxd::nan_to_num(acc + __ldg(bd3));
-        const long long seq = sm.slot_seq[slot];
-        // Ensemble (ensemble.py:54-59, default mean :24): ((s0 + s1) + s2 ...) / M in fp32
-        float tot = (mem == 0) ? y : p.out[seq] + y;
-        if (p.M > 1 && mem == p.M - 1) tot = tot / (float)p.M;
-        p.out[seq] = tot;
-    }
-    __syncthreads();
-}
-
 template <int K, int K3>
 __global__ void __launch_bounds__(NT, 1) cnn_tiled_kernel(const TiledParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    if (p.gate != nullptr && *p.gate == 0) return;  // uniform across the grid
     const Smem sm = carve(smem_raw, p);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     constexpr int NWARP = NT / 32;
@@ -260,7 +193,9 @@ __global__ void __launch_bounds__(NT, 1) cnn_tiled_kernel(const TiledParams p) {
             const int s_item = (int)min((int64_t)p.S, p.n - first);
             const int rows_item = s_item * P;
             if (nslots + s_item > p.sbcap) {
-                dense_flush(p, sm, w, nslots, mem);
+                fxd::DenseArgs da{w + p.o.wd1, w + p.o.bd1, w + p.o.wd2, w + p.o.bd2, w + p.o.wd3, w + p.o.bd3,
+                                  sm.featT, sm.h1, sm.slot_seq, p.out, F, p.d.H, p.sbp, nslots, mem, p.M, p.stage};
+                fxd::dense_head_flush<NT>(da);
                 nslots = 0;
             }
             for (int i = tid; i < F * s_item; i += NT) sm.featT[(i / s_item) * p.sbp + nslots + (i % s_item)] = 0.f;
@@ -369,7 +304,11 @@ __global__ void __launch_bounds__(NT, 1) cnn_tiled_kernel(const TiledParams p) {
             }
             nslots += s_item;
         }
-        if (nslots > 0) dense_flush(p, sm, w, nslots, mem);
+        if (nslots > 0) {
+            fxd::DenseArgs da{w + p.o.wd1, w + p.o.bd1, w + p.o.wd2, w + p.o.bd2, w + p.o.wd3, w + p.o.bd3,
+                              sm.featT, sm.h1, sm.slot_seq, p.out, F, p.d.H, p.sbp, nslots, mem, p.M, p.stage};
+            fxd::dense_head_flush<NT>(da);
+        }
     }
 }
 
@@ -392,6 +331,7 @@ static bool plan(const flexs_model *m, TiledParams &p) {
         while (sbcap >= 8 && (size_t)2 * p.d.H * (sbcap + 4) > (size_t)2 * F * rcap) sbcap -= 8;
         if (sbcap < 8) continue;
         p.sbcap = sbcap; p.sbp = sbcap + 4;
+        p.stage = fxd::dense_scratch_floats(F, p.d.H, p.sbp, true) <= (size_t)2 * F * rcap ? 1 : 0;
         p.S = std::max(1, std::min(p.rout / p.P, sbcap));
         p.idx_slot = ((p.S * p.d.L + 32) + 15) & ~15;
         if ((int64_t)smem_bytes(p) <= m->max_smem_optin) return true;
@@ -411,9 +351,14 @@ bool cnn_tiled_supported(const flexs_model *m) {
 }
 
 int launch_cnn_tiled(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s) {
+    return launch_cnn_tiled_gated(m, d_idx, n, d_out, nullptr, s);
+}
+
+int launch_cnn_tiled_gated(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, const int *d_gate,
+                           cudaStream_t s) {
     TiledParams p;
     FX_REQUIRE(cnn_tiled_supported(m) && plan(m, p), "shape not supported by the tiled CNN kernel");
-    p.idx = d_idx; p.out = d_out; p.weights = m->d_weights; p.n = n;
+    p.idx = d_idx; p.out = d_out; p.weights = m->d_weights; p.n = n; p.gate = d_gate;
     p.n_items = (n + p.S - 1) / p.S;
     const size_t smem = smem_bytes(p);
     const int grid = (int)std::min<int64_t>(p.n_items, m->sm_count);

@@ -58,8 +58,12 @@ struct flexs_model {
     float *d_weights = nullptr;      // [M][member_floats], Keras layout, fp32
 
     // derived operand layouts (rebuilt by set_weights when a variant needs them)
-    void *d_umma_w = nullptr;        // bf16 hi/lo canonical-layout conv weights, all members
+    void *d_umma_w = nullptr;        // fp16 hi/lo canonical-layout conv weights, all members
     bool umma_ready = false;
+    void *d_umma2_w = nullptr;       // same for cnn_umma2.cu ([hi|lo] fused N=64 planes + gather tables)
+    bool umma2_ready = false;
+    bool umma_weights_ok = true;     // false: non-finite conv weights, use the fp32 kernel
+    int *d_flag = nullptr;           // fp16-overflow flag raised by the UMMA kernel
 
     // Adam state for K4 (same layout as d_weights) and the 1-based step counter per member
     float *d_adam_m = nullptr, *d_adam_v = nullptr;
@@ -91,10 +95,16 @@ int launch_encode(const uint8_t *d_chars, int64_t n_bytes, const char *alphabet,
                   uint8_t *d_idx, int64_t *d_status, cudaStream_t s);
 int launch_cnn_simple(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s);
 int launch_cnn_tiled(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s);
+// same kernel, but every CTA returns immediately unless *d_gate != 0 (fp16-overflow fall-back)
+int launch_cnn_tiled_gated(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, const int *d_gate,
+                           cudaStream_t s);
 bool cnn_tiled_supported(const flexs_model *m);
 int launch_cnn_umma(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s);
 bool cnn_umma_supported(const flexs_model *m);
 int prepare_cnn_umma(flexs_model *m);
+// pipelined tcgen05 kernel for the A = 4 shapes (cnn_umma2.cu)
+bool cnn_umma2_supported(const flexs_model *m);
+int launch_cnn_umma2(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s);
 int launch_mlp(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s);
 
 }  // namespace fx
@@ -131,12 +141,14 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t done;
     do {
+        // the suspend-time hint lets the hardware park the warp instead of spinning through the
+        // issue slots the working warps need (first v2 profile: 19 % of all instructions were spins)
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680)
             : "memory");
     } while (!done);
 }
