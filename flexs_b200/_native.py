@@ -45,6 +45,8 @@ _SIGNATURES = [
     ("flexs_argmax_decode_dev", c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
     ("flexs_model_fit_dev", c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_uint64, c_void_p, c_void_p]),
     ("flexs_model_train_step_dev", c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, POINTER(c_float), c_void_p]),
+    ("flexs_model_get_optimizer_state", c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64)]),
+    ("flexs_model_reset_optimizer", c_int, [c_void_p]),
 ]
 
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
@@ -197,6 +199,18 @@ class NativeModel:
         check(lib().flexs_model_fit_dev(self._h, c_void_p(d_idx), c_void_p(d_labels), n, batch_size, epochs,
                                         c_uint64(seed), losses.ctypes.data_as(c_void_p), c_void_p(stream)), "fit")
         return losses
+
+    def optimizer_state(self, member: int = 0):
+        """(m arrays, v arrays, step) of the Adam optimiser of one member."""
+        ms = [np.empty(size, dtype=np.float32) for size in self.array_sizes]
+        vs = [np.empty(size, dtype=np.float32) for size in self.array_sizes]
+        step = c_int64(0)
+        check(lib().flexs_model_get_optimizer_state(self._h, member, _as_ptr_array(ms), _as_ptr_array(vs),
+                                                    ctypes.byref(step)), "get_optimizer_state")
+        return ms, vs, int(step.value)
+
+    def reset_optimizer(self) -> None:
+        check(lib().flexs_model_reset_optimizer(self._h), "reset_optimizer")
 
     def train_step_dev(self, member: int, d_idx: int, d_labels: int, n: int, d_mask: int = 0, stream: int = 0) -> float:
         loss = c_float(0.0)

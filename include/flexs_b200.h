@@ -163,6 +163,14 @@ int flexs_model_train_step_dev(flexs_model_t *m, int member, const uint8_t *d_id
                                const float *d_labels, int64_t n, const float *d_dropout_mask,
                                float *h_loss, void *stream);
 
+/* Adam moments (m, v; same arrays/layout as the weights; either pointer table may be NULL) and
+ * the 1-based step count of one member — what keras `model.optimizer.get_weights()` exposes; the
+ * parity tests read the gradient of a first step back as m / (1 - beta1).                       */
+int flexs_model_get_optimizer_state(flexs_model_t *m, int member, float *const *h_m, float *const *h_v,
+                                    int64_t *step);
+/* Forget the optimiser state of every member (a freshly compiled Keras model).                  */
+int flexs_model_reset_optimizer(flexs_model_t *m);
+
 #ifdef __cplusplus
 }
 #endif
