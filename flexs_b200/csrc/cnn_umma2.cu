@@ -32,8 +32,12 @@
 
 namespace {
 
-constexpr int F = 32, NT = 512, K = 5, K3 = 3, ALPHA = 4;
-constexpr int NEPI = 8, NPROD = 7;  // warps 0-7, 9-15 (warp 8 = MMA issuer)
+constexpr int F = 32, NT = 544, K = 5, K3 = 3, ALPHA = 4;
+// 17 warps: 0-7 conv2 epilogue (E2) of chunk n-1 then conv1 of chunk n, 8-15 conv3 epilogue (E3), 16 MMA issuer.
+// Measured alternatives (profiles/r01_umma_v2_roles.txt): conv1 on its own 3 warps (14.1k cycles/chunk), conv1
+// shared by all 16 warps (15.0k), conv1 with E3 (13.5k); this split is the fastest (12.3k).  Every generic
+// shared-memory access competes with the tensor core's operand fetch, which is the real limiter.
+constexpr int NEPI = 8, NPROD = 8, PRODW0 = 0, MMAW = 16;
 constexpr int NTILE = 4;
 constexpr int WR1 = K - 1, WR2 = K3 - 1;                      // wrap core matrices
 constexpr int TS1 = (16 + WR1) * 128, TS2 = (16 + WR2) * 128;  // bytes per tile per plane
@@ -58,11 +62,25 @@ struct U2Params {
     int M;
     int P, hl, S;
     int sbcap, sbp, idx_slot, rs_bytes, stage;
+    int dense_umma;  // dense head on the tensor cores (H <= 112)
     long long *prof;
+    int dbg;  // profiling knobs (FLEXS_UMMA_DBG bitmask): 1 skip E3 reduction, 2 skip conv1 math, 4 skip E2 split/stores
 };
 
 constexpr int OFF_UW3 = K * UWTAP, OFF_T012 = OFF_UW3 + K3 * UWTAP, OFF_T34 = OFF_T012 + 64 * F * 4;
-constexpr int OFF_SCAL = OFF_T34 + 16 * F * 4, UW_MEMBER_BYTES = (OFF_SCAL + 16 + 255) / 256 * 256;
+constexpr int OFF_SCAL = OFF_T34 + 16 * F * 4;
+// tensor-core dense head (H <= 112): [128 sequence slots] x [32 -> 112 -> 112] as two UMMA GEMMs with the same
+// fp16 hi/lo split; weights as [k chunk][n: hi 0..111 | lo 112..223][8 k] planes, vectors padded to 112
+constexpr int DH = 112, DN = 2 * DH, DSLOTS = 128, DPLANE = DSLOTS * 16, DBK = DN * 16;
+constexpr int OFF_DB1 = (OFF_SCAL + 16 + 255) / 256 * 256, OFF_DB2 = OFF_DB1 + 4 * DBK, OFF_DV = OFF_DB2 + 14 * DBK;
+constexpr int DV_FLOATS = 3 * DH + 4;  // bd1*ASCALE | bd2 | wd3 | inv_d1s, inv_d2, bd3
+constexpr int UW_MEMBER_BYTES = (OFF_DV + DV_FLOATS * 4 + 255) / 256 * 256;
+// dense scratch inside the (idle) activation buffers
+constexpr int DS_X1 = 0, DS_B1 = DS_X1 + 8 * DPLANE, DS_X2 = DS_B1 + 4 * DBK, DS_B2 = DS_X2 + 28 * DPLANE;
+constexpr int DS_PART = DS_B2 + 14 * DBK, DS_DV = DS_PART + 2 * DSLOTS * 4, DS_TOTAL = DS_DV + (DV_FLOATS * 4 + 15) / 16 * 16;
+constexpr uint32_t IDESC_DN = (1u << 4) | ((uint32_t)(DN >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t IDESC_DH = (1u << 4) | ((uint32_t)(DH >> 3) << 17) | ((128u >> 4) << 24);
+static_assert(DS_TOTAL <= 8 * (PL1 + PL2), "dense scratch must fit the activation buffers");
 
 struct Offs {
     int mbar, tm, b, t012, t34, uw2, uw3, i0, i1, rs, feat, slot, a1, a2;
@@ -132,6 +150,11 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[1
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_NONE shared-memory matrix descriptor (verified on hardware by the v1 kernel):
@@ -155,6 +178,20 @@ __device__ __forceinline__ void issue_conv_tile(uint32_t a_tile_addr, uint32_t w
             umma_f16_elect(d_tmem, a_hi, DESC_HI, bd, DESC_HI, IDESC_N64, (j | kp) ? 1u : 0u);
             umma_f16_elect(d_tmem, a_lo, DESC_HI, bd, DESC_HI, IDESC_N32, 1u);
         }
+    }
+}
+
+// one dense layer: [128 slots, 16*KP] x [16*KP, 112] with X = hi + lo planes (NPL planes per split)
+template <int KP, int NPL>
+__device__ __forceinline__ void issue_dense_layer(uint32_t x_addr, uint32_t b_addr, uint32_t d_tmem) {
+    const uint32_t a0 = desc_lo(x_addr, DPLANE), b0 = desc_lo(b_addr, DBK);
+#pragma unroll
+    for (int kp = 0; kp < KP; ++kp) {
+        const uint32_t a_hi = a0 + (((uint32_t)(2 * kp) * DPLANE) >> 4);
+        const uint32_t a_lo = a_hi + (((uint32_t)NPL * DPLANE) >> 4);
+        const uint32_t bd = b0 + (((uint32_t)(2 * kp) * DBK) >> 4);
+        umma_f16_elect(d_tmem, a_hi, DESC_HI, bd, DESC_HI, IDESC_DN, kp ? 1u : 0u);
+        umma_f16_elect(d_tmem, a_lo, DESC_HI, bd, DESC_HI, IDESC_DH, 1u);
     }
 }
 
@@ -218,7 +255,7 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma2_kernel(const U2Params p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const Offs of = carve(p);
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + of.mbar);
-    uint64_t *mbar_idx = mbar, *a1_full = mbar + 2, *a2_full = mbar + 3, *e3_done = mbar + 4, *c2 = mbar + 5, *c3 = mbar + 9;
+    uint64_t *mbar_idx = mbar, *a1_full = mbar + 2, *a2_full = mbar + 3, *e3_done = mbar + 4, *c2 = mbar + 5, *c3 = mbar + 9, *dbar = mbar + 13;
     uint32_t *tmem_addr_s = reinterpret_cast<uint32_t *>(smem_raw + of.tm);
     float *b2s = reinterpret_cast<float *>(smem_raw + of.b), *b3 = b2s + F;
     float *t012 = reinterpret_cast<float *>(smem_raw + of.t012), *t34 = reinterpret_cast<float *>(smem_raw + of.t34);
@@ -234,7 +271,8 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma2_kernel(const U2Params p) {
 
     if (tid == 0) {
         fxd::mbar_init(&mbar_idx[0], 1); fxd::mbar_init(&mbar_idx[1], 1);
-        fxd::mbar_init(a1_full, NPROD); fxd::mbar_init(a2_full, NEPI); fxd::mbar_init(e3_done, NEPI);
+        fxd::mbar_init(dbar, 1);
+        fxd::mbar_init(a1_full, NPROD); fxd::mbar_init(a2_full, NEPI); fxd::mbar_init(e3_done, 8);
         for (int i = 0; i < NTILE; ++i) { fxd::mbar_init(&c2[i], 1); fxd::mbar_init(&c3[i], 1); }
         fxd::fence_mbar_init();
     }
@@ -256,8 +294,9 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma2_kernel(const U2Params p) {
     const uint32_t uw2_addr = fxd::smem_u32(uw2), uw3_addr = fxd::smem_u32(uw3);
 
     uint32_t n = 0, iter = 0;  // chunks done, items done (running over members and groups)
+    uint32_t dph = 0;          // completed phases of the dense-head barrier
     float xmax = 0.f;          // largest activation written as fp16 (range guard)
-    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long pt[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
     for (int mem = 0; mem < p.M; ++mem) {
         const float *w = p.weights + (int64_t)mem * p.member_floats;
@@ -281,7 +320,7 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma2_kernel(const U2Params p) {
         __syncthreads();
 
         int64_t item = blockIdx.x;
-        if (tid == 9 * 32 && item < p.n_items) issue_idx_load(p, smem_raw + ((iter & 1) ? of.i1 : of.i0), &mbar_idx[iter & 1], item);
+        if (tid == PRODW0 * 32 && item < p.n_items) issue_idx_load(p, smem_raw + ((iter & 1) ? of.i1 : of.i0), &mbar_idx[iter & 1], item);
         while (item < p.n_items) {
             // ---- the group of items whose features fit the dense-head batch ----
             int64_t g_end = item;
@@ -297,12 +336,13 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma2_kernel(const U2Params p) {
             }
             const long long tg0 = clock64();
 
-            if (wid >= 9) {
-                // =========================== producers: conv1 -> A1 ===========================
-                const int pw = wid - 9, ptid = tid - 9 * 32;
-                walk_group(p, item, g_end, n, iter, [&](const Chunk &c) {
+            // conv1 -> A1 for one chunk; shared by all 16 worker warps (warp `wid` takes units wid, wid+16, ...)
+            const int pw = wid - PRODW0, ptid = tid - PRODW0 * 32;
+            auto conv1 = [&](const Chunk &c) {
                     const int buf = c.iter & 1;
+                    const long long q0 = clock64();
                     if (c.n > 0) fxd::mbar_wait(&c2[NTILE - 1], (c.n - 1) & 1);  // A1 free again
+                    const long long q1 = clock64();
                     if (c.first_chunk) {
                         const int64_t next = c.item + gridDim.x;
                         if (ptid == 0 && next < p.n_items)
@@ -310,6 +350,7 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma2_kernel(const U2Params p) {
                         for (int i = ptid; i < c.s_item; i += NPROD * 32) slot_seq[c.slot0 + i] = c.first + i;
                         fxd::mbar_wait(&mbar_idx[buf], (c.iter >> 1) & 1);
                     }
+                    const long long q2 = clock64();
                     const uint8_t *sidx = smem_raw + (buf ? of.i1 : of.i0) +
                                           ((reinterpret_cast<uintptr_t>(p.idx) + (uintptr_t)(c.first * L)) & 15);
                     // One unit = 32 MMA rows of a tile (lane -> row i = 8a + b -> conv position 16b + a, so a warp's
@@ -326,7 +367,8 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma2_kernel(const U2Params p) {
                         }
                         const int r = tile * 128 + 16 * b + a;  // chunk-local h1 row
                         const int rho = c.c0 - pl3 - pl2 + r;
-                        const int s = (rho >= 0 && rho < c.rows_item) ? rowseq[rho] : 0xFF;
+                        int s = (rho >= 0 && rho < c.rows_item) ? rowseq[rho] : 0xFF;
+                        if (p.dbg & 2) { if (lane || u) continue; s = 0xFF; }
                         // slots of this row inside a plane: main copy and (for a < k-1) the wrap copy
                         const int main_off = (tile < NTILE) ? tile * TS1 + a * 128 + b * 16 : -1;
                         int wrap_off = -1;
@@ -334,6 +376,9 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma2_kernel(const U2Params p) {
                             const int tt = (b == 0) ? tile - 1 : tile, bb = (b == 0) ? 7 : b - 1;
                             if (tt >= 0 && tt < NTILE) wrap_off = tt * TS1 + (16 + a) * 128 + bb * 16;
                         }
+                        // h1 row = relu(T012[a0,a1,a2] + T34[a3,a4]) (bias and activation scale folded into the tables).
+                        // A single 4^5-entry table in L2 was measured slower (L2 latency under load: 3.4k cycles per
+                        // 32-row unit vs 2k for the two padded smem tables).
                         int i012 = 0, i34 = 0;
                         if (s != 0xFF) {
                             const uint8_t *ip = sidx + s * L + (rho - s * P - hl);
@@ -364,34 +409,15 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma2_kernel(const U2Params p) {
                             }
                         }
                     }
+                    const long long q3 = clock64();
                     fence_async_smem();
                     __syncwarp();
+                    const long long q4 = clock64();
                     if (lane == 0) mbar_arrive(a1_full);
-                });
-            } else if (wid == 8) {
-                // =========================== MMA issuer ===========================
-                walk_group(p, item, g_end, n, iter, [&](const Chunk &c) {
-                    const uint32_t par = c.n & 1;
-                    fxd::mbar_wait(a1_full, par);
-                    tc_fence_after();
-#pragma unroll
-                    for (int t = 0; t < NTILE; ++t) {
-                        if (t < c.ntile2)
-                            issue_conv_tile<K, PL1>(a1_addr + (uint32_t)t * TS1, uw2_addr, tmem_base + (uint32_t)t * 64u);
-                        umma_commit_elect(&c2[t]);
-                    }
-                    fxd::mbar_wait(a2_full, par);
-                    if (c.n > 0) fxd::mbar_wait(e3_done, (c.n - 1) & 1);  // conv3 accumulators drained
-                    tc_fence_after();
-#pragma unroll
-                    for (int t = 0; t < NTILE; ++t) {
-                        if (t < c.ntile3)
-                            issue_conv_tile<K3, PL2>(a2_addr + (uint32_t)t * TS2, uw3_addr, tmem_base + 256u + (uint32_t)t * 64u);
-                        umma_commit_elect(&c3[t]);
-                    }
-                });
-            } else {
-                // =========================== epilogue warps ===========================
+                    if (ptid == 0) { pt[8] += q1 - q0; pt[9] += clock64() - q1; pt[14] += q2 - q1; pt[15] += q3 - q2; pt[1] += q4 - q3; }
+                };
+            if (wid < 8) {
+                // ====== warps 0-7: conv2 epilogue (E2) + conv1 producer ======
                 const int lq = wid & 3, ch = wid >> 2;
                 // TMEM lane i = 32*lq + lane is MMA row i = 8a + b, i.e. conv position 16b + a of the tile
                 const int ea = 4 * lq + (lane >> 3), eb = lane & 7;
@@ -401,7 +427,7 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma2_kernel(const U2Params p) {
                 const int e_wrap_off = (16 + ea) * 128 + ((eb == 0) ? 7 : eb - 1) * 16;
                 const uint32_t tlane = tmem_base + ((uint32_t)(lq * 32) << 16);
                 unsigned char *a2h = a2 + (size_t)(ch * 2) * PL2;            // hi plane of this warp's first chunk
-                walk_group(p, item, g_end, n, iter, [&](const Chunk &c) {
+                auto e2 = [&](const Chunk &c) {
                     const uint32_t par = c.n & 1;
                     // ---- E2: conv2 accumulators -> bias, ReLU, mask, split -> A2 ----
                     for (int t = 0; t < c.ntile2; ++t) {
@@ -417,6 +443,7 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma2_kernel(const U2Params p) {
                         const bool valid = (rho >= 0) && (rho < c.rows_item) && (rowseq[rho] != 0xFF);
                         const int wrap_tile = (eb == 0) ? t - 1 : t;
                         tmem_ld_wait();
+                        if (p.dbg & 4) continue;
 #pragma unroll
                         for (int cc = 0; cc < 2; ++cc) {
                             float x[8];
@@ -449,11 +476,28 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma2_kernel(const U2Params p) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(a2_full);
+                };
+                Chunk prev;
+                bool have_prev = false;
+                walk_group(p, item, g_end, n, iter, [&](const Chunk &c) {
+                    if (have_prev) e2(prev);   // E2(n-1) ...
+                    conv1(c);                  // ... then h1 of chunk n while the tensor core runs conv3(n-1)
+                    prev = c; have_prev = true;
+                });
+                if (have_prev) e2(prev);
+            } else if (wid < 16) {
+                // ====== warps 8-15: conv3 epilogue (E3) ======
+                const int lq = wid & 3, ch = (wid >> 2) & 1;
+                const int ea = 4 * lq + (lane >> 3), eb = lane & 7;
+                const int pos = 16 * eb + ea;  // conv position of TMEM lane 32*lq + lane inside a tile
+                const uint32_t tlane = tmem_base + ((uint32_t)(lq * 32) << 16);
+                auto e3 = [&](const Chunk &c) {
+                    const uint32_t par = c.n & 1;
                     // ---- E3: conv3 accumulators -> bias, ReLU, mask -> max per sequence -> featT ----
                     for (int t = 0; t < c.ntile3; ++t) {
                         const long long w0 = clock64();
                         fxd::mbar_wait(&c3[t], par);
-                        if (tid == 0) pt[4] += clock64() - w0;
+                        if (tid == 8 * 32) pt[4] += clock64() - w0;
                         tc_fence_after();
                         uint32_t v[16], v2[16];
                         tmem_ld16_nowait(tlane + 256u + (uint32_t)(t * 64 + ch * 16), v);
@@ -476,7 +520,7 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma2_kernel(const U2Params p) {
                         }
                         // GlobalMaxPooling1D over the rows of each sequence present in this warp: one REDUX per
                         // filter, lane q keeps filter q, then a single 16-address shared atomic per sequence
-                        unsigned todo = __ballot_sync(0xffffffffu, valid);
+                        unsigned todo = (p.dbg & 1) ? 0u : __ballot_sync(0xffffffffu, valid);
                         while (todo) {
                             const int leader = __ffs(todo) - 1;
                             const int s_l = __shfl_sync(0xffffffffu, s, leader);
@@ -496,6 +540,35 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma2_kernel(const U2Params p) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(e3_done);
+                };
+                walk_group(p, item, g_end, n, iter, [&](const Chunk &c) { e3(c); });
+            } else {
+                // =========================== MMA issuer ===========================
+                walk_group(p, item, g_end, n, iter, [&](const Chunk &c) {
+                    const uint32_t par = c.n & 1;
+                    const long long m0 = clock64();
+                    fxd::mbar_wait(a1_full, par);
+                    const long long m1 = clock64();
+                    tc_fence_after();
+#pragma unroll
+                    for (int t = 0; t < NTILE; ++t) {
+                        if (t < c.ntile2)
+                            issue_conv_tile<K, PL1>(a1_addr + (uint32_t)t * TS1, uw2_addr, tmem_base + (uint32_t)t * 64u);
+                        umma_commit_elect(&c2[t]);
+                    }
+                    const long long m2 = clock64();
+                    fxd::mbar_wait(a2_full, par);
+                    const long long m3 = clock64();
+                    if (c.n > 0) fxd::mbar_wait(e3_done, (c.n - 1) & 1);  // conv3 accumulators drained
+                    const long long m4 = clock64();
+                    if (lane == 0) { pt[10] += m1 - m0; pt[11] += m3 - m2; pt[12] += m4 - m3; pt[13] += m2 - m1; }
+                    tc_fence_after();
+#pragma unroll
+                    for (int t = 0; t < NTILE; ++t) {
+                        if (t < c.ntile3)
+                            issue_conv_tile<K3, PL2>(a2_addr + (uint32_t)t * TS2, uw3_addr, tmem_base + 256u + (uint32_t)t * 64u);
+                        umma_commit_elect(&c3[t]);
+                    }
                 });
             }
             n += g_chunks; iter += g_items; item = g_end;
@@ -503,7 +576,105 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma2_kernel(const U2Params p) {
             tc_fence_before();
             __syncthreads();
             const long long tg1 = clock64();
-            {
+            if (p.dense_umma) {
+                unsigned char *dx1 = a1 + DS_X1, *db1 = a1 + DS_B1, *dx2 = a1 + DS_X2, *db2 = a1 + DS_B2;
+                float *dpart = reinterpret_cast<float *>(a1 + DS_PART);
+                const float *gdv = reinterpret_cast<const float *>(uw + OFF_DV);
+                float *dv = reinterpret_cast<float *>(a1 + DS_DV);  // bias / output-weight vectors, staged in smem
+                const float inv_d1s = __ldg(gdv + 3 * DH), inv_d2 = __ldg(gdv + 3 * DH + 1), bd3v = __ldg(gdv + 3 * DH + 2);
+                for (int i = tid; i < 3 * DH; i += NT) dv[i] = __ldg(gdv + i);
+                // (1) stage the dense weight planes, turn the features into the A operand of layer 1
+                for (int i = tid; i < 4 * DBK / 16; i += NT)
+                    reinterpret_cast<uint4 *>(db1)[i] = __ldg(reinterpret_cast<const uint4 *>(uw + OFF_DB1) + i);
+                for (int i = tid; i < 14 * DBK / 16; i += NT)
+                    reinterpret_cast<uint4 *>(db2)[i] = __ldg(reinterpret_cast<const uint4 *>(uw + OFF_DB2) + i);
+                if (tid < 4 * DSLOTS) {
+                    const int slot = tid & (DSLOTS - 1), cchunk = tid >> 7;
+                    float x[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) x[q] = (slot < p.sbcap) ? featT[(cchunk * 8 + q) * p.sbp + slot] * ASCALE : 0.f;
+                    uint4 hi4, lo4;
+                    split8(x, hi4, lo4, xmax);
+                    *reinterpret_cast<uint4 *>(dx1 + (size_t)cchunk * DPLANE + slot * 16) = hi4;
+                    *reinterpret_cast<uint4 *>(dx1 + (size_t)(4 + cchunk) * DPLANE + slot * 16) = lo4;
+                }
+                fence_async_smem();
+                __syncthreads();
+                const int lq = wid & 3, half = wid >> 2, slot = 32 * lq + lane;
+                const uint32_t tl = tmem_base + ((uint32_t)(lq * 32) << 16);
+                // (2) layer 1 on the tensor cores, (3) bias + ReLU + split -> A operand of layer 2
+                if (wid == MMAW) {
+                    tc_fence_after();
+                    issue_dense_layer<2, 4>(fxd::smem_u32(dx1), fxd::smem_u32(db1), tmem_base);
+                    umma_commit_elect(dbar);
+                } else if (wid < 8) {
+                    fxd::mbar_wait(dbar, dph & 1);
+                    tc_fence_after();
+                    for (int c7 = 0; c7 < 7; ++c7) {
+                        const int cchunk = half * 7 + c7;
+                        uint32_t va[8], vb[8];
+                        tmem_ld8_nowait(tl + (uint32_t)(cchunk * 8), va);
+                        tmem_ld8_nowait(tl + (uint32_t)(DH + cchunk * 8), vb);
+                        const float4 b0 = *reinterpret_cast<const float4 *>(dv + cchunk * 8);
+                        const float4 b1 = *reinterpret_cast<const float4 *>(dv + cchunk * 8 + 4);
+                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                        tmem_ld_wait();
+                        float x[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            x[q] = fmaxf(fmaf(__uint_as_float(va[q]) + __uint_as_float(vb[q]), inv_d1s, bb[q]), 0.f);
+                        uint4 hi4, lo4;
+                        split8(x, hi4, lo4, xmax);
+                        *reinterpret_cast<uint4 *>(dx2 + (size_t)cchunk * DPLANE + slot * 16) = hi4;
+                        *reinterpret_cast<uint4 *>(dx2 + (size_t)(14 + cchunk) * DPLANE + slot * 16) = lo4;
+                    }
+                }
+                ++dph;
+                fence_async_smem();
+                tc_fence_before();
+                __syncthreads();
+                // (4) layer 2, (5) bias + ReLU + dot with the output weights
+                if (wid == MMAW) {
+                    tc_fence_after();
+                    issue_dense_layer<7, 14>(fxd::smem_u32(dx2), fxd::smem_u32(db2), tmem_base + 256u);
+                    umma_commit_elect(dbar);
+                } else if (wid < 8) {
+                    fxd::mbar_wait(dbar, dph & 1);
+                    tc_fence_after();
+                    float sum = 0.f;
+                    for (int c7 = 0; c7 < 7; ++c7) {
+                        const int cchunk = half * 7 + c7;
+                        uint32_t va[8], vb[8];
+                        tmem_ld8_nowait(tl + 256u + (uint32_t)(cchunk * 8), va);
+                        tmem_ld8_nowait(tl + 256u + (uint32_t)(DH + cchunk * 8), vb);
+                        const float4 b0 = *reinterpret_cast<const float4 *>(dv + DH + cchunk * 8);
+                        const float4 b1 = *reinterpret_cast<const float4 *>(dv + DH + cchunk * 8 + 4);
+                        const float4 w0 = *reinterpret_cast<const float4 *>(dv + 2 * DH + cchunk * 8);
+                        const float4 w1 = *reinterpret_cast<const float4 *>(dv + 2 * DH + cchunk * 8 + 4);
+                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                        const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float d2 = fmaxf(fmaf(__uint_as_float(va[q]) + __uint_as_float(vb[q]), inv_d2, bb[q]), 0.f);
+                            sum = fmaf(d2, ww[q], sum);
+                        }
+                    }
+                    dpart[half * DSLOTS + slot] = sum;
+                }
+                ++dph;
+                tc_fence_before();
+                __syncthreads();
+                // (6) Dense(1) bias, nan_to_num (keras_model.py:77), ensemble mean (ensemble.py:24)
+                for (int sl = tid; sl < g_slots; sl += NT) {
+                    const float y = fxd::nan_to_num(dpart[sl] + dpart[DSLOTS + sl] + bd3v);
+                    const long long seq = slot_seq[sl];
+                    float tot = (mem == 0) ? y : p.out[seq] + y;
+                    if (p.M > 1 && mem == p.M - 1) tot = tot / (float)p.M;
+                    p.out[seq] = tot;
+                }
+                __syncthreads();
+            } else {
                 fxd::DenseArgs da{w + p.o.wd1, w + p.o.bd1, w + p.o.wd2, w + p.o.bd2, w + p.o.wd3, w + p.o.bd3,
                                   featT, reinterpret_cast<float *>(a1), slot_seq, p.out,
                                   F, p.d.H, p.sbp, g_slots, mem, p.M, p.stage};
@@ -515,8 +686,9 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma2_kernel(const U2Params p) {
         }
     }
     if (xmax > 60000.f) atomicExch(p.overflow_flag, 1);
-    if (p.prof != nullptr && tid == 0)
-        for (int i = 0; i < 8; ++i) p.prof[(size_t)blockIdx.x * 8 + i] = pt[i];
+    if (p.prof != nullptr && (tid == 0 || tid == 8 * 32 || tid == PRODW0 * 32 || tid == MMAW * 32))  // warp 0 times the conv2 waits, warp 8 the conv3 waits
+        for (int i = 0; i < 16; ++i)
+            if (pt[i]) atomicAdd(reinterpret_cast<unsigned long long *>(&p.prof[(size_t)blockIdx.x * 16 + i]), (unsigned long long)pt[i]);
     tc_fence_before();
     __syncthreads();
     if (wid == 0) tmem_dealloc(tmem_base, 512);
@@ -532,11 +704,12 @@ static bool plan(const flexs_model *m, U2Params &p) {
     const int hr = std::max(p.d.pr2, p.d.pr3);
     p.P = (p.hl + p.d.T + hr + 3) & ~3;
     const size_t abytes = (size_t)8 * (PL1 + PL2);
-    int sbcap = 64;
-    while (sbcap >= 8 && fxd::dense_scratch_floats(F, p.d.H, sbcap + 4, false) * 4 > abytes) sbcap -= 8;
+    p.dense_umma = (p.d.H <= DH) ? 1 : 0;
+    int sbcap = p.dense_umma ? DSLOTS : 64;
+    while (!p.dense_umma && sbcap >= 8 && fxd::dense_scratch_floats(F, p.d.H, sbcap + 4, false) * 4 > abytes) sbcap -= 8;
     if (sbcap < 8) return false;
     p.sbcap = sbcap; p.sbp = sbcap + 4;
-    p.stage = fxd::dense_scratch_floats(F, p.d.H, p.sbp, true) * 4 <= abytes ? 1 : 0;
+    p.stage = (!p.dense_umma && fxd::dense_scratch_floats(F, p.d.H, p.sbp, true) * 4 <= abytes) ? 1 : 0;
     p.S = std::max(1, std::min(ROUT / p.P, sbcap));
     p.idx_slot = (int)align_up((size_t)p.S * p.d.L + 32, 16);
     p.rs_bytes = (int)align_up((size_t)p.S * p.P, 16);
@@ -597,6 +770,44 @@ static int prepare(flexs_model *m, const U2Params &p) {
         float *tail = reinterpret_cast<float *>(dst + OFF_SCAL);
         tail[0] = inv[0] * ASCALE;  // conv2 epilogue emits activations pre-scaled by ASCALE
         tail[1] = inv[1];
+        // dense head operands (used when H <= 112): Wd1 (F,H) and Wd2 (H,H) as [k chunk][n hi|lo][8 k] planes
+        const int H = p.d.H;
+        if (H <= DH) {
+            float dinv[2];
+            for (int layer = 0; layer < 2; ++layer) {
+                const int kin = layer == 0 ? F : H;
+                const float *src = w + (layer == 0 ? p.o.wd1 : p.o.wd2);  // (in, out)
+                float mx = 0.f;
+                for (int i = 0; i < kin * H; ++i) {
+                    if (!std::isfinite(src[i])) m->umma_weights_ok = false;
+                    mx = std::max(mx, std::fabs(src[i]));
+                }
+                int e = 0;
+                if (mx > 0.f && std::isfinite(mx)) e = 14 - (int)std::floor(std::log2(mx));
+                e = std::max(-24, std::min(e, 40));
+                const float scale = std::ldexp(1.f, e);
+                dinv[layer] = std::ldexp(1.f, -e) / ASCALE;
+                __half *planes = reinterpret_cast<__half *>(dst + (layer == 0 ? OFF_DB1 : OFF_DB2));
+                for (int k = 0; k < kin; ++k)
+                    for (int o = 0; o < H; ++o) {
+                        const float v = src[(size_t)k * H + o] * scale;
+                        const __half hi = __float2half_rn(v);
+                        const __half lo = __float2half_rn(v - __half2float(hi));
+                        const size_t base = (size_t)(k >> 3) * (DBK / 2) + (k & 7);
+                        planes[base + (size_t)o * 8] = hi;
+                        planes[base + (size_t)(DH + o) * 8] = lo;
+                    }
+            }
+            float *dv = reinterpret_cast<float *>(dst + OFF_DV);
+            for (int o = 0; o < H; ++o) {
+                dv[o] = w[p.o.bd1 + o] * ASCALE;
+                dv[DH + o] = w[p.o.bd2 + o];
+                dv[2 * DH + o] = w[p.o.wd3 + o];
+            }
+            dv[3 * DH] = dinv[0] * ASCALE;  // layer-1 epilogue emits activations pre-scaled by ASCALE
+            dv[3 * DH + 1] = dinv[1];
+            dv[3 * DH + 2] = w[p.o.bd3];
+        }
     }
     FX_CUDA(cudaSetDevice(m->device));
     if (!m->d_umma2_w) FX_CUDA(cudaMalloc(&m->d_umma2_w, blob.size()));
@@ -630,10 +841,11 @@ int launch_cnn_umma2(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_o
     const size_t smem = carve(p).total + 1024;
     const int grid = (int)std::min<int64_t>(p.n_items, m->sm_count);
     static const bool prof = std::getenv("FLEXS_UMMA_PROF") && std::getenv("FLEXS_UMMA_PROF")[0] == '1';
+    p.dbg = std::getenv("FLEXS_UMMA_DBG") ? std::atoi(std::getenv("FLEXS_UMMA_DBG")) : 0;
     p.prof = nullptr;
     if (prof) {
-        FX_CUDA(cudaMalloc(&p.prof, (size_t)grid * 8 * sizeof(long long)));
-        FX_CUDA(cudaMemset(p.prof, 0, (size_t)grid * 8 * sizeof(long long)));
+        FX_CUDA(cudaMalloc(&p.prof, (size_t)grid * 16 * sizeof(long long)));
+        FX_CUDA(cudaMemset(p.prof, 0, (size_t)grid * 16 * sizeof(long long)));
     }
     FX_CUDA(cudaMemsetAsync(m->d_flag, 0, sizeof(int), s));
     FX_CUDA(cudaFuncSetAttribute(cnn_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -642,15 +854,17 @@ int launch_cnn_umma2(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_o
     m->launches += 1;
     if (prof) {
         FX_CUDA(cudaStreamSynchronize(s));
-        std::vector<long long> h((size_t)grid * 8);
+        std::vector<long long> h((size_t)grid * 16);
         FX_CUDA(cudaMemcpy(h.data(), p.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         cudaFree(p.prof);
-        double a[8] = {0};
-        for (int b = 0; b < grid; ++b) for (int i = 0; i < 8; ++i) a[i] += (double)h[(size_t)b * 8 + i] / grid;
+        double a[16] = {0};
+        for (int b = 0; b < grid; ++b) for (int i = 0; i < 16; ++i) a[i] += (double)h[(size_t)b * 16 + i] / grid;
         const double ch = a[6] > 0 ? a[6] : 1;
         fprintf(stderr, "[umma2 prof] n=%lld grid=%d chunks/CTA=%.0f | cycles per chunk: pipeline %.0f (epilogue warp 0 "
-                        "waiting on conv2 MMAs %.0f, conv3 MMAs %.0f), dense+drain %.0f\n",
-                (long long)n, grid, a[6], a[0] / ch, a[2] / ch, a[4] / ch, a[5] / ch);
+                        "waiting on conv2 MMAs %.0f, conv3 MMAs %.0f), dense+drain %.0f | producer: wait A1 free %.0f, conv1 %.0f | "
+                        "MMA warp: wait A1 %.0f, issue conv2 %.0f, wait A2 %.0f, wait E3 %.0f | conv1 parts: idx wait %.0f, rows %.0f, fence %.0f\n",
+                (long long)n, grid, a[6], a[0] / ch, a[2] / ch, a[4] / ch, a[5] / ch, a[8] / ch, a[9] / ch, a[10] / ch, a[13] / ch,
+                a[11] / ch, a[12] / ch, a[14] / ch, a[15] / ch, a[1] / ch);
     }
     // fp16 range guard: the gated FFMA kernel recomputes the batch iff the flag was raised
     return launch_cnn_tiled_gated(m, d_idx, n, d_out, m->d_flag, s);

@@ -427,3 +427,26 @@ def test_mutate_rates_and_determinism():
     _native.mutate_dev(d.data_ptr(), n, L, A, 0.2, 1234, 1, out2.data_ptr())
     torch.cuda.synchronize()
     assert not torch.equal(out, out2)
+
+
+def test_real_keras_golden_if_present():
+    """tools/export_keras_golden.py output (made where TensorFlow exists) pins the float parity."""
+    import glob
+    import os
+
+    files = glob.glob(os.path.join(os.path.dirname(__file__), "golden", "keras_*.npz"))
+    if not files:
+        pytest.skip("no real-Keras vectors committed (TensorFlow is absent in the authoring container): parity unpinned")
+    for path in files:
+        g = np.load(path)
+        ws = [g[f"w{i}"] for i in range(len([k for k in g.files if k.startswith("w")]))]
+        idx, y = g["idx"], g["y"]
+        if str(g["kind"]) == "cnn":
+            m = _native.NativeModel("cnn", seq_len=idx.shape[1], alphabet_size=ws[0].shape[1], num_filters=ws[0].shape[2],
+                                    hidden_size=ws[6].shape[1], kernel_size=int(g["kernel_size"]))
+        else:
+            m = _native.NativeModel("mlp", seq_len=idx.shape[1], alphabet_size=ws[0].shape[0] // idx.shape[1],
+                                    hidden_size=ws[0].shape[1])
+        m.set_weights(ws)
+        assert rel_err(_device_forward(m, idx), y, _floor(y)) < TOL, path
+        m.close()
