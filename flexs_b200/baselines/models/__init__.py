@@ -5,3 +5,4 @@ from flexs_b200.baselines.models.surrogate import B200Surrogate  # noqa: F401
 
 #: drop-in alias: code that subclasses / type-checks against ``baselines.models.KerasModel``
 KerasModel = B200Surrogate
+from flexs_b200.baselines.models.noisy_abstract_model import NoisyAbstractModel  # noqa: F401,E402

@@ -94,3 +94,100 @@ def test_cma_sampler_minimises_sphere_full_and_separable():
         assert min(fs) < 1e-3 * f0
     xs, fs = es.ask_and_eval(lambda x: float(np.sum(x * x)))
     assert len(xs) == len(fs) == 16
+
+
+def test_cbas_and_dbas_run_like_reference_smoke_test():
+    """tests/test_explorers.py:115-128 of the reference: 2-epoch VAE, rounds=3, B=5, Q=20."""
+    from flexs_b200.baselines.explorers import VAE, CbAS
+
+    for algo in ("cbas", "dbas"):
+        vae = VAE(len(START), alphabet=ALPHABET, epochs=2, verbose=False)
+        model = FakeModel()
+        ex = CbAS(model, vae, rounds=3, starting_sequence=START, sequences_batch_size=5, model_queries_per_batch=20,
+                  alphabet=ALPHABET, algo=algo, cycle_batch_size=10)
+        assert ex.name == f"{algo}_Q=0.7_generator=VAE_latent_dim=2_intermediate_dim=250"
+        table, _ = ex.run(FakeLandscape("l"), verbose=False)
+        assert set(table["round"]) == {0, 1, 2, 3}
+        assert len(table[table["round"] == 1]) == 5          # round 1: random neighbourhood, B sequences
+        for r in (2, 3):
+            rows = table[table["round"] == r]
+            assert 1 <= len(rows) <= 4                        # B-1 (cbas_dbas.py:199)
+            assert rows["model_cost"].iloc[0] - table[table["round"] == r - 1]["model_cost"].iloc[0] == 20
+    with pytest.raises(ValueError):
+        CbAS(FakeModel(), vae, 1, START, 5, 20, ALPHABET, algo="nope")
+
+
+def test_vae_pieces():
+    from flexs_b200.utils import VAE_utils
+
+    w = VAE_utils.pwm_to_boltzmann_weights(np.array([[0.1, 0.9], [0.9, 0.1], [0.5, 0.5]]), 0.5)
+    np.testing.assert_allclose(w.sum(axis=0), 1.0)
+    vae = VAE_utils.VAE(6, "ATCG", epochs=1, verbose=False)
+    seqs = ["ATCGAT", "TTTTTT", "ACACAC", "GGGGGG", "ATATAT", "CGCGCG", "AAAAAA", "TGTGTG", "CACACA", "GTGTGT"]
+    vae.train_model(seqs, np.ones(len(seqs)))
+    lp = vae.calculate_log_probability(seqs)
+    assert lp.shape == (10,) and np.all(lp <= 0) and np.all(np.isfinite(lp))
+    out = vae.generate(7, seqs, np.ones(len(seqs)))
+    assert len(out) == len(set(out)) == 7 and not set(out) & set(seqs) and all(len(s) == 6 for s in out)
+    clone = VAE_utils.VAE(6, "ATCG", epochs=1, verbose=False)
+    clone.vae.set_weights(vae.vae.get_weights())
+    for a, b in zip(clone.vae.get_weights(), vae.vae.get_weights()):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_dynappo_runs_and_budgets():
+    """tests/test_explorers.py:86-97 of the reference (DynaPPO with a fake model)."""
+    from flexs_b200.baselines.explorers import DynaPPO
+    from flexs_b200.baselines.explorers.dyna_ppo import bounded_edit_distance
+
+    assert bounded_edit_distance("ATCG", "ATCG", 2) == 0
+    assert bounded_edit_distance("ATCG", "ATGG", 2) == 1
+    assert bounded_edit_distance("ATCG", "TCGA", 2) == 2
+    assert bounded_edit_distance("ATCG", "GCTA", 2) == 3   # capped at radius + 1
+    assert bounded_edit_distance("ATCGAAA", "ATCG", 2) == 3
+    model, landscape = FakeModel(), FakeLandscape("l")
+    ex = DynaPPO(landscape=landscape, model=model, rounds=3, sequences_batch_size=5, model_queries_per_batch=20,
+                 starting_sequence=START, alphabet=ALPHABET)
+    assert ex.name == "DynaPPO_Agent_10_1"
+    table, _ = ex.run(landscape, verbose=False)
+    assert set(table["round"]) <= {0, 1, 2, 3}
+    for r in (1, 2, 3):
+        rows = table[table["round"] == r]
+        assert len(rows) <= 5
+        assert all(s.endswith(ALPHABET[0]) for s in rows["sequence"])   # last position is never sampled (quirk 5)
+    assert all(c == 4 for c in model.calls)                                # one env_batch_size call per episode end
+    assert model.cost == 3 * 20                                            # 5 episodes x 4 per round
+
+
+def test_noisy_abstract_model_and_evaluate_drivers():
+    """tests/test_models.py:80-99 of the reference + the three flexs.evaluate sweeps with fakes."""
+    from flexs_b200.baselines.models import NoisyAbstractModel
+    from flexs_b200.baselines.models.noisy_abstract_model import edit_distance
+
+    assert edit_distance("kitten", "sitting") == 3 and edit_distance("", "abc") == 3 and edit_distance("ab", "ab") == 0
+
+    class Additive(flexs.Landscape):
+        def _fitness_function(self, sequences):
+            return np.array([sum(ch == "A" for ch in s) / len(s) for s in sequences])
+
+    land = Additive("additive")
+    nam = NoisyAbstractModel(land, signal_strength=1.0)
+    np.testing.assert_allclose(nam.get_fitness(["AATT", "TTTT"]), [0.5, 0.0])   # ss = 1: exact ground truth
+    nam = NoisyAbstractModel(land, signal_strength=0.5)
+    first = nam.get_fitness(["AATT", "ATAT"])
+    np.testing.assert_array_equal(nam.get_fitness(["AATT", "ATAT"]), first)       # cached -> deterministic
+    nam.train(["CCCC"], [7.0])
+    assert nam.get_fitness(["CCCC"])[0] == 7.0
+
+    def mk(model, ss):
+        return Adalead(model, rounds=2, sequences_batch_size=4, model_queries_per_batch=12, starting_sequence="ATCATCAT",
+                       alphabet="ATCG", eval_batch_size=1)
+
+    res = flexs.evaluate.robustness(land, mk, signal_strengths=[0, 1], verbose=False)
+    assert [r[0] for r in res] == [0, 1] and all(len(r[1][0]) > 1 for r in res)
+    res = flexs.evaluate.efficiency(land, lambda b, q: Adalead(FakeModel(), 1, b, q, "ATCATCAT", "ATCG", eval_batch_size=1),
+                                    budgets=[(3, 9), (4, 12)])
+    assert [r[0] for r in res] == [(3, 9), (4, 12)]
+    res = flexs.evaluate.adaptivity(land, lambda r, b, q: Adalead(FakeModel(), r, b, q, "ATCATCAT", "ATCG", eval_batch_size=1),
+                                    num_rounds=[1, 2], total_ground_truth_measurements=8, total_model_queries=24)
+    assert [r[0] for r in res] == [1, 2]
