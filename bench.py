@@ -394,7 +394,7 @@ def main():
         "hbm_frac": (L_NS + 4) * args.batch / (fwd_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
         "fp32_ffma_peak_tflops_nominal": 148 * 128 * 2 * 1.965e9 / 1e12,
         "note": "compute-bound path (1.55e4 flop/B): fraction is of the dense bf16 tensor peak; "
-                "algorithmic flops count each MAC once even when the kernel runs 3 split-bf16 passes",
+                "algorithmic flops count each MAC once even though the tcgen05 kernel runs 3 fp16 hi/lo split products per MAC",
     }
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -266,6 +266,14 @@ int flexs_model_score_host(flexs_model_t *m, const char *h_chars, int64_t n, con
     int rc = ensure_host_staging(m);
     if (rc != FLEXS_OK) return rc;
     const int64_t chunk = m->host_chunk, L = m->L;
+    // Buffers the caller already page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) are used
+    // directly by the async copies; pageable ones go through the model's pinned staging slots.
+    auto is_pinned = [](const void *ptr) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+        return attr.type == cudaMemoryTypeHost;
+    };
+    const bool in_pinned = is_pinned(h_chars), out_pinned = is_pinned(h_out);
     const int64_t nchunks = (n + chunk - 1) / chunk;
     int64_t first_bad = std::numeric_limits<int64_t>::max();
     // slot bookkeeping: what is in flight in each slot
@@ -275,7 +283,7 @@ int flexs_model_score_host(flexs_model_t *m, const char *h_chars, int64_t n, con
         FX_CUDA(cudaEventSynchronize(m->slot_done[slot]));
         const int64_t *st = m->h_status + 2 * slot;
         if (st[0] != 0) first_bad = std::min(first_bad, inflight_start[slot] * L + st[1]);
-        std::memcpy(h_out + inflight_start[slot], m->h_pin_out[slot], inflight_cnt[slot] * sizeof(float));
+        if (!out_pinned) std::memcpy(h_out + inflight_start[slot], m->h_pin_out[slot], inflight_cnt[slot] * sizeof(float));
         inflight_start[slot] = -1;
         return FLEXS_OK;
     };
@@ -285,14 +293,16 @@ int flexs_model_score_host(flexs_model_t *m, const char *h_chars, int64_t n, con
         if (rc != FLEXS_OK) return rc;
         const int64_t start = c * chunk, cnt = std::min(chunk, n - start);
         cudaStream_t s = m->streams[slot];
-        std::memcpy(m->h_pin_chars[slot], h_chars + start * L, cnt * L);
-        FX_CUDA(cudaMemcpyAsync(m->d_chars[slot], m->h_pin_chars[slot], cnt * L, cudaMemcpyHostToDevice, s));
+        const void *src = h_chars + start * L;
+        if (!in_pinned) { std::memcpy(m->h_pin_chars[slot], src, cnt * L); src = m->h_pin_chars[slot]; }
+        FX_CUDA(cudaMemcpyAsync(m->d_chars[slot], src, cnt * L, cudaMemcpyHostToDevice, s));
         rc = launch_encode(m->d_chars[slot], cnt * L, alphabet, m->A, m->d_idx[slot], m->d_status + 2 * slot, s);
         if (rc != FLEXS_OK) return rc;
         m->launches += 1;
         rc = flexs_model_forward_dev(m, m->d_idx[slot], cnt, m->d_out[slot], s);
         if (rc != FLEXS_OK) return rc;
-        FX_CUDA(cudaMemcpyAsync(m->h_pin_out[slot], m->d_out[slot], cnt * sizeof(float), cudaMemcpyDeviceToHost, s));
+        FX_CUDA(cudaMemcpyAsync(out_pinned ? (void *)(h_out + start) : (void *)m->h_pin_out[slot], m->d_out[slot],
+                                cnt * sizeof(float), cudaMemcpyDeviceToHost, s));
         FX_CUDA(cudaMemcpyAsync(m->h_status + 2 * slot, m->d_status + 2 * slot, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
         FX_CUDA(cudaEventRecord(m->slot_done[slot], s));
         inflight_start[slot] = start; inflight_cnt[slot] = cnt;
