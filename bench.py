@@ -311,8 +311,12 @@ def run_reference(args, rank):
     oneDNN-backed torch-CPU conv1d/linear standing in for TF's CPU kernels, squeeze, nan_to_num."""
     if rank != 0:
         return
+    import torch
+
     from oracle import ref_path
 
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm is entitled to every host core
+    torch.set_num_threads(os.cpu_count() or 1)
     model = ref_path.ReferenceCNN(L_NS, "TGCA", F_NS, H_NS, K_NS, make_weights(cnn_shapes(L_NS, A_NS, F_NS, H_NS, K_NS), 0))
     n = 4096
     rng = np.random.default_rng(1234)
