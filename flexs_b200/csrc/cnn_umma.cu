@@ -19,9 +19,9 @@
 //
 // Per chunk of up to ntile*128 rows:
 //   conv1 gather-add (CUDA cores, all warps)            -> A1 planes (fp16 hi/lo)
-//   thread 256 issues conv2 MMAs, tcgen05.commit per tile -> mbarrier
+//   warp 8 issues conv2 MMAs (one elected lane), tcgen05.commit per tile -> mbarrier
 //   warps 0-7: tcgen05.ld, bias+ReLU+mask, split        -> A2 planes
-//   thread 256 issues conv3 MMAs
+//   warp 8 issues conv3 MMAs
 //   warps 0-7: tcgen05.ld, bias+ReLU+mask, warp REDUX max per sequence -> featT (smem atomics)
 //   every <=64 sequences: dense head (dense_head.cuh)    -> out
 #include <cuda_fp16.h>
@@ -135,16 +135,19 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                          uint32_t accumulate) {
+    // reached by the whole (converged) MMA warp, issued by one elected lane: keeps the descriptor arithmetic on
+    // the uniform datapath instead of a single thread's R2UR chain (see cnn_umma2.cu / profiles)
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                     fxd::smem_u32(bar))
-                 : "memory");
+    asm volatile(
+        "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(fxd::smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
@@ -335,11 +338,12 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma_kernel(const UmmaParams p) {
                 __syncthreads();
                 const long long tB = clock64();
                 // ---- conv2 on the tensor cores ----
-                if (tid == 256) {
+                if (wid == 8) {  // every barrier completes one phase per chunk, used tile or not (parity = chunk & 1)
                     tc_fence_after();
-                    for (int t = 0; t < ntile2; ++t) {
-                        issue_conv_tile(a1_addr, pl1_bytes, uw2_addr, K, t * 128, tmem_base + (uint32_t)(t * 32),
-                                        p.swap_lbo_sbo != 0);
+                    for (int t = 0; t < 4; ++t) {
+                        if (t < ntile2)
+                            issue_conv_tile(a1_addr, pl1_bytes, uw2_addr, K, t * 128, tmem_base + (uint32_t)(t * 32),
+                                            p.swap_lbo_sbo != 0);
                         umma_commit(&sm.mbar_c2[t]);
                     }
                 }
@@ -377,11 +381,12 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma_kernel(const UmmaParams p) {
                 __syncthreads();
                 const long long tC = clock64();
                 // ---- conv3 on the tensor cores ----
-                if (tid == 256) {
+                if (wid == 8) {
                     tc_fence_after();
-                    for (int t = 0; t < ntile3; ++t) {
-                        issue_conv_tile(a2_addr, pl2_bytes, uw3_addr, K3, t * 128, tmem_base + 128u + (uint32_t)(t * 32),
-                                        p.swap_lbo_sbo != 0);
+                    for (int t = 0; t < 4; ++t) {
+                        if (t < ntile3)
+                            issue_conv_tile(a2_addr, pl2_bytes, uw3_addr, K3, t * 128, tmem_base + 128u + (uint32_t)(t * 32),
+                                            p.swap_lbo_sbo != 0);
                         umma_commit(&sm.mbar_c3[t]);
                     }
                 }
