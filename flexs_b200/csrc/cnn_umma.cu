@@ -41,8 +41,8 @@ constexpr int F = 32;
 constexpr int NT = 512;
 constexpr int W1P = 36;
 constexpr float ASCALE = 8.f;
-constexpr int WPLANE = 512;    // bytes of one 8-channel weight plane: 32 filters x 16 B
-constexpr int WTAP = 4 * WPLANE;  // one (tap, split): 4 chunks
+constexpr int WPLANE = 1024;   // bytes of one 8-channel weight plane: [hi 32 filters | lo 32 filters] x 16 B
+constexpr int WTAP = 2 * WPLANE;  // half a tap (kept so that a tap = 2 * WTAP = 4 chunks x 1 KB, as sized below)
 
 struct UmmaParams {
     const uint8_t *idx;
@@ -167,26 +167,25 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo, 
 }
 
 // kind::f16 instruction descriptor: D=F32 (bit 4), A=B=F16 (0), K-major both, N=32, M=128
-constexpr uint32_t IDESC = (1u << 4) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t IDESC = (1u << 4) | ((32u >> 3) << 17) | ((128u >> 4) << 24);    // N = 32: A_lo x W_hi
+constexpr uint32_t IDESC64 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);  // N = 64: A_hi x [W_hi | W_lo]
 
-// one tile (128 rows) of an implicit-GEMM conv: taps x 2 channel pairs x 3 split products
+// one tile (128 rows) of an implicit-GEMM conv: taps x 2 channel pairs x {A_hi x [W_hi|W_lo] (N=64), A_lo x W_hi (N=32)}.
+// The two 32-column halves of the accumulator are added in the epilogue; the activation planes are read twice per
+// (tap, channel pair) instead of three times.
 __device__ __forceinline__ void issue_conv_tile(uint32_t a_base, uint32_t a_plane, uint32_t w_base, int taps,
                                                 int row0, uint32_t d_tmem, bool swap) {
     uint32_t first = 0;
     for (int j = 0; j < taps; ++j) {
 #pragma unroll
         for (int kp = 0; kp < 2; ++kp) {
-#pragma unroll
-            for (int pr = 0; pr < 3; ++pr) {
-                const int sa = (pr == 2) ? 1 : 0;  // (hi,hi) (hi,lo) (lo,hi)
-                const int sb = (pr == 1) ? 1 : 0;
-                const uint32_t a_addr = a_base + (uint32_t)(sa * 4 + 2 * kp) * a_plane + (uint32_t)(row0 + j) * 16u;
-                const uint32_t b_addr = w_base + (uint32_t)((j * 2 + sb) * 4 + 2 * kp) * WPLANE;
-                const uint64_t ad = swap ? make_desc(a_addr, 128, a_plane) : make_desc(a_addr, a_plane, 128);
-                const uint64_t bd = swap ? make_desc(b_addr, 128, WPLANE) : make_desc(b_addr, WPLANE, 128);
-                umma_f16(d_tmem, ad, bd, IDESC, first);
-                first = 1;
-            }
+            const uint32_t a_hi = a_base + (uint32_t)(2 * kp) * a_plane + (uint32_t)(row0 + j) * 16u;
+            const uint32_t a_lo = a_hi + 4u * a_plane;
+            const uint32_t b_addr = w_base + (uint32_t)(j * 4 + 2 * kp) * WPLANE;
+            const uint64_t bd = swap ? make_desc(b_addr, 128, WPLANE) : make_desc(b_addr, WPLANE, 128);
+            umma_f16(d_tmem, swap ? make_desc(a_hi, 128, a_plane) : make_desc(a_hi, a_plane, 128), bd, IDESC64, first);
+            umma_f16(d_tmem, swap ? make_desc(a_lo, 128, a_plane) : make_desc(a_lo, a_plane, 128), bd, IDESC, 1u);
+            first = 1;
         }
     }
 }
@@ -229,7 +228,7 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma_kernel(const UmmaParams p) {
     const int T = p.d.T, P = p.P, hl = p.hl, L = p.d.L, A = p.d.A, K = p.d.K, K3 = p.d.K3;
     const int pl2 = p.d.pl2, pl3 = p.d.pl3;
     const uint32_t pl1_bytes = (uint32_t)p.rows1 * 16u, pl2_bytes = (uint32_t)p.rows2 * 16u;
-    const uint32_t tmem_cols = 256;
+    const uint32_t tmem_cols = 512;  // conv2: 4 tiles x 64 columns, conv3: the other 256
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) fxd::mbar_init(&sm.mbar_idx[i], 1);
@@ -342,7 +341,7 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma_kernel(const UmmaParams p) {
                     tc_fence_after();
                     for (int t = 0; t < 4; ++t) {
                         if (t < ntile2)
-                            issue_conv_tile(a1_addr, pl1_bytes, uw2_addr, K, t * 128, tmem_base + (uint32_t)(t * 32),
+                            issue_conv_tile(a1_addr, pl1_bytes, uw2_addr, K, t * 128, tmem_base + (uint32_t)(t * 64),
                                             p.swap_lbo_sbo != 0);
                         umma_commit(&sm.mbar_c2[t]);
                     }
@@ -354,8 +353,11 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma_kernel(const UmmaParams p) {
                         fxd::mbar_wait(&sm.mbar_c2[t], par);
                         pt[2] += clock64() - w0;
                         tc_fence_after();
-                        uint32_t v[16];
-                        tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(t * 32 + ch * 16), v);
+                        uint32_t v[16], vlo[16];
+                        tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(t * 64 + ch * 16), v);
+                        tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(t * 64 + 32 + ch * 16), vlo);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(vlo[i]));
                         const int r = t * 128 + lq * 32 + lane;  // A2 row
                         const int rho = c0 - pl3 + r;
                         const int sh = rho + 4 * P;
@@ -385,7 +387,7 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma_kernel(const UmmaParams p) {
                     tc_fence_after();
                     for (int t = 0; t < 4; ++t) {
                         if (t < ntile3)
-                            issue_conv_tile(a2_addr, pl2_bytes, uw3_addr, K3, t * 128, tmem_base + 128u + (uint32_t)(t * 32),
+                            issue_conv_tile(a2_addr, pl2_bytes, uw3_addr, K3, t * 128, tmem_base + 256u + (uint32_t)(t * 64),
                                             p.swap_lbo_sbo != 0);
                         umma_commit(&sm.mbar_c3[t]);
                     }
@@ -397,8 +399,11 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma_kernel(const UmmaParams p) {
                         fxd::mbar_wait(&sm.mbar_c3[t], par);
                         pt[4] += clock64() - w0;
                         tc_fence_after();
-                        uint32_t v[16];
-                        tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + 128u + (uint32_t)(t * 32 + ch * 16), v);
+                        uint32_t v[16], vlo[16];
+                        tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + 256u + (uint32_t)(t * 64 + ch * 16), v);
+                        tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + 256u + (uint32_t)(t * 64 + 32 + ch * 16), vlo);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(vlo[i]));
                         const int r = t * 128 + lq * 32 + lane;  // output row of this chunk
                         const int rho = c0 + r;
                         const int s = rho / P;
@@ -496,7 +501,7 @@ bool cnn_umma_supported(const flexs_model *m) {
     return plan(m, p);
 }
 
-// Re-lay conv2/conv3 weights of every member as fp16 hi/lo UMMA planes [tap][split][chunk][filter][8 ch].
+// Re-lay conv2/conv3 weights of every member as fp16 UMMA planes [tap][chunk][hi filters | lo filters][8 ch].
 int prepare_cnn_umma(flexs_model *m) {
     if (m->umma_ready) return FLEXS_OK;
     UmmaParams p;
@@ -530,9 +535,9 @@ int prepare_cnn_umma(flexs_model *m) {
                         const float v = src[((size_t)j * F + g) * F + f] * scale;
                         const __half hi = __float2half_rn(v);
                         const __half lo = __float2half_rn(v - __half2float(hi));
-                        const size_t base = ((size_t)(j * 2) * 4 + (g >> 3)) * (WPLANE / 2) + (size_t)f * 8 + (g & 7);
-                        planes[base] = hi;
-                        planes[base + 4 * (WPLANE / 2)] = lo;
+                        const size_t base = ((size_t)j * 4 + (g >> 3)) * (WPLANE / 2) + (g & 7);
+                        planes[base + (size_t)f * 8] = hi;
+                        planes[base + (size_t)(32 + f) * 8] = lo;
                     }
         }
         float *tail = reinterpret_cast<float *>(dst + (size_t)(K + K3) * 2 * WTAP);
