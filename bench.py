@@ -418,7 +418,10 @@ def main():
             line["cpu_baseline"] = None
         others = {}
         for tag, (L, A, members, batch) in {"tfbind8_cnn_1M (configs[1])": (8, 4, 1, 1 << 20),
-                                            "rna14_ens3cnn_1M (configs[2])": (14, 4, 3, 1 << 20)}.items():
+                                            "rna14_ens3cnn_1M (configs[2])": (14, 4, 3, 1 << 20),
+                                            "aav735_cnn (configs[3], per-GPU shard)": (735, 20, 1, 1 << 15),
+                                            "aav90_cnn (AAV registry window)": (90, 20, 1, 1 << 18),
+                                            "gfp237_cnn (configs[4], per-GPU shard)": (237, 20, 1, 1 << 17)}.items():
             sc = Screen(L, A, F_NS, H_NS, K_NS, members, batch, rank, world, device)
             sc.model.set_variant(variant)
             oms, _ = timed_steps(sc, max(3, args.steps), args.warmup, world, device)
@@ -426,7 +429,8 @@ def main():
             others[tag] = {"value": world * batch * st / (oms / 1e3), "unit": UNIT, "ms_per_step": oms / st,
                            "kernel_ms": float(np.mean(sc.fwd_ms)), "members": members,
                            "achieved_tflops": members * flop_alg(L, A, F_NS, H_NS, K_NS) * batch / (np.mean(sc.fwd_ms) / 1e3) / 1e12,
-                           "note": "batch fits in L2 (input re-read from L2 between steps); compute-bound, so unaffected"}
+                           "kernel": _native.VARIANT_NAMES[sc.model.active_variant(batch)],
+                           "note": "input <= L2 size (re-read from L2 between steps); compute-bound path, so unaffected"}
             del sc
         line["other_workloads"] = others
     if world > 1:

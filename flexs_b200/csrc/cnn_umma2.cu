@@ -521,6 +521,16 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma2_kernel(const U2Params p) {
                         // GlobalMaxPooling1D over the rows of each sequence present in this warp: one REDUX per
                         // filter, lane q keeps filter q, then a single 16-address shared atomic per sequence
                         unsigned todo = (p.dbg & 1) ? 0u : __ballot_sync(0xffffffffu, valid);
+                        if (P < 48) {
+                            // short sequences: a tile holds many of them, each owning only a lane or two of this warp,
+                            // so per-lane shared atomics (<= 2-way conflicts) beat one REDUX round per sequence
+                            if (valid && todo) {
+                                unsigned int *dst = reinterpret_cast<unsigned int *>(featT) + (size_t)(ch * 16) * p.sbp + c.slot0 + s;
+#pragma unroll
+                                for (int q = 0; q < 16; ++q) atomicMax(dst + (size_t)q * p.sbp, bits[q]);
+                            }
+                            todo = 0;
+                        }
                         while (todo) {
                             const int leader = __ffs(todo) - 1;
                             const int s_l = __shfl_sync(0xffffffffu, s, leader);

@@ -477,3 +477,24 @@ def test_fp16_range_guard_falls_back_to_fp32_kernel():
             assert np.isfinite(got).all()
             assert rel_err(got, ref, _floor(ref)) < TOL, (L, A, v)
         m.close()
+
+
+def test_virtual_screen_single_rank_matches_numpy():
+    """flexs_b200.screen.VirtualScreen (the sharded top-k of the path) on one rank: same winners, same order and
+    scores as np.argsort over get_fitness; with >= 2 GPUs the NCCL form is covered by bench.py --gpus N."""
+    import flexs_b200 as flexs
+    from flexs_b200.screen import VirtualScreen
+
+    L, n, B = 14, 5000, 100
+    ens = flexs.Ensemble([flexs.baselines.models.CNN(L, 32, 100, su.RNAA, seed=i) for i in range(3)])
+    seqs = np.array(su.generate_random_sequences(L, n, su.RNAA))
+    scores = ens.get_fitness(seqs)
+    screen = VirtualScreen(ens, k=B - 1)          # the [: -B : -1] slice keeps B-1
+    top_seqs, top_scores = screen.screen(seqs)
+    order = np.lexsort((np.arange(n), -scores.astype(np.float64)))[: B - 1]
+    np.testing.assert_array_equal(top_seqs, seqs[order])
+    np.testing.assert_array_equal(top_scores, scores[order])
+    assert ens.cost == 2 * n and all(m.cost == 2 * n for m in ens.models)
+    # tie-free batches agree with the reference's own slice
+    if len(np.unique(scores)) == n:
+        np.testing.assert_array_equal(top_seqs, seqs[np.argsort(scores)[: -B: -1]])
