@@ -315,8 +315,23 @@ def run_reference(args, rank):
 
     from oracle import ref_path
 
-    # torchrun exports OMP_NUM_THREADS=1; the reference arm is entitled to every host core
-    torch.set_num_threads(os.cpu_count() or 1)
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm is entitled to every host core.  Batch-256 convolutions
+    # do not scale to 128 threads (oversubscription makes them slower), so pick the thread count that maximises the
+    # reference's own throughput on a probe, as TF's intra-op pool sizing would.
+    ncpu = os.cpu_count() or 1
+    probe_w = make_weights(cnn_shapes(L_NS, A_NS, F_NS, H_NS, K_NS), 0)
+    probe_seqs = ["".join("TGCA"[i] for i in row) for row in np.random.default_rng(7).integers(0, 4, size=(1024, L_NS))]
+    best_threads, best_rate = 1, 0.0
+    for nthreads in sorted({1, 4, 8, 16, 32, 64, ncpu}):
+        if nthreads > ncpu:
+            continue
+        torch.set_num_threads(nthreads)
+        probe = ref_path.ReferenceCNN(L_NS, "TGCA", F_NS, H_NS, K_NS, probe_w)
+        probe.get_fitness(probe_seqs[:256])
+        t0 = time.perf_counter(); probe.get_fitness(probe_seqs); rate = len(probe_seqs) / (time.perf_counter() - t0)
+        if rate > best_rate:
+            best_threads, best_rate = nthreads, rate
+    torch.set_num_threads(best_threads)
     model = ref_path.ReferenceCNN(L_NS, "TGCA", F_NS, H_NS, K_NS, make_weights(cnn_shapes(L_NS, A_NS, F_NS, H_NS, K_NS), 0))
     n = 4096
     rng = np.random.default_rng(1234)
