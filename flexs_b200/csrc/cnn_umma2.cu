@@ -74,7 +74,8 @@ constexpr int OFF_SCAL = OFF_T34 + 16 * F * 4;
 constexpr int DH = 112, DN = 2 * DH, DSLOTS = 128, DPLANE = DSLOTS * 16, DBK = DN * 16;
 constexpr int OFF_DB1 = (OFF_SCAL + 16 + 255) / 256 * 256, OFF_DB2 = OFF_DB1 + 4 * DBK, OFF_DV = OFF_DB2 + 14 * DBK;
 constexpr int DV_FLOATS = 3 * DH + 4;  // bd1*ASCALE | bd2 | wd3 | inv_d1s, inv_d2, bd3
-constexpr int UW_MEMBER_BYTES = (OFF_DV + DV_FLOATS * 4 + 255) / 256 * 256;
+constexpr int OFF_TBIG = (OFF_DV + DV_FLOATS * 4 + 255) / 256 * 256;  // 4^5 entries x (4 chunks hi | 4 chunks lo) x 16 B
+constexpr int UW_MEMBER_BYTES = OFF_TBIG + 1024 * 128;
 // dense scratch inside the (idle) activation buffers
 constexpr int DS_X1 = 0, DS_B1 = DS_X1 + 8 * DPLANE, DS_X2 = DS_B1 + 4 * DBK, DS_B2 = DS_X2 + 28 * DPLANE;
 constexpr int DS_PART = DS_B2 + 14 * DBK, DS_DV = DS_PART + 2 * DSLOTS * 4, DS_TOTAL = DS_DV + (DV_FLOATS * 4 + 15) / 16 * 16;
@@ -301,6 +302,7 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma2_kernel(const U2Params p) {
     for (int mem = 0; mem < p.M; ++mem) {
         const float *w = p.weights + (int64_t)mem * p.member_floats;
         const unsigned char *uw = p.uw + (int64_t)mem * p.uw_member_bytes;
+        const unsigned char *tbig = uw + OFF_TBIG;  // conv1 as a single gather (global, L2-resident, 128 KB)
         const float inv2s = __ldg(reinterpret_cast<const float *>(uw + OFF_SCAL));
         const float inv3 = __ldg(reinterpret_cast<const float *>(uw + OFF_SCAL) + 1);
         __syncthreads();
@@ -355,7 +357,14 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma2_kernel(const U2Params p) {
                                           ((reinterpret_cast<uintptr_t>(p.idx) + (uintptr_t)(c.first * L)) & 15);
                     // One unit = 32 MMA rows of a tile (lane -> row i = 8a + b -> conv position 16b + a, so a warp's
                     // 16-byte stores are contiguous), plus one last unit for the k-1 rows behind the last tile.
+                    // A row of h1 is ONE 128-byte entry of a 4^5-entry table (bias, ReLU, activation scale and the fp16
+                    // hi/lo split folded in at prepare time) gathered from L2: no shared-memory table reads compete with
+                    // the tensor core's operand stream.  A warp owns up to three units and issues all their gathers
+                    // before the first store, so the L2 latency is paid once per chunk, not once per unit.
+                    // The gathers are cp.async (LDGSTS) 16-byte copies straight into the operand planes: no registers,
+                    // no shared-memory table reads, and every unit of the warp is in flight before the first one lands.
                     const int nunits = c.ntile2 * 4 + 1;
+                    const uint32_t a1s = a1_addr;
                     for (int u = pw; u < nunits; u += NPROD) {
                         int tile, a, b;
                         if (u < c.ntile2 * 4) {
@@ -365,50 +374,34 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma2_kernel(const U2Params p) {
                             if (lane >= K - 1) continue;
                             tile = c.ntile2; a = lane; b = 0;
                         }
-                        const int r = tile * 128 + 16 * b + a;  // chunk-local h1 row
-                        const int rho = c.c0 - pl3 - pl2 + r;
-                        int s = (rho >= 0 && rho < c.rows_item) ? rowseq[rho] : 0xFF;
-                        if (p.dbg & 2) { if (lane || u) continue; s = 0xFF; }
-                        // slots of this row inside a plane: main copy and (for a < k-1) the wrap copy
-                        const int main_off = (tile < NTILE) ? tile * TS1 + a * 128 + b * 16 : -1;
-                        int wrap_off = -1;
+                        const int rho = c.c0 - pl3 - pl2 + tile * 128 + 16 * b + a;
+                        const int s = (rho >= 0 && rho < c.rows_item) ? rowseq[rho] : 0xFF;
+                        const int moff = (tile < NTILE) ? tile * TS1 + a * 128 + b * 16 : -1;
+                        int woff = -1;
                         if (a < WR1) {
                             const int tt = (b == 0) ? tile - 1 : tile, bb = (b == 0) ? 7 : b - 1;
-                            if (tt >= 0 && tt < NTILE) wrap_off = tt * TS1 + (16 + a) * 128 + bb * 16;
+                            if (tt >= 0 && tt < NTILE) woff = tt * TS1 + (16 + a) * 128 + bb * 16;
                         }
-                        // h1 row = relu(T012[a0,a1,a2] + T34[a3,a4]) (bias and activation scale folded into the tables).
-                        // A single 4^5-entry table in L2 was measured slower (L2 latency under load: 3.4k cycles per
-                        // 32-row unit vs 2k for the two padded smem tables).
-                        int i012 = 0, i34 = 0;
-                        if (s != 0xFF) {
+                        const unsigned char *tp = tbig;
+                        uint32_t nbytes = 0;                       // 0 -> cp.async zero-fills (halo / padding rows)
+                        if (s != 0xFF && !(p.dbg & 2)) {
                             const uint8_t *ip = sidx + s * L + (rho - s * P - hl);
-                            i012 = (ip[0] * ALPHA + ip[1]) * ALPHA + ip[2];
-                            i34 = ip[3] * ALPHA + ip[4];
+                            const int i5 = ((((ip[0] * ALPHA + ip[1]) * ALPHA + ip[2]) * ALPHA + ip[3]) * ALPHA) + ip[4];
+                            tp = tbig + (size_t)i5 * 128;
+                            nbytes = 16;
                         }
-                        const float4 *ta = reinterpret_cast<const float4 *>(t012 + i012 * TP);
-                        const float4 *tb = reinterpret_cast<const float4 *>(t34 + i34 * TP);
 #pragma unroll
-                        for (int cc = 0; cc < 4; ++cc) {
-                            float x[8];
-                            const float4 u0 = ta[2 * cc], u1 = ta[2 * cc + 1], v0 = tb[2 * cc], v1 = tb[2 * cc + 1];
-                            x[0] = fmaxf(u0.x + v0.x, 0.f); x[1] = fmaxf(u0.y + v0.y, 0.f);
-                            x[2] = fmaxf(u0.z + v0.z, 0.f); x[3] = fmaxf(u0.w + v0.w, 0.f);
-                            x[4] = fmaxf(u1.x + v1.x, 0.f); x[5] = fmaxf(u1.y + v1.y, 0.f);
-                            x[6] = fmaxf(u1.z + v1.z, 0.f); x[7] = fmaxf(u1.w + v1.w, 0.f);
-                            uint4 hi4, lo4;
-                            split8(x, hi4, lo4, xmax);
-                            if (s == 0xFF) { hi4 = make_uint4(0, 0, 0, 0); lo4 = hi4; }
-                            unsigned char *ph = a1 + (size_t)cc * PL1, *plo = ph + (size_t)4 * PL1;
-                            if (main_off >= 0) {
-                                *reinterpret_cast<uint4 *>(ph + main_off) = hi4;
-                                *reinterpret_cast<uint4 *>(plo + main_off) = lo4;
-                            }
-                            if (wrap_off >= 0) {
-                                *reinterpret_cast<uint4 *>(ph + wrap_off) = hi4;
-                                *reinterpret_cast<uint4 *>(plo + wrap_off) = lo4;
-                            }
+                        for (int q = 0; q < 8; ++q) {
+                            const uint32_t plane = a1s + (uint32_t)q * PL1;   // q = 0..3 hi chunks, 4..7 lo chunks
+                            if (moff >= 0)
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(plane + moff), "l"(tp + q * 16),
+                                             "r"(nbytes) : "memory");
+                            if (woff >= 0)
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(plane + woff), "l"(tp + q * 16),
+                                             "r"(nbytes) : "memory");
                         }
                     }
+                    asm volatile("cp.async.wait_all;" ::: "memory");
                     const long long q3 = clock64();
                     fence_async_smem();
                     __syncwarp();
@@ -777,6 +770,20 @@ static int prepare(flexs_model *m, const U2Params &p) {
             for (int a4 = 0; a4 < ALPHA; ++a4)
                 for (int f = 0; f < F; ++f)
                     t34[(a3 * ALPHA + a4) * F + f] = (w1[(3 * ALPHA + a3) * F + f] + w1[(4 * ALPHA + a4) * F + f]) * ASCALE;
+        {   // conv1 as one gather: entry[a0..a4] = split(relu(T012 + T34)) for all 32 channels
+            __half *tb = reinterpret_cast<__half *>(dst + OFF_TBIG);
+            for (int i5 = 0; i5 < 1024; ++i5) {
+                const int i012 = i5 >> 4, i34 = i5 & 15;
+                for (int f = 0; f < F; ++f) {
+                    const float x = std::max(t012[i012 * F + f] + t34[i34 * F + f], 0.f);
+                    if (!(x <= 60000.f)) m->umma_weights_ok = false;  // beyond the fp16 window (or NaN): fp32 kernel
+                    const __half hi = __float2half_rn(x);
+                    const __half lo = __float2half_rn(x - __half2float(hi));
+                    tb[(size_t)i5 * 64 + (f >> 3) * 8 + (f & 7)] = hi;
+                    tb[(size_t)i5 * 64 + 32 + (f >> 3) * 8 + (f & 7)] = lo;
+                }
+            }
+        }
         float *tail = reinterpret_cast<float *>(dst + OFF_SCAL);
         tail[0] = inv[0] * ASCALE;  // conv2 epilogue emits activations pre-scaled by ASCALE
         tail[1] = inv[1];
