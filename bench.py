@@ -46,6 +46,70 @@ def flop_alg(L, A, F, H, K):
     return T * F * K + 2 * (T * F * K * F + T * F * K3 * F + F * H + H * H + H)
 
 
+def plugin_api_timings(device):
+    """The two other calls an explorer makes through the drop-in classes, wall clock:
+    AdaLead's ``model.get_fitness`` on eval_batch_size=20 strings (adalead.py:123) and ``model.train`` on a round's
+    history (explorer.py:157; 1000 sequences, batch 256, 20 epochs = 80 Adam steps)."""
+    import torch
+
+    import flexs_b200 as flexs
+
+    rng = np.random.default_rng(7)
+    out = {}
+    for tag, L, alphabet in (("cnn_100x4", 100, "ACGT"), ("cnn_237x20", 237, "ACDEFGHIKLMNPQRSTVWY")):
+        model = flexs.baselines.models.CNN(L, num_filters=F_NS, hidden_size=H_NS, alphabet=alphabet,
+                                           loss="MSE", device=device.index or 0, seed=0)
+        letters = np.array(list(alphabet))
+        seqs = ["".join(r) for r in letters[rng.integers(0, len(alphabet), size=(1000, L))]]
+        labels = rng.random(1000)
+        model.train(seqs[:64], labels[:64])          # warm-up: workspace allocation
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        model.train(seqs, labels)
+        fit_s = time.perf_counter() - t0
+        small = seqs[:20]
+        for _ in range(5):
+            model.get_fitness(small)
+        lat = []
+        for _ in range(50):
+            t0 = time.perf_counter()
+            model.get_fitness(small)
+            lat.append(time.perf_counter() - t0)
+        out[tag] = {"train_1000seq_20epochs_s": fit_s, "train_ms_per_adam_step": fit_s / 80 * 1e3,
+                    "get_fitness_20seq_latency_us_median": float(np.median(lat) * 1e6),
+                    "get_fitness_20seq_latency_us_p90": float(np.quantile(lat, 0.9) * 1e6)}
+        del model
+    out["table_landscapes"] = landscape_timings(device)
+    return out
+
+
+def landscape_timings(device):
+    """K6: the additive AAV landscape on device-resident candidates, CUDA events.
+    HBM-bound byte work: 90 B read + 8 B written per sequence."""
+    import torch
+
+    import flexs_b200 as flexs
+
+    fixture = REPO / "tests" / "golden" / "aav_450_540_subs.json"
+    if not fixture.exists():
+        return None
+    land = flexs.landscapes.AdditiveAAVPackaging(phenotype="heart", start=450, end=540, data_file=str(fixture),
+                                                 device=device.index or 0)
+    n = 1 << 22
+    cols = torch.randint(0, len(land.residues), (n, land.seq_len), dtype=torch.uint8, device=device)
+    for _ in range(3):
+        land.get_fitness_device(cols, columns=True)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(5):
+        land.get_fitness_device(cols, columns=True)
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / 5
+    return {"additive_aav_90mer": {"value": n / (ms / 1e3), "unit": UNIT, "kernel_ms": ms,
+                                   "hbm_gbs_alg": n * (land.seq_len + 8) / (ms / 1e3) / 1e9, "dtype": "f64"}}
+
+
 def load_peaks():
     path = REPO / "MEASURED_PEAKS.json"
     if path.exists():
@@ -448,6 +512,8 @@ def main():
                            "note": "input <= L2 size (re-read from L2 between steps); compute-bound path, so unaffected"}
             del sc
         line["other_workloads"] = others
+        if rank == 0:
+            line["plugin_api"] = plugin_api_timings(device)
     if world > 1:
         import torch.distributed as dist
 

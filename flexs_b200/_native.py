@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_uint8, c_uint64, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_uint8, c_uint64, c_void_p
 from pathlib import Path
 from typing import List, Optional, Sequence
 
@@ -47,6 +47,9 @@ _SIGNATURES = [
     ("flexs_model_train_step_dev", c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, POINTER(c_float), c_void_p]),
     ("flexs_model_get_optimizer_state", c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64)]),
     ("flexs_model_reset_optimizer", c_int, [c_void_p]),
+    ("flexs_additive_score_dev", c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_double, c_double, c_void_p,
+                                         c_void_p, c_void_p]),
+    ("flexs_lookup_score_dev", c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
 ]
 
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
@@ -248,3 +251,28 @@ def argmax_decode_dev(d_x: int, n: int, seq_len: int, row_stride: int, alphabet_
                       stream: int = 0) -> None:
     check(lib().flexs_argmax_decode_dev(c_void_p(d_x), n, seq_len, row_stride, alphabet_size, c_void_p(d_idx),
                                         c_void_p(stream)), "argmax_decode")
+
+
+def _column_table(column_of_char: Optional[np.ndarray]):
+    if column_of_char is None:
+        return None, c_void_p(0)
+    lut = np.ascontiguousarray(column_of_char, dtype=np.uint8)
+    if lut.shape != (256,):
+        raise ValueError("column_of_char must be uint8[256]")
+    return lut, lut.ctypes.data_as(c_void_p)
+
+
+def additive_score_dev(d_seq: int, n: int, seq_len: int, column_of_char: Optional[np.ndarray], ncols: int, d_table: int,
+                       offset: float, denom: float, d_noise: int, d_out: int, stream: int = 0) -> None:
+    """K6 additive table landscape (additive_aav_packaging.py:101-118) on device buffers."""
+    keep, ptr = _column_table(column_of_char)
+    check(lib().flexs_additive_score_dev(c_void_p(d_seq), n, seq_len, ptr, ncols, c_void_p(d_table), offset, denom,
+                                         c_void_p(d_noise), c_void_p(d_out), c_void_p(stream)), "additive_score")
+
+
+def lookup_score_dev(d_seq: int, n: int, seq_len: int, column_of_char: Optional[np.ndarray], base: int, d_table: int,
+                     table_len: int, d_out: int, stream: int = 0) -> None:
+    """K6 dictionary landscape (tf_binding.py:43-44) as a dense table on device buffers."""
+    keep, ptr = _column_table(column_of_char)
+    check(lib().flexs_lookup_score_dev(c_void_p(d_seq), n, seq_len, ptr, base, c_void_p(d_table), table_len,
+                                       c_void_p(d_out), c_void_p(stream)), "lookup_score")

@@ -346,9 +346,6 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma2_kernel(const U2Params p) {
                     if (c.n > 0) fxd::mbar_wait(&c2[NTILE - 1], (c.n - 1) & 1);  // A1 free again
                     const long long q1 = clock64();
                     if (c.first_chunk) {
-                        const int64_t next = c.item + gridDim.x;
-                        if (ptid == 0 && next < p.n_items)
-                            issue_idx_load(p, smem_raw + (buf ? of.i0 : of.i1), &mbar_idx[buf ^ 1], next);
                         for (int i = ptid; i < c.s_item; i += NPROD * 32) slot_seq[c.slot0 + i] = c.first + i;
                         fxd::mbar_wait(&mbar_idx[buf], (c.iter >> 1) & 1);
                     }
@@ -549,6 +546,16 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma2_kernel(const U2Params p) {
                 // =========================== MMA issuer ===========================
                 walk_group(p, item, g_end, n, iter, [&](const Chunk &c) {
                     const uint32_t par = c.n & 1;
+                    if (c.first_chunk) {
+                        // Prefetch the next item's residues into the other slot: its last readers (conv1 of the previous
+                        // item) arrived on a1_full before this warp got here.  Issued from this warp because it is about
+                        // to wait anyway; on a producer warp the bulk-copy issue cost ~0.8k cycles of the critical path.
+                        const int64_t next = c.item + gridDim.x;
+                        const int buf = c.iter & 1;
+                        if (lane == 0 && next < p.n_items)
+                            issue_idx_load(p, smem_raw + (buf ? of.i0 : of.i1), &mbar_idx[buf ^ 1], next);
+                        __syncwarp();
+                    }
                     const long long m0 = clock64();
                     fxd::mbar_wait(a1_full, par);
                     const long long m1 = clock64();

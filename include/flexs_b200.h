@@ -171,6 +171,31 @@ int flexs_model_get_optimizer_state(flexs_model_t *m, int member, float *const *
 /* Forget the optimiser state of every member (a freshly compiled Keras model).                  */
 int flexs_model_reset_optimizer(flexs_model_t *m);
 
+/* ---- K6: table landscapes ------------------------------------------
+ * Ground-truth landscapes that are pure tables, evaluated on the device so a whole explorer
+ * round can stay there.  d_seq is uint8[n, seq_len]: residue CHARACTERS when h_column_of_char
+ * (256 host bytes: table column of each character, 0xFF = none) is non-NULL, else column
+ * indices.  Outputs are float64, like the reference's.
+ *
+ * flexs_additive_score_dev replaces AdditiveAAVPackaging._fitness_function
+ * (flexs/landscapes/additive_aav_packaging.py:101-118):
+ *   out = max(0, (sum_i table[i, col(seq[i])] + offset) / denom + noise)
+ * with offset = mfm * max_possible, denom = max_possible * (mfm + 1); characters without a
+ * column contribute nothing (:104); the sum runs left to right in float64, bit-identical to the
+ * reference's Python loop.  d_table float64[seq_len, ncols]; d_noise float64[n] or NULL.
+ *
+ * flexs_lookup_score_dev replaces TFBinding._fitness_function (flexs/landscapes/tf_binding.py:43-44):
+ * the dict of all sequences is a dense float64 table of base**seq_len entries indexed by the
+ * big-endian base-`base` number formed by the columns; a sequence with an unknown character is
+ * reported as NaN (as is a key the caller left NaN in the table) — the host raises KeyError.  */
+int flexs_additive_score_dev(const uint8_t *d_seq, int64_t n, int seq_len,
+                             const uint8_t *h_column_of_char, int ncols, const double *d_table,
+                             double offset, double denom, const double *d_noise, double *d_out,
+                             void *stream);
+int flexs_lookup_score_dev(const uint8_t *d_seq, int64_t n, int seq_len,
+                           const uint8_t *h_column_of_char, int base, const double *d_table,
+                           int64_t table_len, double *d_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
