@@ -35,13 +35,32 @@ __global__ void __launch_bounds__(LS_THREADS) additive_kernel(const uint8_t *__r
     __syncthreads();
     const double *tab = TABLE_IN_SMEM ? stab : table;
     const int64_t stride = (int64_t)gridDim.x * LS_THREADS;
+    const uintptr_t buf0 = reinterpret_cast<uintptr_t>(seq), buf1 = buf0 + (uintptr_t)(n * L);
     for (int64_t s = (int64_t)blockIdx.x * LS_THREADS + threadIdx.x; s < n; s += stride) {
-        const uint8_t *p = seq + s * L;
+        // A thread streams its own sequence in aligned 16-byte words (both halves of every 32-byte sector are used by
+        // consecutive loads of the same thread), not byte by byte: byte loads at a 90-byte lane stride cost a sector each.
+        const uintptr_t g0 = reinterpret_cast<uintptr_t>(seq) + (uintptr_t)(s * L), g1 = g0 + (uintptr_t)L;
         double total = 0.0;
-        for (int i = 0; i < L; ++i) {
-            const int c = scol[__ldg(p + i)];
-            // `if s in self.data[pos]: total_fitness += ...` (additive_aav_packaging.py:103-105)
-            if (c != 0xFF) total = __dadd_rn(total, TABLE_IN_SMEM ? tab[i * ncols + c] : __ldg(tab + i * ncols + c));
+        for (uintptr_t wa = g0 & ~(uintptr_t)15; wa < g1; wa += 16) {
+            uint32_t w4[4] = {0u, 0u, 0u, 0u};
+            if (wa >= buf0 && wa + 16 <= buf1) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4 *>(wa));
+                w4[0] = q.x; w4[1] = q.y; w4[2] = q.z; w4[3] = q.w;
+            } else {  // the word straddles an end of the buffer: stay inside it
+                for (int k = 0; k < 16; ++k) {
+                    const uintptr_t ga = wa + (uintptr_t)k;
+                    if (ga >= buf0 && ga < buf1) w4[k >> 2] |= (uint32_t)__ldg(reinterpret_cast<const uint8_t *>(ga)) << (8 * (k & 3));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const uintptr_t ga = wa + (uintptr_t)k;
+                if (ga < g0 || ga >= g1) continue;
+                const int i = (int)(ga - g0);
+                const int c = scol[(w4[k >> 2] >> (8 * (k & 3))) & 0xFF];
+                // `if s in self.data[pos]: total_fitness += ...` (additive_aav_packaging.py:103-105)
+                if (c != 0xFF) total = __dadd_rn(total, TABLE_IN_SMEM ? tab[i * ncols + c] : __ldg(tab + i * ncols + c));
+            }
         }
         // (raw + mfm * max_possible) / (max_possible * (mfm + 1)) + noise, then max(0, .)   (:107, :112-116)
         double f = __ddiv_rn(__dadd_rn(total, offset), denom);

@@ -5,8 +5,10 @@
 // compiled Keras model's (explorer.py:157-160 retrains every round on the whole history).
 //
 // The data set is at most ~1000 measured sequences (B-1 per round), so this is a latency problem, not
-// a throughput one: every layer is a plain deterministic kernel over global memory (no atomics — the
-// reductions loop inside a thread), the whole fit runs on one stream with a single sync at the end.
+// a throughput one: 80 optimiser steps of ~25 small launches on one stream with a single sync at the
+// end.  Everything is deterministic (no atomics).  The reductions over (sample, position) — the conv
+// weight/bias gradients — are two-stage: one CTA per sample group accumulates its partial sums in shared
+// memory tiles, then a second kernel adds the partials in fixed group order.
 #include <algorithm>
 #include <cmath>
 #include <random>
@@ -203,69 +205,6 @@ __global__ void k_gmax_bwd(const float *h3, const int *am, const float *gp, floa
     }
 }
 
-// conv weight gradient: gw[j,g,f] = sum_{b,t} x[b,t+j-pl,g] * gz[b,t,f]; gb[f] = sum_{b,t} gz[b,t,f]
-__global__ void k_conv_bwd_w(const float *x, const float *gz, float *gw, float *gb, int B, int T, int F, int K, int pl) {
-    const int64_t total = (int64_t)K * F * F + F, stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-        float acc = 0.f;
-        if (e < (int64_t)K * F * F) {
-            const int f = (int)(e % F), g = (int)((e / F) % F), j = (int)(e / ((int64_t)F * F));
-            for (int b = 0; b < B; ++b)
-                for (int t = 0; t < T; ++t) {
-                    const int s = t + j - pl;
-                    if (s < 0 || s >= T) continue;
-                    acc = fmaf(x[((size_t)b * T + s) * F + g], gz[((size_t)b * T + t) * F + f], acc);
-                }
-            gw[e] = acc;
-        } else {
-            const int f = (int)(e - (int64_t)K * F * F);
-            for (int64_t q = 0; q < (int64_t)B * T; ++q) acc += gz[q * F + f];
-            gb[f] = acc;
-        }
-    }
-}
-
-// conv data gradient fused with the producer's ReLU: gx[b,s,g] = (x[b,s,g] > 0) * sum_j sum_f gz[b,s-j+pl,f] * w[j,g,f]
-__global__ void k_conv_bwd_x(const float *x, const float *w, const float *gz, float *gx, int B, int T, int F, int K, int pl) {
-    const int64_t total = (int64_t)B * T * F, stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-        const int g = (int)(e % F), s = (int)((e / F) % T), b = (int)(e / ((int64_t)F * T));
-        float acc = 0.f;
-        if (x[e] > 0.f) {
-            for (int j = 0; j < K; ++j) {
-                const int t = s - j + pl;
-                if (t < 0 || t >= T) continue;
-                const float *gr = gz + ((size_t)b * T + t) * F;
-                const float *wr = w + ((size_t)j * F + g) * F;
-                for (int f = 0; f < F; ++f) acc = fmaf(gr[f], wr[f], acc);
-            }
-        }
-        gx[e] = acc;
-    }
-}
-
-// conv1 (one-hot input): gw1[j,a,f] = sum_{b,t : idx[b,t+j]==a} gz1[b,t,f]; gb1[f] = sum gz1
-__global__ void k_conv1_bwd_w(const uint8_t *idx, const int *perm, const float *gz1, float *gw1, float *gb1, int B, int L,
-                              int A, int T, int F, int K) {
-    const int64_t total = (int64_t)K * A * F + F, stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-        float acc = 0.f;
-        if (e < (int64_t)K * A * F) {
-            const int f = (int)(e % F), a = (int)((e / F) % A), j = (int)(e / ((int64_t)F * A));
-            for (int b = 0; b < B; ++b) {
-                const uint8_t *ip = idx + src_row(perm, b) * L + j;
-                for (int t = 0; t < T; ++t)
-                    if (ip[t] == a) acc += gz1[((size_t)b * T + t) * F + f];
-            }
-            gw1[e] = acc;
-        } else {
-            const int f = (int)(e - (int64_t)K * A * F);
-            for (int64_t q = 0; q < (int64_t)B * T; ++q) acc += gz1[q * F + f];
-            gb1[f] = acc;
-        }
-    }
-}
-
 // MLP layer-1 weight gradient: gw1[l*A+a, o] = sum_{b : idx[b,l]==a} gu1[b,o]; gb1[o] = sum_b gu1[b,o]
 __global__ void k_gather_bwd_w(const uint8_t *idx, const int *perm, const float *gu1, float *gw1, float *gb1, int B, int L,
                                int A, int H) {
@@ -282,6 +221,142 @@ __global__ void k_gather_bwd_w(const uint8_t *idx, const int *perm, const float 
         } else {
             for (int b = 0; b < B; ++b) acc += gu1[(size_t)b * H + o];
             gb1[o] = acc;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- two-stage (sample-group) gradient kernels
+constexpr int GROUPS_MAX = 296;   // partial-sum slots: 2 CTAs per SM
+constexpr int TCHUNK = 128;       // positions per shared-memory tile
+
+// Stage 1 of the conv weight/bias gradient.  CTA `grp` owns samples grp, grp+G, ... and writes
+//   part[grp][j,g,f] = sum_{b in group} sum_t x[b,t+j-pl,g] * gz[b,t,f],   part[grp][K*F*F + f] = sum gz[b,t,f]
+// x and gz tiles (TCHUNK positions, x with a K-1 halo, zero outside [0,T)) are staged in shared memory.
+__global__ void __launch_bounds__(TPB) k_conv_bwd_w_part(const float *__restrict__ x, const float *__restrict__ gz,
+                                                         float *__restrict__ part, int B, int T, int F, int K, int pl) {
+    extern __shared__ __align__(16) float tsm[];
+    float *xs = tsm;                                   // [(TCHUNK + K - 1)][F]
+    float *gs = tsm + (size_t)(TCHUNK + K - 1) * F;    // [TCHUNK][F]
+    const int G = gridDim.x, grp = blockIdx.x, tid = threadIdx.x;
+    const int count = K * F * F + F;
+    float *mine = part + (size_t)grp * count;
+    for (int e = tid; e < count; e += TPB) mine[e] = 0.f;
+    const bool vec = (F % 4) == 0;
+    for (int b = grp; b < B; b += G) {
+        for (int c0 = 0; c0 < T; c0 += TCHUNK) {
+            const int tc = min(TCHUNK, T - c0);
+            __syncthreads();
+            for (int e = tid; e < (tc + K - 1) * F; e += TPB) {
+                const int s = c0 - pl + e / F;
+                xs[e] = (s >= 0 && s < T) ? x[((size_t)b * T + s) * F + (e % F)] : 0.f;
+            }
+            for (int e = tid; e < tc * F; e += TPB) gs[e] = gz[((size_t)b * T + c0) * F + e];
+            __syncthreads();
+            for (int j = 0; j < K; ++j) {
+                if (vec) {
+                    const int fq = F / 4;
+                    for (int u = tid; u < F * fq; u += TPB) {
+                        const int g = u / fq, f0 = (u % fq) * 4;
+                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int t = 0; t < tc; ++t) {
+                            const float xv = xs[(t + j) * F + g];
+                            const float4 gv = *reinterpret_cast<const float4 *>(gs + t * F + f0);
+                            acc.x = fmaf(xv, gv.x, acc.x); acc.y = fmaf(xv, gv.y, acc.y);
+                            acc.z = fmaf(xv, gv.z, acc.z); acc.w = fmaf(xv, gv.w, acc.w);
+                        }
+                        float *o = mine + ((size_t)j * F + g) * F + f0;   // this thread is the only writer of these four
+                        o[0] += acc.x; o[1] += acc.y; o[2] += acc.z; o[3] += acc.w;
+                    }
+                } else {
+                    for (int u = tid; u < F * F; u += TPB) {
+                        const int g = u / F, f = u % F;
+                        float acc = 0.f;
+                        for (int t = 0; t < tc; ++t) acc = fmaf(xs[(t + j) * F + g], gs[t * F + f], acc);
+                        mine[((size_t)j * F + g) * F + f] += acc;
+                    }
+                }
+            }
+            for (int f = tid; f < F; f += TPB) {
+                float acc = 0.f;
+                for (int t = 0; t < tc; ++t) acc += gs[t * F + f];
+                mine[(size_t)K * F * F + f] += acc;
+            }
+        }
+    }
+}
+
+// Stage 1 of the conv1 (one-hot input) gradient: part[grp][j,a,f] = sum_{b,t : idx[b,t+j]==a} gz1[b,t,f]; then gb1.
+// Thread (j,f) is the only writer of column [j][.][f] of the shared accumulator, so the scatter needs no atomics.
+__global__ void __launch_bounds__(TPB) k_conv1_bwd_w_part(const uint8_t *__restrict__ idx, const int *__restrict__ perm,
+                                                          const float *__restrict__ gz1, float *__restrict__ part, int B,
+                                                          int L, int A, int T, int F, int K) {
+    extern __shared__ __align__(16) float tsm[];   // [K][A][F] + [F]
+    const int G = gridDim.x, grp = blockIdx.x, tid = threadIdx.x;
+    const int count = K * A * F + F;
+    for (int e = tid; e < count; e += TPB) tsm[e] = 0.f;
+    __syncthreads();
+    for (int u = tid; u < K * F; u += TPB) {
+        const int j = u / F, f = u % F;
+        float bsum = 0.f;
+        for (int b = grp; b < B; b += G) {
+            const uint8_t *ip = idx + src_row(perm, b) * L + j;
+            const float *gr = gz1 + (size_t)b * T * F + f;
+            for (int t = 0; t < T; ++t) {
+                const float v = gr[(size_t)t * F];
+                tsm[((size_t)j * A + ip[t]) * F + f] += v;
+                bsum += v;
+            }
+        }
+        if (j == 0) tsm[(size_t)K * A * F + f] = bsum;
+    }
+    __syncthreads();
+    for (int e = tid; e < count; e += TPB) part[(size_t)grp * count + e] = tsm[e];
+}
+
+// Stage 2: out[e] = part[0][e] + part[1][e] + ... in group order (fixed for a given batch size).
+__global__ void k_sum_parts(const float *__restrict__ part, int G, int count, int split, float *__restrict__ out_a,
+                            float *__restrict__ out_b) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += stride) {
+        float acc = 0.f;
+        for (int g = 0; g < G; ++g) acc += part[(size_t)g * count + e];
+        if (e < split) out_a[e] = acc; else out_b[e - split] = acc;
+    }
+}
+
+// conv data gradient fused with the producer's ReLU, one CTA per sample: weights (padded rows) and a gz tile with a
+// K-1 halo in shared memory;  gx[b,s,g] = (x[b,s,g] > 0) * sum_j sum_f gz[b,s-j+pl,f] * w[j,g,f]
+__global__ void __launch_bounds__(TPB) k_conv_bwd_x_tile(const float *__restrict__ x, const float *__restrict__ w,
+                                                         const float *__restrict__ gz, float *__restrict__ gx, int B,
+                                                         int T, int F, int K, int pl) {
+    extern __shared__ __align__(16) float tsm[];
+    const int FP = F + 1;
+    float *ws = tsm;                               // [K][F][F+1]
+    float *gs = tsm + (size_t)K * F * FP;          // [(TCHUNK + K - 1)][F], row r holds t = c0 + pl - (K-1) + r
+    const int tid = threadIdx.x;
+    for (int e = tid; e < K * F * F; e += TPB) ws[(size_t)(e / F) * FP + (e % F)] = w[e];
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        for (int c0 = 0; c0 < T; c0 += TCHUNK) {
+            const int tc = min(TCHUNK, T - c0);
+            __syncthreads();
+            for (int e = tid; e < (tc + K - 1) * F; e += TPB) {
+                const int t = c0 + pl - (K - 1) + e / F;
+                gs[e] = (t >= 0 && t < T) ? gz[((size_t)b * T + t) * F + (e % F)] : 0.f;
+            }
+            __syncthreads();
+            for (int e = tid; e < tc * F; e += TPB) {
+                const int sl = e / F, g = e % F;
+                const size_t ge = ((size_t)b * T + c0 + sl) * F + g;
+                float acc = 0.f;
+                if (x[ge] > 0.f) {
+                    for (int j = 0; j < K; ++j) {
+                        const float *gr = gs + (size_t)(sl + (K - 1) - j) * F;
+                        const float *wr = ws + ((size_t)j * F + g) * FP;
+                        for (int f = 0; f < F; ++f) acc = fmaf(gr[f], wr[f], acc);
+                    }
+                }
+                gx[ge] = acc;
+            }
         }
     }
 }
@@ -314,6 +389,8 @@ int64_t ws_floats(const flexs_model *m, int B) {
     n += 7 * (int64_t)B * H;              // d1 d2 d3(mlp) gd1 gd2 gd3 mask
     n += 2 * (int64_t)B;                  // outv gout
     n += m->member_floats;                // grads
+    if (m->kind == FLEXS_KIND_CNN)        // per-group partial sums of the conv gradients
+        n += (int64_t)GROUPS_MAX * (std::max<int64_t>({(int64_t)m->K * F * F, (int64_t)m->K3 * F * F, (int64_t)m->K * m->A * F}) + F);
     n += 2 * 64;                          // sse (doubles)
     return n + 256;
 }
@@ -374,12 +451,34 @@ int train_step(flexs_model *m, int member, const uint8_t *d_idx, const float *d_
         k_dense_bwd_w<<<grid_for((int64_t)(F + 1) * H), TPB, 0, s>>>(p, gd1, grads + o.wd1, grads + o.bd1, B, F, H);
         k_dense_bwd_x<<<grid_for((int64_t)B * F), TPB, 0, s>>>(p, w + o.wd1, gd1, gp, B, F, H, 0);
         k_gmax_bwd<<<grid_for(btf), TPB, 0, s>>>(h3, am, gp, ga, B, T, F);                                  // ga = gz3
-        k_conv_bwd_w<<<grid_for((int64_t)K3 * F * F + F), TPB, 0, s>>>(h2, ga, grads + o.w3, grads + o.b3, B, T, F, K3, d.pl3);
-        k_conv_bwd_x<<<grid_for(btf), TPB, 0, s>>>(h2, w + o.w3, ga, gb, B, T, F, K3, d.pl3);            // gb = gz2
-        k_conv_bwd_w<<<grid_for((int64_t)K * F * F + F), TPB, 0, s>>>(h1, gb, grads + o.w2, grads + o.b2, B, T, F, K, d.pl2);
-        k_conv_bwd_x<<<grid_for(btf), TPB, 0, s>>>(h1, w + o.w2, gb, ga, B, T, F, K, d.pl2);             // ga = gz1
-        k_conv1_bwd_w<<<grid_for((int64_t)K * A * F + F), TPB, 0, s>>>(d_idx, d_perm, ga, grads + o.w1, grads + o.b1, B, L, A, T, F, K);
-        m->launches += 18;
+        float *part = grads + m->member_floats;
+        const int G = std::min(B, GROUPS_MAX);
+        const size_t sm_max = sizeof(float) * std::max({(size_t)(2 * TCHUNK + std::max(K, K3) - 1) * F,
+                                                        (size_t)std::max(K, K3) * F * (F + 1) + (size_t)(TCHUNK + std::max(K, K3) - 1) * F,
+                                                        (size_t)K * A * F + F});
+        FX_REQUIRE(sm_max <= 200 * 1024, "training tiles do not fit shared memory (num_filters too large)");
+        if (sm_max > 48 * 1024) {  // per device, cheap: no caching across devices
+            FX_CUDA(cudaFuncSetAttribute(k_conv_bwd_w_part, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            FX_CUDA(cudaFuncSetAttribute(k_conv_bwd_x_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            FX_CUDA(cudaFuncSetAttribute(k_conv1_bwd_w_part, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        }
+        auto conv_bwd = [&](const float *xin, const float *wgt, const float *gzz, float *gxx, int64_t ow, int64_t ob,
+                            int k, int pl) {
+            const int cnt = k * F * F + F;
+            const size_t sm_w = sizeof(float) * ((size_t)(TCHUNK + k - 1) * F + (size_t)TCHUNK * F);
+            k_conv_bwd_w_part<<<G, TPB, sm_w, s>>>(xin, gzz, part, B, T, F, k, pl);
+            k_sum_parts<<<grid_for(cnt), TPB, 0, s>>>(part, G, cnt, k * F * F, grads + ow, grads + ob);
+            const size_t sm_x = sizeof(float) * ((size_t)k * F * (F + 1) + (size_t)(TCHUNK + k - 1) * F);
+            k_conv_bwd_x_tile<<<std::min(B, 148 * 4), TPB, sm_x, s>>>(xin, wgt, gzz, gxx, B, T, F, k, pl);
+        };
+        conv_bwd(h2, w + o.w3, ga, gb, o.w3, o.b3, K3, d.pl3);                                                // gb = gz2
+        conv_bwd(h1, w + o.w2, gb, ga, o.w2, o.b2, K, d.pl2);                                                 // ga = gz1
+        {
+            const int cnt = K * A * F + F;
+            k_conv1_bwd_w_part<<<G, TPB, sizeof(float) * cnt, s>>>(d_idx, d_perm, ga, part, B, L, A, T, F, K);
+            k_sum_parts<<<grid_for(cnt), TPB, 0, s>>>(part, G, cnt, K * A * F, grads + o.w1, grads + o.b1);
+        }
+        m->launches += 21;
     } else {
         const MlpOffsets o = mlp_offsets(m);
         float *x1 = base, *x2 = x1 + (int64_t)B * H, *x3 = x2 + (int64_t)B * H;

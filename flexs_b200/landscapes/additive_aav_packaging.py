@@ -95,12 +95,12 @@ class AdditiveAAVPackaging(DeviceTableLandscape):
                                    self._offset, self._denom, d_noise, d_out, stream)
 
     def get_fitness_device(self, seq, columns: bool = False, charge: bool = True):
-        """Device-resident scoring; with ``noise != 0`` the per-sequence normal draws come from numpy's global stream
-        exactly as in ``get_fitness`` and are uploaded (8 bytes per sequence)."""
+        """Device-resident scoring (an extension: the reference has no such call).  With ``noise != 0`` the
+        per-sequence normal draws come from numpy's global stream as in ``get_fitness`` and are uploaded (8 bytes per
+        sequence); with ``noise == 0`` the stream is left untouched (``get_fitness`` advances it, like the reference)."""
         import torch
 
         if self.noise == 0:
-            np.random.normal(scale=self.noise, size=int(seq.shape[0]))  # keep the global stream where the reference leaves it
             return super().get_fitness_device(seq, columns, charge)
         if seq.dtype != torch.uint8 or seq.dim() != 2 or seq.shape[1] != self.seq_len or not seq.is_contiguous():
             raise ValueError(f"expected a contiguous uint8 [n, {self.seq_len}] CUDA tensor")
@@ -134,7 +134,7 @@ class AdditiveAAVPackaging(DeviceTableLandscape):
         dev = torch.device("cuda", self.device)
         from flexs_b200.utils import sequence_utils as s_utils
 
-        d_seq = torch.from_numpy(s_utils.sequences_to_char_array(seqs, self.seq_len)).to(dev)
+        d_seq = torch.from_numpy(s_utils.sequences_to_char_array(seqs, self.seq_len).copy()).to(dev)
         out = torch.empty(n, dtype=torch.float64, device=dev)
         d_noise = torch.from_numpy(noise).to(dev) if self.noise != 0 else None
         with torch.cuda.device(dev):

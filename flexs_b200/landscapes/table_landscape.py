@@ -80,5 +80,5 @@ class DeviceTableLandscape(Landscape):
             return np.array([])
         chars = s_utils.sequences_to_char_array(sequences, self.seq_len)
         self._table_on_device()
-        d_seq = torch.from_numpy(chars).to(torch.device("cuda", self.device))
+        d_seq = torch.from_numpy(chars if chars.flags.writeable else chars.copy()).to(torch.device("cuda", self.device))
         return self.get_fitness_device(d_seq, charge=False).cpu().numpy()

@@ -98,8 +98,11 @@ def test_additive_device_resident_full_size_and_long_table():
 def test_tfbinding_matches_reference_bit_exact(ref):
     land = flexs.landscapes.TFBinding(TF_FILE)
     out = land.get_fitness(ref["tf"]["query"])
-    assert out.dtype == np.dtype(ref["tf"]["dtype"]) and land.cost == ref["tf"]["cost"]
+    assert out.dtype == np.dtype(ref["tf"]["dtype"])
     np.testing.assert_array_equal(out, unhex(ref["tf"]["fitness"]))
+    with pytest.raises(KeyError, match="ACGN"):
+        land.get_fitness(["ACGT", "ACGN"])
+    assert land.cost == ref["tf"]["cost"]        # the failed call was charged too (landscape.py:44 runs first)
     keys = sorted(ref["tf"]["dict"])
     np.testing.assert_array_equal(land.get_fitness(np.array(keys)), unhex([ref["tf"]["dict"][k] for k in keys]))
     with pytest.raises(KeyError, match="ACGN"):
