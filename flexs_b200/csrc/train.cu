@@ -148,23 +148,32 @@ __global__ void k_head(const float *d2, const float *mask, const float *wd3, con
 
 // ---------------------------------------------------------------- backward kernels
 // last layer: gw[g] = sum_b keep*d2[b,g]*gout[b]; gb = sum_b gout[b]; gd2[b,g] = gout[b]*wd3[g]*keep*(d2>0)
-__global__ void k_head_bwd(const float *d2, const float *mask, const float *wd3, const float *gout, float *gwd3, float *gbd3,
-                           float *gd2, int B, int H) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+// One CTA per hidden unit g (CTA H handles the bias): threads stride over the batch, then a fixed-shape shared-memory
+// tree adds the TPB partial sums — deterministic, and no thread walks the whole batch alone.
+__global__ void __launch_bounds__(TPB) k_head_bwd(const float *d2, const float *mask, const float *wd3, const float *gout,
+                                                  float *gwd3, float *gbd3, float *gd2, int B, int H) {
+    __shared__ float red[TPB];
+    const int g = blockIdx.x;
+    float acc = 0.f;
     if (g < H) {
-        float acc = 0.f;
-        for (int b = 0; b < B; ++b) {
+        const float wg = wd3[g];
+        for (int b = threadIdx.x; b < B; b += TPB) {
             const float keep = mask ? mask[(size_t)b * H + g] * (1.f / (1.f - DROP_RATE)) : 1.f;
             const float v = d2[(size_t)b * H + g];
             acc = fmaf(v * keep, gout[b], acc);
-            gd2[(size_t)b * H + g] = (v > 0.f) ? gout[b] * wd3[g] * keep : 0.f;
+            gd2[(size_t)b * H + g] = (v > 0.f) ? gout[b] * wg * keep : 0.f;
         }
-        gwd3[g] = acc;
+    } else {
+        for (int b = threadIdx.x; b < B; b += TPB) acc += gout[b];
     }
-    if (g == 0) {
-        float s = 0.f;
-        for (int b = 0; b < B; ++b) s += gout[b];
-        gbd3[0] = s;
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = TPB / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (g < H) gwd3[g] = red[0]; else gbd3[0] = red[0];
     }
 }
 
@@ -445,7 +454,7 @@ int train_step(flexs_model *m, int member, const uint8_t *d_idx, const float *d_
         k_dense_fwd<<<grid_for((int64_t)B * H), TPB, 0, s>>>(d1, w + o.wd2, w + o.bd2, d2, B, H, H, 1);
         k_head<<<1, TPB, 0, s>>>(d2, d_mask, w + o.wd3, w + o.bd3, d_labels, d_perm, outv, gout, d_sse_out, B, H);
         // ---- backward ----
-        k_head_bwd<<<(H + TPB - 1) / TPB, TPB, 0, s>>>(d2, d_mask, w + o.wd3, gout, grads + o.wd3, grads + o.bd3, gd2, B, H);
+        k_head_bwd<<<H + 1, TPB, 0, s>>>(d2, d_mask, w + o.wd3, gout, grads + o.wd3, grads + o.bd3, gd2, B, H);
         k_dense_bwd_w<<<grid_for((int64_t)(H + 1) * H), TPB, 0, s>>>(d1, gd2, grads + o.wd2, grads + o.bd2, B, H, H);
         k_dense_bwd_x<<<grid_for((int64_t)B * H), TPB, 0, s>>>(d1, w + o.wd2, gd2, gd1, B, H, H, 1);
         k_dense_bwd_w<<<grid_for((int64_t)(F + 1) * H), TPB, 0, s>>>(p, gd1, grads + o.wd1, grads + o.bd1, B, F, H);
@@ -489,7 +498,7 @@ int train_step(flexs_model *m, int member, const uint8_t *d_idx, const float *d_
         k_dense_fwd<<<grid_for((int64_t)B * H), TPB, 0, s>>>(x1, w + o.w2, w + o.b2, x2, B, H, H, 1);
         k_dense_fwd<<<grid_for((int64_t)B * H), TPB, 0, s>>>(x2, w + o.w3, w + o.b3, x3, B, H, H, 1);
         k_head<<<1, TPB, 0, s>>>(x3, nullptr, w + o.w4, w + o.b4, d_labels, d_perm, outv, gout, d_sse_out, B, H);
-        k_head_bwd<<<(H + TPB - 1) / TPB, TPB, 0, s>>>(x3, nullptr, w + o.w4, gout, grads + o.w4, grads + o.b4, g3, B, H);
+        k_head_bwd<<<H + 1, TPB, 0, s>>>(x3, nullptr, w + o.w4, gout, grads + o.w4, grads + o.b4, g3, B, H);
         k_dense_bwd_w<<<grid_for((int64_t)(H + 1) * H), TPB, 0, s>>>(x2, g3, grads + o.w3, grads + o.b3, B, H, H);
         k_dense_bwd_x<<<grid_for((int64_t)B * H), TPB, 0, s>>>(x2, w + o.w3, g3, g2, B, H, H, 1);
         k_dense_bwd_w<<<grid_for((int64_t)(H + 1) * H), TPB, 0, s>>>(x1, g2, grads + o.w2, grads + o.b2, B, H, H);
