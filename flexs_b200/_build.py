@@ -14,7 +14,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libflexs_b200.so"
 
-SOURCES = ["api.cu", "encode.cu", "cnn_simple.cu", "cnn_tiled.cu", "cnn_umma.cu", "cnn_umma2.cu", "mlp.cu",
+SOURCES = ["api.cu", "encode.cu", "cnn_simple.cu", "cnn_tiled.cu", "cnn_umma.cu", "cnn_umma2.cu", "cnn_k9.cu", "mlp.cu",
            "topk.cu", "gen.cu", "train.cu", "landscape.cu"]
 
 NVCC_FLAGS = [

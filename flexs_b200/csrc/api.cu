@@ -129,6 +129,8 @@ void flexs_model_destroy(flexs_model_t *m) {
     cudaFree(m->d_weights);
     cudaFree(m->d_umma_w);
     cudaFree(m->d_umma2_w);
+    cudaFree(m->d_k9_tab);
+    cudaFree(m->d_k9_ovf);
     cudaFree(m->d_flag);
     cudaFree(m->d_adam_m);
     cudaFree(m->d_adam_v);
@@ -166,6 +168,7 @@ int flexs_model_set_weights(flexs_model_t *m, int member, const float *const *h_
     }
     m->umma_ready = false;
     m->umma2_ready = false;
+    m->k9_ready = false;
     return FLEXS_OK;
 }
 
@@ -184,10 +187,11 @@ int flexs_model_get_weights(flexs_model_t *m, int member, float *const *h_arrays
 
 int flexs_model_set_variant(flexs_model_t *m, int variant) {
     FX_REQUIRE(m, "null model");
-    FX_REQUIRE(variant >= FLEXS_VARIANT_AUTO && variant <= FLEXS_VARIANT_UMMA, "unknown variant");
+    FX_REQUIRE(variant >= FLEXS_VARIANT_AUTO && variant <= FLEXS_VARIANT_UMMA_LUT, "unknown variant");
     if (m->kind == FLEXS_KIND_CNN) {
         if (variant == FLEXS_VARIANT_TILED) FX_REQUIRE(cnn_tiled_supported(m), "TILED variant needs F=32, k=5, A in {4,20}");
         if (variant == FLEXS_VARIANT_UMMA) FX_REQUIRE(cnn_umma_supported(m), "UMMA variant not available for this shape");
+        if (variant == FLEXS_VARIANT_UMMA_LUT) FX_REQUIRE(cnn_k9_supported(m), "UMMA_LUT variant needs A=4, F=32, k=5, H<=112, 20 <= L <~ 190");
     } else {
         FX_REQUIRE(variant == FLEXS_VARIANT_AUTO, "MLP has a single kernel");
     }
@@ -197,9 +201,9 @@ int flexs_model_set_variant(flexs_model_t *m, int variant) {
 
 int flexs_model_active_variant(const flexs_model_t *m, int64_t n) {
     if (!m) return FLEXS_EINVAL;
-    (void)n;
     if (m->kind != FLEXS_KIND_CNN) return FLEXS_VARIANT_AUTO;
     if (m->variant != FLEXS_VARIANT_AUTO) return m->variant;
+    if (cnn_k9_supported(m) && n >= (m->k9_ready ? K9_MIN_N_READY : K9_MIN_N)) return FLEXS_VARIANT_UMMA_LUT;
     if (cnn_umma_supported(m)) return FLEXS_VARIANT_UMMA;
     if (cnn_tiled_supported(m)) return FLEXS_VARIANT_TILED;
     return FLEXS_VARIANT_SIMPLE;
@@ -226,6 +230,7 @@ int flexs_model_forward_dev(flexs_model_t *m, const uint8_t *d_idx, int64_t n, f
     cudaStream_t s = (cudaStream_t)stream;
     if (m->kind == FLEXS_KIND_MLP) return launch_mlp(m, d_idx, n, d_out, s);
     switch (flexs_model_active_variant(m, n)) {
+        case FLEXS_VARIANT_UMMA_LUT: return launch_cnn_k9(m, d_idx, n, d_out, s);
         case FLEXS_VARIANT_UMMA: return launch_cnn_umma(m, d_idx, n, d_out, s);
         case FLEXS_VARIANT_TILED: return launch_cnn_tiled(m, d_idx, n, d_out, s);
         default: return launch_cnn_simple(m, d_idx, n, d_out, s);

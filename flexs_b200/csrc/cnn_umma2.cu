@@ -29,10 +29,12 @@
 
 #include "common.cuh"
 #include "dense_head.cuh"
+#include "umma2_layout.cuh"
 
 namespace {
 
-constexpr int F = 32, NT = 544, K = 5, K3 = 3, ALPHA = 4;
+using namespace u2;
+constexpr int NT = 544;
 // 17 warps: 0-7 conv2 epilogue (E2) of chunk n-1 then conv1 of chunk n, 8-15 conv3 epilogue (E3), 16 MMA issuer.
 // Measured alternatives (profiles/r01_umma_v2_roles.txt): conv1 on its own 3 warps (14.1k cycles/chunk), conv1
 // shared by all 16 warps (15.0k), conv1 with E3 (13.5k); this split is the fastest (12.3k).  Every generic
@@ -42,13 +44,8 @@ constexpr int NTILE = 4;
 constexpr int WR1 = K - 1, WR2 = K3 - 1;                      // wrap core matrices
 constexpr int TS1 = (16 + WR1) * 128, TS2 = (16 + WR2) * 128;  // bytes per tile per plane
 constexpr int PL1 = NTILE * TS1, PL2 = NTILE * TS2;            // bytes per plane
-constexpr int UWTAP = 4 * 64 * 16;  // one tap: 4 channel chunks x ([hi|lo] 64 filters) x 16 B
-constexpr int UWKC = 64 * 16;       // one channel chunk of a tap
-constexpr float ASCALE = 8.f;
 constexpr int TP = 36;  // padded row (floats) of the conv1 gather tables: rows land in different bank groups
 constexpr int ROUT = (NTILE * 128 - (K3 - 1)) & ~3;  // conv3 output rows per chunk (508)
-constexpr uint32_t IDESC_N64 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-constexpr uint32_t IDESC_N32 = (1u << 4) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
 
 struct U2Params {
     const uint8_t *idx;
@@ -67,20 +64,7 @@ struct U2Params {
     int dbg;  // profiling knobs (FLEXS_UMMA_DBG bitmask): 1 skip E3 reduction, 2 skip conv1 math, 4 skip E2 split/stores
 };
 
-constexpr int OFF_UW3 = K * UWTAP, OFF_T012 = OFF_UW3 + K3 * UWTAP, OFF_T34 = OFF_T012 + 64 * F * 4;
-constexpr int OFF_SCAL = OFF_T34 + 16 * F * 4;
-// tensor-core dense head (H <= 112): [128 sequence slots] x [32 -> 112 -> 112] as two UMMA GEMMs with the same
-// fp16 hi/lo split; weights as [k chunk][n: hi 0..111 | lo 112..223][8 k] planes, vectors padded to 112
-constexpr int DH = 112, DN = 2 * DH, DSLOTS = 128, DPLANE = DSLOTS * 16, DBK = DN * 16;
-constexpr int OFF_DB1 = (OFF_SCAL + 16 + 255) / 256 * 256, OFF_DB2 = OFF_DB1 + 4 * DBK, OFF_DV = OFF_DB2 + 14 * DBK;
-constexpr int DV_FLOATS = 3 * DH + 4;  // bd1*ASCALE | bd2 | wd3 | inv_d1s, inv_d2, bd3
-constexpr int OFF_TBIG = (OFF_DV + DV_FLOATS * 4 + 255) / 256 * 256;  // 4^5 entries x (4 chunks hi | 4 chunks lo) x 16 B
-constexpr int UW_MEMBER_BYTES = OFF_TBIG + 1024 * 128;
 // dense scratch inside the (idle) activation buffers
-constexpr int DS_X1 = 0, DS_B1 = DS_X1 + 8 * DPLANE, DS_X2 = DS_B1 + 4 * DBK, DS_B2 = DS_X2 + 28 * DPLANE;
-constexpr int DS_PART = DS_B2 + 14 * DBK, DS_DV = DS_PART + 2 * DSLOTS * 4, DS_TOTAL = DS_DV + (DV_FLOATS * 4 + 15) / 16 * 16;
-constexpr uint32_t IDESC_DN = (1u << 4) | ((uint32_t)(DN >> 3) << 17) | ((128u >> 4) << 24);
-constexpr uint32_t IDESC_DH = (1u << 4) | ((uint32_t)(DH >> 3) << 17) | ((128u >> 4) << 24);
 static_assert(DS_TOTAL <= 8 * (PL1 + PL2), "dense scratch must fit the activation buffers");
 
 struct Offs {
@@ -111,90 +95,7 @@ __host__ __device__ inline Offs carve(const U2Params &p) {
     return o;
 }
 
-// ---- PTX wrappers ---------------------------------------------------------------------------------
-__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(fxd::smem_u32(dst_smem)),
-                 "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fxd::smem_u32(bar)) : "memory");
-}
-// tcgen05.mma issued by ONE elected lane, but reached by the whole (converged) warp: control flow stays
-// warp-uniform, so the descriptor arithmetic runs on the uniform datapath instead of one thread's
-// R2UR-latency-bound chain (the first v2 profile spent ~2000 single-thread instructions per chunk there).
-__device__ __forceinline__ void umma_f16_elect(uint32_t d_tmem, uint32_t a_lo32, uint32_t a_hi32, uint32_t b_lo32,
-                                               uint32_t b_hi32, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
-        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
-        "elect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %6, 0;\n\t"
-        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_lo32), "r"(a_hi32), "r"(b_lo32), "r"(b_hi32), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit_elect(uint64_t *bar) {
-    asm volatile(
-        "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
-        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
-        ::"r"(fxd::smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&v)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                 : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major, SWIZZLE_NONE shared-memory matrix descriptor (verified on hardware by the v1 kernel):
-//   lo word: bits 0-13 start address >> 4, bits 16-29 LBO >> 4 (bytes between the two 8-element K chunks)
-//   hi word: bits 0-13 SBO >> 4 (bytes between consecutive 8-row core matrices), bit 14 = version 1
-__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo) { return (smem_addr >> 4) | ((lbo >> 4) << 16); }
-constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
-
-// one 128-row tile of an implicit-GEMM conv: taps x 2 channel pairs x {A_hi x [W_hi|W_lo], A_lo x W_hi}.
-// Called by all 32 lanes of the MMA warp; every offset is a compile-time constant added to two base words.
-template <int TAPS, uint32_t A_PLANE>
-__device__ __forceinline__ void issue_conv_tile(uint32_t a_tile_addr, uint32_t w_addr, uint32_t d_tmem) {
-    const uint32_t a0 = desc_lo(a_tile_addr, A_PLANE), b0 = desc_lo(w_addr, UWKC);
-#pragma unroll
-    for (int j = 0; j < TAPS; ++j) {
-#pragma unroll
-        for (int kp = 0; kp < 2; ++kp) {
-            const uint32_t a_hi = a0 + (((uint32_t)(2 * kp) * A_PLANE + (uint32_t)j * 128u) >> 4);
-            const uint32_t a_lo = a_hi + ((4u * A_PLANE) >> 4);
-            const uint32_t bd = b0 + (((uint32_t)j * UWTAP + (uint32_t)(2 * kp) * UWKC) >> 4);
-            umma_f16_elect(d_tmem, a_hi, DESC_HI, bd, DESC_HI, IDESC_N64, (j | kp) ? 1u : 0u);
-            umma_f16_elect(d_tmem, a_lo, DESC_HI, bd, DESC_HI, IDESC_N32, 1u);
-        }
-    }
-}
-
-// one dense layer: [128 slots, 16*KP] x [16*KP, 112] with X = hi + lo planes (NPL planes per split)
-template <int KP, int NPL>
-__device__ __forceinline__ void issue_dense_layer(uint32_t x_addr, uint32_t b_addr, uint32_t d_tmem) {
-    const uint32_t a0 = desc_lo(x_addr, DPLANE), b0 = desc_lo(b_addr, DBK);
-#pragma unroll
-    for (int kp = 0; kp < KP; ++kp) {
-        const uint32_t a_hi = a0 + (((uint32_t)(2 * kp) * DPLANE) >> 4);
-        const uint32_t a_lo = a_hi + (((uint32_t)NPL * DPLANE) >> 4);
-        const uint32_t bd = b0 + (((uint32_t)(2 * kp) * DBK) >> 4);
-        umma_f16_elect(d_tmem, a_hi, DESC_HI, bd, DESC_HI, IDESC_DN, kp ? 1u : 0u);
-        umma_f16_elect(d_tmem, a_lo, DESC_HI, bd, DESC_HI, IDESC_DH, 1u);
-    }
-}
 
 __device__ __forceinline__ void issue_idx_load(const U2Params &p, uint8_t *dst, uint64_t *bar, int64_t item) {
     const int64_t first = item * p.S;
@@ -235,22 +136,6 @@ __device__ __forceinline__ void walk_group(const U2Params &p, int64_t item_begin
     }
 }
 
-// 8 fp32 -> fp16 hi row + lo row; mx tracks the largest value seen (fp16 range guard)
-__device__ __forceinline__ void split8(const float (&x)[8], uint4 &hi4, uint4 &lo4, float &mx) {
-    uint32_t hi[4], lo[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float a = x[2 * i], b = x[2 * i + 1];
-        mx = fmaxf(mx, fmaxf(a, b));
-        const __half2 h = __floats2half2_rn(a, b);
-        const float2 back = __half22float2(h);
-        const __half2 l = __floats2half2_rn(a - back.x, b - back.y);
-        hi[i] = *reinterpret_cast<const uint32_t *>(&h);
-        lo[i] = *reinterpret_cast<const uint32_t *>(&l);
-    }
-    hi4 = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    lo4 = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-}
 
 __global__ void __launch_bounds__(NT, 1) cnn_umma2_kernel(const U2Params p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -844,6 +729,12 @@ static int prepare(flexs_model *m, const U2Params &p) {
 }  // namespace
 
 namespace fx {
+
+int prepare_cnn_umma2(flexs_model *m) {
+    U2Params p;
+    FX_REQUIRE(plan(m, p), "shape not supported by the pipelined UMMA kernel");
+    return prepare(m, p);
+}
 
 bool cnn_umma2_supported(const flexs_model *m) {
     if (m->kind != FLEXS_KIND_CNN || m->F != 32 || m->K != 5 || m->A != 4) return false;

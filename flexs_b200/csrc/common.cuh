@@ -63,6 +63,9 @@ struct flexs_model {
     void *d_umma2_w = nullptr;       // same for cnn_umma2.cu ([hi|lo] fused N=64 planes + gather tables)
     bool umma2_ready = false;
     bool umma_weights_ok = true;     // false: non-finite conv weights, use the fp32 kernel
+    void *d_k9_tab = nullptr;        // cnn_k9.cu: conv1 o conv2 as a table over 9 residues, [M][425984][128 B]
+    int *d_k9_ovf = nullptr;         // raised by the table builder when an entry left the fp16 window
+    bool k9_ready = false;
     int *d_flag = nullptr;           // fp16-overflow flag raised by the UMMA kernel
 
     // Adam state for K4 (same layout as d_weights) and the 1-based step counter per member
@@ -105,6 +108,13 @@ int prepare_cnn_umma(flexs_model *m);
 // pipelined tcgen05 kernel for the A = 4 shapes (cnn_umma2.cu)
 bool cnn_umma2_supported(const flexs_model *m);
 int launch_cnn_umma2(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s);
+// table (conv1 o conv2 over 9 residues, L2-resident) + tcgen05 conv3/dense kernel for large A = 4 batches (cnn_k9.cu)
+bool cnn_k9_supported(const flexs_model *m);
+int launch_cnn_k9(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s);
+int prepare_cnn_umma2(flexs_model *m);
+// AUTO picks the table kernel from this batch size on (building the table costs about as much as scoring
+// 3e4 sequences with cnn_umma2), or for any batch once the table of the current weights exists
+constexpr int64_t K9_MIN_N = 65536, K9_MIN_N_READY = 1024;
 int launch_mlp(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s);
 
 }  // namespace fx

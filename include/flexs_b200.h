@@ -52,7 +52,9 @@ enum {
     FLEXS_VARIANT_AUTO = 0,
     FLEXS_VARIANT_SIMPLE = 1, /* one CTA per sequence, any shape                          */
     FLEXS_VARIANT_TILED = 2,  /* register-tiled FP32 FFMA, F == 32                        */
-    FLEXS_VARIANT_UMMA = 3    /* tcgen05 (3x bf16 split) convs, F == 32                   */
+    FLEXS_VARIANT_UMMA = 3,   /* tcgen05 (fp16 hi/lo split) convs, F == 32                */
+    FLEXS_VARIANT_UMMA_LUT = 4 /* A == 4: conv1+conv2 as an L2-resident table over 9 residues,
+                                * conv3 + dense head on tcgen05; AUTO uses it for large batches */
 };
 
 typedef struct flexs_model flexs_model_t;

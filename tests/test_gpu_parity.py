@@ -47,7 +47,7 @@ def _device_forward(model, idx):
 
 def _variants(model):
     vs = [_native.VARIANT_SIMPLE]
-    for v in (_native.VARIANT_TILED, _native.VARIANT_UMMA):
+    for v in (_native.VARIANT_TILED, _native.VARIANT_UMMA, _native.VARIANT_UMMA_LUT):
         try:
             model.set_variant(v)
             vs.append(v)
@@ -179,6 +179,66 @@ def test_cnn_full_size_properties():
             other = _device_forward(m, idx)
             assert rel_err(other, base, _floor(base)) < TOL
         m.close()
+
+
+@pytest.mark.parametrize("L,n", [(20, 1000), (21, 259), (37, 1031), (100, 128 * 148 + 77), (120, 515), (180, 300)])
+def test_cnn_table_kernel_lengths_and_ragged_groups(L, n):
+    """cnn_k9.cu (conv1+conv2 as an L2-resident table over 9 residues): lengths whose conv positions do and do not
+    fill the last 16-row tile, batches that end inside a group of 128 / an item of 8 sequences, unaligned pointers."""
+    A = 4
+    ws = fo.trained_like_weights(fo.CNNShape(L, A, 32, 100, 5).weight_shapes(), L)
+    idx = np.random.default_rng(L).integers(0, A, size=(n, L), dtype=np.uint8)
+    ref = co.cnn_forward(idx, [ws])
+    m = _native.NativeModel("cnn", seq_len=L, alphabet_size=A, num_filters=32, hidden_size=100, kernel_size=5)
+    m.set_weights(ws)
+    m.set_variant(_native.VARIANT_UMMA_LUT)
+    got = _device_forward(m, idx)
+    assert rel_err(got, ref, _floor(ref)) < TOL
+    for cut in (1, 7, 8, 9, 127, 129):
+        np.testing.assert_array_equal(_device_forward(m, idx[:cut]), got[:cut])
+    buf = torch.zeros(n * L + 64, dtype=torch.uint8, device="cuda")
+    buf[5: 5 + n * L] = torch.from_numpy(idx.reshape(-1)).cuda()
+    out = torch.empty(n, dtype=torch.float32, device="cuda")
+    m.forward_dev(buf.data_ptr() + 5, n, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy(), got)
+    m.close()
+
+
+def test_cnn_table_kernel_selection_rebuild_and_ensemble():
+    """AUTO picks the table kernel for large batches only; new weights rebuild the table; an ensemble keeps one
+    table per member; residues outside [0, A) cannot index outside the table."""
+    L, A = 40, 4
+    shp = fo.CNNShape(L, A, 32, 100, 5)
+    wss = [fo.trained_like_weights(shp.weight_shapes(), 30 + i) for i in range(3)]
+    idx = np.random.default_rng(3).integers(0, A, size=(70_000, L), dtype=np.uint8)
+    m = _native.NativeModel("cnn", seq_len=L, alphabet_size=A, num_filters=32, hidden_size=100, kernel_size=5)
+    m.set_weights(wss[0])
+    assert m.active_variant(100) == _native.VARIANT_UMMA and m.active_variant(70_000) == _native.VARIANT_UMMA_LUT
+    small = _device_forward(m, idx[:100])                      # cnn_umma2
+    big = _device_forward(m, idx)                              # builds the table, cnn_k9
+    assert m.active_variant(2000) == _native.VARIANT_UMMA_LUT  # the table of these weights exists now
+    sample = np.arange(0, len(idx), 499)
+    ref = co.cnn_forward(idx[sample], [wss[0]])
+    assert rel_err(big[sample], ref, _floor(ref)) < TOL
+    assert rel_err(big[:100], small, _floor(small)) < TOL
+    m.set_weights(wss[1])                                      # stale table must not be used
+    assert m.active_variant(2000) == _native.VARIANT_UMMA
+    ref = co.cnn_forward(idx[sample], [wss[1]])
+    assert rel_err(_device_forward(m, idx)[sample], ref, _floor(ref)) < TOL
+    bad = idx[:300].copy(); bad[:, ::7] |= 0xF0               # garbage high bits: the kernel masks residues to 2 bits
+    m.set_variant(_native.VARIANT_UMMA_LUT)
+    np.testing.assert_array_equal(_device_forward(m, bad), _device_forward(m, bad & 3))
+    m.close()
+    ens = _native.NativeModel("cnn", seq_len=L, alphabet_size=A, num_filters=32, hidden_size=100, kernel_size=5,
+                              n_members=3)
+    for i, ws in enumerate(wss):
+        ens.set_weights(ws, i)
+    ens.set_variant(_native.VARIANT_UMMA_LUT)
+    sub = idx[:1000]
+    ref = fo.ensemble_mean([fo.nan_to_num_f32(fo.cnn_forward(sub, ws, np.float64)) for ws in wss])
+    assert rel_err(_device_forward(ens, sub), ref, _floor(ref)) < TOL
+    ens.close()
 
 
 @pytest.mark.parametrize("members", [2, 3])
