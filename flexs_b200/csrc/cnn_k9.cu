@@ -33,11 +33,11 @@ namespace {
 
 using namespace u2;
 
-constexpr int NT = 544, NPROD = 8, MMAW = 16;
+constexpr int NT = 576, NPROD = 8, MMAW = 16, NMMA = 2;  // warps: 0-7 producers, 8-15 epilogue, 16-17 MMA issue
 constexpr int RING = 8;                 // operand slots == TMEM accumulators == producer warps
-constexpr int CM = 16 + K3 - 1;         // core matrices per tile and plane (16 positions + k3-1 behind them)
-constexpr int PLANE = CM * 128;         // bytes per channel-chunk plane of a slot
-constexpr int SLOT = 8 * PLANE;         // 4 hi + 4 lo planes
+constexpr int CM = 16 + K3 - 1;         // 8-row groups per tile and plane (16 positions + k3-1 behind them)
+constexpr int PLANE = CM * 256;         // bytes per K-step plane of a slot: rows of 32 B (16 channels), SWIZZLE_32B
+constexpr int SLOT = 4 * PLANE;         // hi ch 0-15 | hi ch 16-31 | lo ch 0-15 | lo ch 16-31
 constexpr int GS = DSLOTS, SBP = GS + 4;  // sequences per dense-head batch, padded feature row
 static_assert(RING * SLOT >= DS_TOTAL, "dense scratch must fit the operand ring");
 
@@ -57,12 +57,13 @@ struct K9Params {
     int *overflow_flag;
     int64_t n, n_groups, member_floats, uw_member_bytes;
     fx::CnnOffsets o;
-    int M, L, T, nti, idx_slot;
+    int M, L, T, nti, idx_slot, nwp;
     long long *prof;
+    int dbg;  // profiling knobs (FLEXS_UMMA_DBG bitmask): 1 skip the MMAs, 2 skip the gathers, 4 skip the epilogue math
 };
 
 struct Offs {
-    int mbar, tm, b3, uw3, i0, i1, feat, ring;
+    int mbar, tm, b3, uw3, i0, i1, pw, feat, ring;
     size_t total;
 };
 
@@ -80,6 +81,7 @@ __host__ __device__ inline Offs carve(const K9Params &p) {
     o.mbar = take(64 * 8, 16); o.tm = take(16, 16); o.b3 = take(F * 4, 16);
     o.uw3 = take((size_t)K3 * UWTAP, 128);
     o.i0 = take(p.idx_slot, 16); o.i1 = take(p.idx_slot, 16);
+    o.pw = take((size_t)GS * p.nwp * 4, 16);
     o.feat = take((size_t)F * SBP * 4, 16);
     o.ring = take((size_t)RING * SLOT, 1024);
     o.total = off;
@@ -143,6 +145,35 @@ __global__ void __launch_bounds__(256) k9_build_kernel(const float *__restrict__
 }
 
 // ---- forward -------------------------------------------------------------------------------------------------
+// A operand: K-major SWIZZLE_32B (rows of 32 B = the 16 channels of one K step; 8-row groups of 256 B; a tap is one
+// group = +256 B, which keeps the swizzle phase).  hi word: SBO = 256 B, version 1, layout type 6 (bits 61-63).
+constexpr uint32_t A_DESC_HI = (256u >> 4) | (1u << 14) | (6u << 29);
+
+// one 128-row tile of conv3: taps x 2 K steps x {A_hi x [W_hi|W_lo], A_lo x W_hi}; all 32 lanes call it
+__device__ __forceinline__ void issue_conv3_tile(uint32_t a_slot_addr, uint32_t w_addr, uint32_t d_tmem) {
+    const uint32_t a0 = desc_lo(a_slot_addr, 16), b0 = desc_lo(w_addr, UWKC);
+#pragma unroll
+    for (int j = 0; j < K3; ++j) {
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) {
+            const uint32_t a_hi = a0 + (((uint32_t)kp * PLANE + (uint32_t)j * 256u) >> 4);
+            const uint32_t a_lo = a_hi + ((2u * PLANE) >> 4);
+            const uint32_t bd = b0 + (((uint32_t)j * UWTAP + (uint32_t)(2 * kp) * UWKC) >> 4);
+            umma_f16_elect(d_tmem, a_hi, A_DESC_HI, bd, DESC_HI, IDESC_N64, (j | kp) ? 1u : 0u);
+            umma_f16_elect(d_tmem, a_lo, A_DESC_HI, bd, DESC_HI, IDESC_N32, 1u);
+        }
+    }
+}
+
+// packed fp32 add (sm_100 FADD2): two accumulator halves of two filters per instruction
+__device__ __forceinline__ void add_f32x2(float &x0, float &x1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 rc, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rc;\n\t}"
+        : "=f"(x0), "=f"(x1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
 __device__ __forceinline__ void issue_idx_load(const K9Params &p, uint8_t *dst, uint64_t *bar, int64_t group) {
     const int64_t first = group * GS;
     const int64_t cnt = min((int64_t)GS, p.n - first);
@@ -160,7 +191,9 @@ __device__ __forceinline__ void issue_idx_load(const K9Params &p, uint8_t *dst, 
         : "memory");
 }
 
+template <bool PROF>
 __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
+    auto now = [] { return PROF ? clock64() : 0ll; };  // phase timers exist only in the FLEXS_UMMA_PROF=1 instantiation
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const Offs of = carve(p);
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + of.mbar);
@@ -196,7 +229,7 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
     uint32_t gi = 0;   // groups done: residue buffer = gi & 1
     uint32_t dph = 0;  // completed phases of the dense-head barrier
     float xmax = 0.f;  // largest dense-head activation written as fp16 (range guard)
-    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long pt[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
     for (int mem = 0; mem < p.M; ++mem) {
         const float *w = p.weights + (int64_t)mem * p.member_floats;
@@ -217,81 +250,96 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
             const int s_grp = (int)min((int64_t)GS, p.n - first);
             const uint32_t ntiles = (uint32_t)(((s_grp + 7) >> 3) * nti);
             const int buf = gi & 1;
-            const long long tg0 = clock64();
+            const long long tg0 = now();
 
             if (wid < NPROD) {
                 // =========================== producers: residues -> table rows -> operand slot ===========================
-                const int b = lane & 7, qq = lane >> 3;
+                // lane = 16 pp + 2 b + h: stream b, K-step plane pp of the pair an instruction covers, 16-byte half h.
+                // Adjacent lanes read the two halves of one 32-byte sector of the entry and a quarter warp writes 4 rows
+                // x 32 B = 128 contiguous bytes of a plane: no sector is fetched twice, no bank conflict.
+                const int b = (lane >> 1) & 7, h = lane & 1, pp = lane >> 4;
                 const uint32_t slot_addr = ring_addr + (uint32_t)wid * SLOT;
+                uint32_t *pw = reinterpret_cast<uint32_t *>(smem_raw + of.pw);
+                const int nwp = p.nwp;
                 fxd::mbar_wait(&mbar_idx[buf], (gi >> 1) & 1);
                 const uint8_t *sidx = smem_raw + (buf ? of.i1 : of.i0) +
                                       ((reinterpret_cast<uintptr_t>(p.idx) + (uintptr_t)(first * L)) & 15);
+                // residues -> 2 bits each, 16 per word, first residue in the top bits; a zero word on either side
+                for (int i = tid; i < s_grp * nwp; i += NPROD * 32) {
+                    const int sq = i / nwp, wv = i - sq * nwp - 1;
+                    uint32_t word = 0;
+                    if (wv >= 0 && wv * 16 < L) {
+                        const uint8_t *src = sidx + sq * L + wv * 16;
+                        const int cnt = min(16, L - wv * 16);
+#pragma unroll
+                        for (int r = 0; r < 16; ++r)
+                            word = (word << 2) | (r < cnt ? (uint32_t)(src[r] & 3) : 0u);
+                    }
+                    pw[i] = word;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(NPROD * 32) : "memory");
+                // per-lane constants of the copy: source byte inside an entry, destination byte inside a row group
+                const uint32_t src_off = (uint32_t)(pp * 32 + h * 16);
+                const uint32_t swz = (uint32_t)((b >> 2) & 1);  // SWIZZLE_32B: rows 4-7 swap their halves
+                const uint32_t dst_off = (uint32_t)(pp * PLANE + b * 32) + (((uint32_t)h ^ swz) << 4);
                 for (uint32_t tl = ((uint32_t)wid - kt) & 7u; tl < ntiles; tl += NPROD) {
                     const uint32_t use = (kt + tl) >> 3;
-                    const long long q0 = clock64();
+                    const long long q0 = now();
                     if (use > 0) fxd::mbar_wait(&empty[wid], (use - 1) & 1);  // the MMAs that read this slot retired
-                    const long long q1 = clock64();
+                    const long long q1 = now();
                     const int item = (int)tl / nti, q = (int)tl - item * nti;
                     const int sl = item * 8 + b;
-                    const uint8_t *sq = sidx + sl * L;
+                    if (PROF && (p.dbg & 2)) { if (lane == 0) mbar_arrive(&full[wid]); continue; }
                     const bool stream_ok = sl < s_grp;
+                    // residues 16(q-1) .. 16(q+2)-1 of stream b (word index + 1 in the padded array)
+                    const uint32_t *ws = pw + (stream_ok ? sl : 0) * nwp + q;
+                    const uint32_t w0 = ws[0], w1 = ws[1], w2 = (q + 2 < nwp) ? ws[2] : 0u;
 #pragma unroll
-                    for (int bt = 0; bt < (CM + 3) / 4; ++bt) {
-                        // lane (b, qq) looks up the entry of input row c = 4 bt + qq of stream b: h2 position o = 16 q + c - 1
-                        const int c = 4 * bt + qq;
+                    for (int c = 0; c < CM; ++c) {
+                        // input row c of the tile = h2 position o = 16 q + c - 1; its window starts at residue o - 2,
+                        // i.e. 2 (c + 13) bits into w0:w1:w2 (a compile-time shift)
                         const int o = 16 * q + c - 1;
-                        int ent = -1;  // -1: zero row ("same" padding of conv3, rows past the sequence, absent streams)
-                        if (c < CM && stream_ok && o >= 0 && o < T) {
-                            int start = o - 2, len = 9, base = 0;
-                            if (o == 0) { start = 0; len = 7; base = ENT_EL0; }
-                            else if (o == 1) { start = 0; len = 8; base = ENT_EL1; }
-                            else if (o == T - 2) { len = 8; base = ENT_ER1; }
-                            else if (o == T - 1) { len = 7; base = ENT_ER0; }
-                            int code = 0;
-#pragma unroll
-                            for (int mm = 0; mm < 9; ++mm)
-                                if (mm < len) code = code * 4 + (sq[start + mm] & 3);
-                            ent = base + code;
-                        }
-                        // core matrix c2 = 4 bt + cc: its 8 rows (streams) x 8 chunks of 16 B = 2 cp.async per lane:
-                        // lane (b, qq) moves chunk qq (hi plane qq) and chunk 4 + qq (lo plane qq) of stream b's row
-#pragma unroll
-                        for (int cc = 0; cc < 4; ++cc) {
-                            const int c2 = 4 * bt + cc;
-                            if (c2 >= CM) break;
-                            const int e = __shfl_sync(0xffffffffu, ent, cc * 8 + b);
-                            const unsigned char *src = tab + (e >= 0 ? (size_t)e * 128 : (size_t)0) + qq * 16;
-                            const uint32_t nbytes = e >= 0 ? 16u : 0u;  // 0 -> cp.async zero-fills
-                            const uint32_t dst = slot_addr + (uint32_t)(qq * PLANE + c2 * 128 + b * 16);
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 4u * PLANE), "l"(src + 64),
-                                         "r"(nbytes) : "memory");
-                        }
+                        constexpr int dummy = 0; (void)dummy;
+                        uint32_t code;
+                        if (c < 3) code = __funnelshift_l(w1, w0, 2 * (c + 13)) >> 14;
+                        else if (c <= 10) code = (w1 << (2 * (c - 3))) >> 14;
+                        else code = __funnelshift_l(w2, w1, 2 * (c - 3)) >> 14;
+                        // truncated windows: o = 0, 1 read zeros in front (the code is already that of the short window),
+                        // o = T-2, T-1 drop the residues past the end
+                        uint32_t ent = code;
+                        if (o <= 1) ent = code + (o == 0 ? ENT_EL0 : ENT_EL1);
+                        if (o >= T - 2) ent = (o == T - 2) ? ENT_ER1 + (code >> 2) : ENT_ER0 + (code >> 4);
+                        const bool row_ok = stream_ok && o >= 0 && o < T;
+                        const unsigned char *src = tab + (row_ok ? (size_t)ent * 128 : (size_t)0) + src_off;
+                        const uint32_t nbytes = row_ok ? 16u : 0u;  // 0 -> cp.async zero-fills
+                        const uint32_t dst = slot_addr + dst_off + (uint32_t)(c * 256);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 2u * PLANE), "l"(src + 64),
+                                     "r"(nbytes) : "memory");
                     }
                     asm volatile("cp.async.wait_all;" ::: "memory");
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&full[wid]);
-                    if (tid == 0) { pt[2] += q1 - q0; pt[3] += clock64() - q1; }
+                    if (PROF && tid == 0) { pt[2] += q1 - q0; pt[3] += now() - q1; }
                 }
-            } else if (wid < 16) {
+            } else if (wid < MMAW) {
                 // =========================== conv3 epilogue: bias, ReLU, running max per sequence ===========================
                 const int lq = wid & 3, ch = (wid >> 2) & 1;
                 // TMEM lane 32 lq + lane is MMA row 8 c + b: position c of stream b
-                const int c = 4 * lq + (lane >> 3), b = lane & 7, qq = lane >> 3;
+                const int c = 4 * lq + (lane >> 3), b = lane & 7;
                 const uint32_t tlane = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(ch * 16);
-                float bb[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) bb[j] = b3[ch * 16 + j];
+                // max_t relu(a_t * inv3 + b) == relu(max_t(a_t) * inv3 + b) (inv3 > 0): the per-tile work is one packed add
+                // of the two accumulator halves and one fmaxf per filter; scale, bias and ReLU wait for the item's end
                 float mx[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) mx[j] = 0.f;
+                for (int j = 0; j < 16; ++j) mx[j] = -INFINITY;
                 int q = 0, item = 0;
                 for (uint32_t tl = 0; tl < ntiles; ++tl) {
                     const uint32_t k = kt + tl, acc = k & 7u;
-                    const long long w0 = clock64();
+                    const long long w0 = now();
                     fxd::mbar_wait(&tfull[acc], (k >> 3) & 1);
-                    if (tid == 8 * 32) pt[4] += clock64() - w0;
+                    const long long w1 = now();
                     tc_fence_after();
                     uint32_t v[16], v2[16];
                     tmem_ld16_nowait(tlane + acc * 64u, v);
@@ -300,46 +348,67 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[acc]);  // the accumulator is in registers: hand it back
-                    const bool valid = 16 * q + c < T;
+                    const long long w2 = now();
+                    if (!(PROF && (p.dbg & 4)) && 16 * q + c < T) {  // rows past the sequence exist only in its last tile
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float a = __uint_as_float(v[j]) + __uint_as_float(v2[j]);
-                        const float y = fmaxf(fmaf(a, inv3, bb[j]), 0.f);
-                        mx[j] = fmaxf(mx[j], valid ? y : 0.f);
+                        for (int j = 0; j < 16; j += 2) {
+                            float a0, a1;
+                            add_f32x2(a0, a1, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v2[j]),
+                                      __uint_as_float(v2[j + 1]));
+                            mx[j] = fmaxf(mx[j], a0);
+                            mx[j + 1] = fmaxf(mx[j + 1], a1);
+                        }
                     }
                     if (++q == nti) {
-                        // GlobalMaxPooling1D: the 4 lanes of stream b (and the 4 warps of this half) merge their maxima
+                        // GlobalMaxPooling1D: the 4 lanes of stream b merge their maxima with a halving butterfly — after
+                        // the xor-8 step a lane keeps filters 8 (lane bit 3) + 0..7, after the xor-16 step 4 of those —
+                        // then scale, bias and ReLU, and the 4 warps of this half meet in shared memory
                         const int sl = item * 8 + b;
+                        const bool up8 = (lane & 8) != 0, up16 = (lane & 16) != 0;
+                        float k8[8];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            float t = fmaxf(mx[j], __shfl_xor_sync(0xffffffffu, mx[j], 8));
-                            t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, 16));
-                            if ((j >> 2) == qq && sl < s_grp)  // y >= 0: uint order == float order
-                                atomicMax(reinterpret_cast<unsigned int *>(featT) + (size_t)(ch * 16 + j) * SBP + sl,
-                                          __float_as_uint(t));
-                            mx[j] = 0.f;
+                        for (int j = 0; j < 8; ++j) {
+                            const float send = up8 ? mx[j] : mx[j + 8], keep = up8 ? mx[j + 8] : mx[j];
+                            k8[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
                         }
+                        const int f0 = ch * 16 + (up8 ? 8 : 0) + (up16 ? 4 : 0);
+                        unsigned int *dstf = reinterpret_cast<unsigned int *>(featT) + (size_t)f0 * SBP + sl;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float send = up16 ? k8[j] : k8[j + 4], keep = up16 ? k8[j + 4] : k8[j];
+                            const float t = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+                            const float r = fmaxf(fmaf(t, inv3, b3[f0 + j]), 0.f);
+                            if (sl < s_grp) atomicMax(dstf + (size_t)j * SBP, __float_as_uint(r));  // r >= 0: uint order
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) mx[j] = -INFINITY;
                         q = 0; ++item;
                     }
+                    if (PROF && tid == 8 * 32) { pt[4] += w1 - w0; pt[8] += w2 - w1; pt[9] += now() - w2; }
                 }
             } else {
-                // =========================== MMA issuer ===========================
-                {   // prefetch the next group's residues into the other buffer: its last readers (the producers of the
+                // =========================== MMA issuers ===========================
+                // Two warps take alternate tiles: issuing a tile (two barrier waits, 12 MMAs, two commits) costs more
+                // issue time than the tensor pipe needs to run it, and tiles are independent (own slot, own accumulator;
+                // a commit tracks the MMAs of the committing thread).
+                const uint32_t me = (uint32_t)(wid - MMAW);
+                if (me == 0) {
+                    // prefetch the next group's residues into the other buffer: its last readers (the producers of the
                     // previous group) finished before the dense-head barrier this warp has passed
                     const int64_t next = g + gridDim.x;
                     if (lane == 0 && next < p.n_groups)
                         issue_idx_load(p, smem_raw + (buf ? of.i0 : of.i1), &mbar_idx[buf ^ 1], next);
                     __syncwarp();
                 }
-                for (uint32_t tl = 0; tl < ntiles; ++tl) {
+                for (uint32_t tl = (me - kt) & (NMMA - 1); tl < ntiles; tl += NMMA) {
                     const uint32_t k = kt + tl, s = k & 7u, use = k >> 3;
-                    const long long m0 = clock64();
+                    const long long m0 = now();
                     fxd::mbar_wait(&full[s], use & 1);
-                    const long long m1 = clock64();
+                    const long long m1 = now();
                     if (use > 0) fxd::mbar_wait(&tempty[s], (use - 1) & 1);  // accumulator drained by the epilogue
-                    if (lane == 0) { pt[5] += m1 - m0; pt[6] += clock64() - m1; }
+                    if (PROF && lane == 0 && wid == MMAW) { pt[5] += m1 - m0; pt[6] += now() - m1; }
                     tc_fence_after();
-                    issue_conv_tile<K3, PLANE>(ring_addr + s * SLOT, uw3_addr, tmem_base + s * 64u);
+                    if (!(PROF && (p.dbg & 1))) issue_conv3_tile(ring_addr + s * SLOT, uw3_addr, tmem_base + s * 64u);
                     umma_commit_elect(&tfull[s]);
                     umma_commit_elect(&empty[s]);
                 }
@@ -348,19 +417,19 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
             // ---- drain, dense head on the group's features, reset featT ----
             tc_fence_before();
             __syncthreads();
-            const long long tg1 = clock64();
+            const long long tg1 = now();
             dense_head_umma<NT, MMAW>(ring, featT, SBP, GS, s_grp, uw, tmem_base, dbar, dph, xmax, mem, p.M, p.out,
                                       [first](int sl) { return (long long)(first + sl); });
             for (int i = tid; i < F * SBP; i += NT) featT[i] = 0.f;
             __syncthreads();
-            if (tid == 0) { pt[0] += tg1 - tg0; pt[1] += clock64() - tg1; pt[7] += ntiles; }
+            if (PROF && tid == 0) { pt[0] += tg1 - tg0; pt[1] += now() - tg1; pt[7] += ntiles; }
         }
     }
     if (xmax > 60000.f) atomicExch(p.overflow_flag, 1);
     if (blockIdx.x == 0 && tid == 0 && __ldg(p.tab_ovf) != 0) atomicExch(p.overflow_flag, 1);
-    if (p.prof != nullptr && (tid == 0 || tid == 8 * 32 || tid == MMAW * 32))
-        for (int i = 0; i < 8; ++i)
-            if (pt[i]) atomicAdd(reinterpret_cast<unsigned long long *>(&p.prof[(size_t)blockIdx.x * 8 + i]), (unsigned long long)pt[i]);
+    if (PROF && p.prof != nullptr && (tid == 0 || tid == 8 * 32 || tid == MMAW * 32))
+        for (int i = 0; i < 16; ++i)
+            if (pt[i]) atomicAdd(reinterpret_cast<unsigned long long *>(&p.prof[(size_t)blockIdx.x * 16 + i]), (unsigned long long)pt[i]);
     tc_fence_before();
     __syncthreads();
     if (wid == 0) tmem_dealloc(tmem_base, 512);
@@ -375,6 +444,7 @@ static bool plan(const flexs_model *m, K9Params &p) {
     p.member_floats = m->member_floats;
     p.uw_member_bytes = UW_MEMBER_BYTES;
     p.idx_slot = (int)align_up((size_t)GS * m->L + 32, 16);
+    p.nwp = (m->L + 15) / 16 + 2;  // packed residues: a zero word, ceil(L/16) words of 16 residues, a zero word
     return (int64_t)carve(p).total + 1024 <= m->max_smem_optin;
 }
 
@@ -428,28 +498,30 @@ int launch_cnn_k9(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out,
     const size_t smem = carve(p).total + 1024;
     const int grid = (int)std::min<int64_t>(p.n_groups, m->sm_count);
     static const bool prof = std::getenv("FLEXS_UMMA_PROF") && std::getenv("FLEXS_UMMA_PROF")[0] == '1';
+    p.dbg = std::getenv("FLEXS_UMMA_DBG") ? std::atoi(std::getenv("FLEXS_UMMA_DBG")) : 0;
     p.prof = nullptr;
     if (prof) {
-        FX_CUDA(cudaMalloc(&p.prof, (size_t)grid * 8 * sizeof(long long)));
-        FX_CUDA(cudaMemset(p.prof, 0, (size_t)grid * 8 * sizeof(long long)));
+        FX_CUDA(cudaMalloc(&p.prof, (size_t)grid * 16 * sizeof(long long)));
+        FX_CUDA(cudaMemset(p.prof, 0, (size_t)grid * 16 * sizeof(long long)));
     }
     FX_CUDA(cudaMemsetAsync(m->d_flag, 0, sizeof(int), s));
-    FX_CUDA(cudaFuncSetAttribute(cnn_k9_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cnn_k9_kernel<<<grid, NT, smem, s>>>(p);
+    auto kernel = prof ? cnn_k9_kernel<true> : cnn_k9_kernel<false>;
+    FX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<grid, NT, smem, s>>>(p);
     FX_CUDA(cudaGetLastError());
     m->launches += 1;
     if (prof) {
         FX_CUDA(cudaStreamSynchronize(s));
-        std::vector<long long> h((size_t)grid * 8);
+        std::vector<long long> h((size_t)grid * 16);
         FX_CUDA(cudaMemcpy(h.data(), p.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         cudaFree(p.prof);
-        double a[8] = {0};
-        for (int b = 0; b < grid; ++b) for (int i = 0; i < 8; ++i) a[i] += (double)h[(size_t)b * 8 + i] / grid;
+        double a[16] = {0};
+        for (int b = 0; b < grid; ++b) for (int i = 0; i < 16; ++i) a[i] += (double)h[(size_t)b * 16 + i] / grid;
         const double nt = a[7] > 0 ? a[7] : 1;
         fprintf(stderr, "[k9 prof] n=%lld grid=%d tiles/CTA=%.0f | cycles per tile: pipeline %.0f, dense+drain %.0f | "
-                        "producer warp 0 (per own tile = 1/8 of tiles): wait slot %.0f, gather %.0f | epilogue warp 8: wait MMA %.0f | "
-                        "MMA warp: wait operands %.0f, wait accumulator %.0f\n",
-                (long long)n, grid, a[7], a[0] / nt, a[1] / nt, a[2] / nt * 8, a[3] / nt * 8, a[4] / nt, a[5] / nt, a[6] / nt);
+                        "producer warp 0 (per own tile = 1/8 of tiles): wait slot %.0f, gather %.0f | epilogue warp 8: wait MMA %.0f, tmem ld %.0f, math+flush %.0f | "
+                        "MMA warp 16 (per own tile = 1/2 of tiles): wait operands %.0f, wait accumulator %.0f\n",
+                (long long)n, grid, a[7], a[0] / nt, a[1] / nt, a[2] / nt * 8, a[3] / nt * 8, a[4] / nt, a[8] / nt, a[9] / nt, a[5] / nt * 2, a[6] / nt * 2);
     }
     // fp16 range guard: the gated FFMA kernel recomputes the batch iff the flag was raised
     return launch_cnn_tiled_gated(m, d_idx, n, d_out, m->d_flag, s);
