@@ -35,9 +35,9 @@ using namespace u2;
 
 constexpr int NT = 576, NPROD = 8, MMAW = 16, NMMA = 2;  // warps: 0-7 producers, 8-15 epilogue, 16-17 MMA issue
 constexpr int RING = 8;                 // operand slots == TMEM accumulators == producer warps
-constexpr int CM = 16 + K3 - 1;         // 8-row groups per tile and plane (16 positions + k3-1 behind them)
-constexpr int PLANE = CM * 256;         // bytes per K-step plane of a slot: rows of 32 B (16 channels), SWIZZLE_32B
-constexpr int SLOT = 4 * PLANE;         // hi ch 0-15 | hi ch 16-31 | lo ch 0-15 | lo ch 16-31
+constexpr int CM = 16 + K3 - 1;         // 8-row groups per tile (16 positions + k3-1 behind them)
+constexpr int SLOT = CM * 1024;         // rows of 128 B = one table entry: hi ch 0-15 | hi 16-31 | lo 0-15 | lo 16-31,
+                                        // K-major SWIZZLE_128B (16-byte chunk j of row r sits at chunk j ^ (r & 7))
 constexpr int GS = DSLOTS, SBP = GS + 4;  // sequences per dense-head batch, padded feature row
 static_assert(RING * SLOT >= DS_TOTAL, "dense scratch must fit the operand ring");
 
@@ -145,9 +145,10 @@ __global__ void __launch_bounds__(256) k9_build_kernel(const float *__restrict__
 }
 
 // ---- forward -------------------------------------------------------------------------------------------------
-// A operand: K-major SWIZZLE_32B (rows of 32 B = the 16 channels of one K step; 8-row groups of 256 B; a tap is one
-// group = +256 B, which keeps the swizzle phase).  hi word: SBO = 256 B, version 1, layout type 6 (bits 61-63).
-constexpr uint32_t A_DESC_HI = (256u >> 4) | (1u << 14) | (6u << 29);
+// A operand: K-major SWIZZLE_128B, the canonical UMMA layout: 8-row groups of 1024 B (SBO), a K step of 16 channels is
+// 32 B further into the row (start address + 32 B; the hardware applies the XOR to the final address), a tap is one
+// group = +1024 B.  hi word: SBO = 1024 B, version 1, layout type 2 (bits 61-63).
+constexpr uint32_t A_DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
 
 // one 128-row tile of conv3: taps x 2 K steps x {A_hi x [W_hi|W_lo], A_lo x W_hi}; all 32 lanes call it
 __device__ __forceinline__ void issue_conv3_tile(uint32_t a_slot_addr, uint32_t w_addr, uint32_t d_tmem) {
@@ -156,8 +157,8 @@ __device__ __forceinline__ void issue_conv3_tile(uint32_t a_slot_addr, uint32_t 
     for (int j = 0; j < K3; ++j) {
 #pragma unroll
         for (int kp = 0; kp < 2; ++kp) {
-            const uint32_t a_hi = a0 + (((uint32_t)kp * PLANE + (uint32_t)j * 256u) >> 4);
-            const uint32_t a_lo = a_hi + ((2u * PLANE) >> 4);
+            const uint32_t a_hi = a0 + (((uint32_t)j * 1024u + (uint32_t)kp * 32u) >> 4);
+            const uint32_t a_lo = a_hi + (64u >> 4);
             const uint32_t bd = b0 + (((uint32_t)j * UWTAP + (uint32_t)(2 * kp) * UWKC) >> 4);
             umma_f16_elect(d_tmem, a_hi, A_DESC_HI, bd, DESC_HI, IDESC_N64, (j | kp) ? 1u : 0u);
             umma_f16_elect(d_tmem, a_lo, A_DESC_HI, bd, DESC_HI, IDESC_N32, 1u);
@@ -173,6 +174,7 @@ __device__ __forceinline__ void add_f32x2(float &x0, float &x1, float a0, float 
         "mov.b64 {%0, %1}, rc;\n\t}"
         : "=f"(x0), "=f"(x1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
+
 
 __device__ __forceinline__ void issue_idx_load(const K9Params &p, uint8_t *dst, uint64_t *bar, int64_t group) {
     const int64_t first = group * GS;
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
         fxd::mbar_init(dbar, 1);
         for (int i = 0; i < RING; ++i) {
             fxd::mbar_init(&full[i], 1); fxd::mbar_init(&empty[i], 1);
-            fxd::mbar_init(&tfull[i], 1); fxd::mbar_init(&tempty[i], 8);
+            fxd::mbar_init(&tfull[i], 1); fxd::mbar_init(&tempty[i], 4);
         }
         fxd::fence_mbar_init();
     }
@@ -254,10 +256,10 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
 
             if (wid < NPROD) {
                 // =========================== producers: residues -> table rows -> operand slot ===========================
-                // lane = 16 pp + 2 b + h: stream b, K-step plane pp of the pair an instruction covers, 16-byte half h.
-                // Adjacent lanes read the two halves of one 32-byte sector of the entry and a quarter warp writes 4 rows
-                // x 32 B = 128 contiguous bytes of a plane: no sector is fetched twice, no bank conflict.
-                const int b = (lane >> 1) & 7, h = lane & 1, pp = lane >> 4;
+                // lane = 8 rr + j moves 16-byte chunk j of the rows of streams rr and rr + 4: eight adjacent lanes read one
+                // whole 128-byte entry (one L2 request of 4 sectors) and write the 8 chunks of one swizzled row = 8
+                // different bank groups.
+                const int rr = lane >> 3, jch = lane & 7;
                 const uint32_t slot_addr = ring_addr + (uint32_t)wid * SLOT;
                 uint32_t *pw = reinterpret_cast<uint32_t *>(smem_raw + of.pw);
                 const int nwp = p.nwp;
@@ -278,44 +280,60 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
                     pw[i] = word;
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(NPROD * 32) : "memory");
-                // per-lane constants of the copy: source byte inside an entry, destination byte inside a row group
-                const uint32_t src_off = (uint32_t)(pp * 32 + h * 16);
-                const uint32_t swz = (uint32_t)((b >> 2) & 1);  // SWIZZLE_32B: rows 4-7 swap their halves
-                const uint32_t dst_off = (uint32_t)(pp * PLANE + b * 32) + (((uint32_t)h ^ swz) << 4);
+                // per-lane constants of the copy: destination bytes of the two rows inside a group
+                const uint32_t dst0 = (uint32_t)(rr * 128 + ((jch ^ rr) << 4));
+                const uint32_t dst1 = (uint32_t)((rr + 4) * 128 + ((jch ^ (rr + 4)) << 4));
                 for (uint32_t tl = ((uint32_t)wid - kt) & 7u; tl < ntiles; tl += NPROD) {
                     const uint32_t use = (kt + tl) >> 3;
                     const long long q0 = now();
                     if (use > 0) fxd::mbar_wait(&empty[wid], (use - 1) & 1);  // the MMAs that read this slot retired
                     const long long q1 = now();
                     const int item = (int)tl / nti, q = (int)tl - item * nti;
-                    const int sl = item * 8 + b;
                     if (PROF && (p.dbg & 2)) { if (lane == 0) mbar_arrive(&full[wid]); continue; }
-                    const bool stream_ok = sl < s_grp;
-                    // residues 16(q-1) .. 16(q+2)-1 of stream b (word index + 1 in the padded array)
-                    const uint32_t *ws = pw + (stream_ok ? sl : 0) * nwp + q;
-                    const uint32_t w0 = ws[0], w1 = ws[1], w2 = (q + 2 < nwp) ? ws[2] : 0u;
+                    // residues 16(q-1) .. 16(q+2)-1 of the lane's two streams (word index + 1 in the padded array)
+                    const int sl0 = item * 8 + rr, sl1 = sl0 + 4;
+                    const bool ok0 = sl0 < s_grp, ok1 = sl1 < s_grp;
+                    const uint32_t *ws0 = pw + (ok0 ? sl0 : 0) * nwp + q, *ws1 = pw + (ok1 ? sl1 : 0) * nwp + q;
+                    const uint32_t u0 = ws0[0], u1 = ws0[1], u2 = ws0[2];
+                    const uint32_t v0 = ws1[0], v1 = ws1[1], v2 = ws1[2];
+                    const unsigned char *tabj = tab + jch * 16;
+                    // the window of input row c (h2 position o = 16 q + c - 1) starts at residue o - 2, i.e. 2 (c + 13) bits
+                    // into w0:w1:w2 — a compile-time shift
+                    auto code_of = [](int c, uint32_t x0, uint32_t x1, uint32_t x2) -> uint32_t {
+                        if (c < 3) return __funnelshift_l(x1, x0, 2 * (c + 13)) >> 14;
+                        if (c <= 10) return (x1 << (2 * (c - 3))) >> 14;
+                        return __funnelshift_l(x2, x1, 2 * (c - 3)) >> 14;
+                    };
+                    if (q > 0 && 16 * q + 16 <= T - 3 && item * 8 + 7 < s_grp) {
+                        // interior tile of a complete item (4 of 6 tiles of a 100-mer): every row is a full 9-residue
+                        // window of an existing sequence — code, one multiply-add for the address, copy
 #pragma unroll
-                    for (int c = 0; c < CM; ++c) {
-                        // input row c of the tile = h2 position o = 16 q + c - 1; its window starts at residue o - 2,
-                        // i.e. 2 (c + 13) bits into w0:w1:w2 (a compile-time shift)
-                        const int o = 16 * q + c - 1;
-                        constexpr int dummy = 0; (void)dummy;
-                        uint32_t code;
-                        if (c < 3) code = __funnelshift_l(w1, w0, 2 * (c + 13)) >> 14;
-                        else if (c <= 10) code = (w1 << (2 * (c - 3))) >> 14;
-                        else code = __funnelshift_l(w2, w1, 2 * (c - 3)) >> 14;
-                        // truncated windows: o = 0, 1 read zeros in front (the code is already that of the short window),
-                        // o = T-2, T-1 drop the residues past the end
-                        uint32_t ent = code;
-                        if (o <= 1) ent = code + (o == 0 ? ENT_EL0 : ENT_EL1);
-                        if (o >= T - 2) ent = (o == T - 2) ? ENT_ER1 + (code >> 2) : ENT_ER0 + (code >> 4);
-                        const bool row_ok = stream_ok && o >= 0 && o < T;
-                        const unsigned char *src = tab + (row_ok ? (size_t)ent * 128 : (size_t)0) + src_off;
-                        const uint32_t nbytes = row_ok ? 16u : 0u;  // 0 -> cp.async zero-fills
-                        const uint32_t dst = slot_addr + dst_off + (uint32_t)(c * 256);
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 2u * PLANE), "l"(src + 64),
-                                     "r"(nbytes) : "memory");
+                        for (int c = 0; c < CM; ++c) {
+                            const unsigned char *src0 = tabj + (size_t)code_of(c, u0, u1, u2) * 128;
+                            const unsigned char *src1 = tabj + (size_t)code_of(c, v0, v1, v2) * 128;
+                            const uint32_t grp = slot_addr + (uint32_t)(c * 1024);
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(grp + dst0), "l"(src0) : "memory");
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(grp + dst1), "l"(src1) : "memory");
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < CM; ++c) {
+                            const int o = 16 * q + c - 1;
+                            const uint32_t code0 = code_of(c, u0, u1, u2), code1 = code_of(c, v0, v1, v2);
+                            // truncated windows: o = 0, 1 read zeros in front (the code is already that of the short
+                            // window), o = T-2, T-1 drop the residues past the end
+                            uint32_t base = 0, rsh = 0;
+                            if (o <= 1) base = (o == 0 ? ENT_EL0 : ENT_EL1);
+                            if (o >= T - 2) { base = (o == T - 2) ? ENT_ER1 : ENT_ER0; rsh = (o == T - 2) ? 2 : 4; }
+                            const bool pos_ok = o >= 0 && o < T;
+                            const bool r0 = pos_ok && ok0, r1 = pos_ok && ok1;
+                            const unsigned char *src0 = tabj + (r0 ? (size_t)(base + (code0 >> rsh)) * 128 : (size_t)0);
+                            const unsigned char *src1 = tabj + (r1 ? (size_t)(base + (code1 >> rsh)) * 128 : (size_t)0);
+                            const uint32_t grp = slot_addr + (uint32_t)(c * 1024);
+                            // src-size 0 -> cp.async zero-fills ("same" padding of conv3, rows past the sequence, absent streams)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(grp + dst0), "l"(src0), "r"(r0 ? 16u : 0u) : "memory");
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(grp + dst1), "l"(src1), "r"(r1 ? 16u : 0u) : "memory");
+                        }
                     }
                     asm volatile("cp.async.wait_all;" ::: "memory");
                     fence_async_smem();
@@ -324,68 +342,80 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
                     if (PROF && tid == 0) { pt[2] += q1 - q0; pt[3] += now() - q1; }
                 }
             } else if (wid < MMAW) {
-                // =========================== conv3 epilogue: bias, ReLU, running max per sequence ===========================
-                const int lq = wid & 3, ch = (wid >> 2) & 1;
+                // =========================== conv3 epilogue: running max per sequence ===========================
+                // Warp (lq, par) owns TMEM lanes 32 lq .. 32 lq + 31 of the tiles of parity par and all 32 filters: the
+                // fixed cost of a visit (barrier wake-up, TMEM load latency) is paid once per two tiles.
+                // max_t relu(a_t * inv3 + b) == relu(max_t(a_t) * inv3 + b) (inv3 > 0): per tile only one packed add of
+                // the two accumulator halves and one fmaxf per filter; scale, bias and ReLU wait for the item's end.
+                const int lq = wid & 3, par = (wid >> 2) & 1;
                 // TMEM lane 32 lq + lane is MMA row 8 c + b: position c of stream b
                 const int c = 4 * lq + (lane >> 3), b = lane & 7;
-                const uint32_t tlane = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(ch * 16);
-                // max_t relu(a_t * inv3 + b) == relu(max_t(a_t) * inv3 + b) (inv3 > 0): the per-tile work is one packed add
-                // of the two accumulator halves and one fmaxf per filter; scale, bias and ReLU wait for the item's end
-                float mx[16];
+                const uint32_t tlane = tmem_base + ((uint32_t)(lq * 32) << 16);
+                const bool up8 = (lane & 8) != 0, up16 = (lane & 16) != 0;
+                float mx[32];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) mx[j] = -INFINITY;
-                int q = 0, item = 0;
-                for (uint32_t tl = 0; tl < ntiles; ++tl) {
+                for (int j = 0; j < 32; ++j) mx[j] = -INFINITY;
+                // GlobalMaxPooling1D: the 4 lanes of stream b merge their maxima with a halving butterfly — after the
+                // xor-8 step a lane keeps filters 16 (lane bit 3) + 0..15, after the xor-16 step 8 of those — then scale,
+                // bias and ReLU, and the warps that saw the item meet in shared memory
+                auto flush = [&](int item) {
+                    const int sl = item * 8 + b;
+                    float k16[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float send = up8 ? mx[j] : mx[j + 16], keep = up8 ? mx[j + 16] : mx[j];
+                        k16[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+                    }
+                    const int f0 = (up8 ? 16 : 0) + (up16 ? 8 : 0);
+                    unsigned int *dstf = reinterpret_cast<unsigned int *>(featT) + (size_t)f0 * SBP + sl;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float send = up16 ? k16[j] : k16[j + 8], keep = up16 ? k16[j + 8] : k16[j];
+                        const float t = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+                        const float r = fmaxf(fmaf(t, inv3, b3[f0 + j]), 0.f);
+                        if (sl < s_grp) atomicMax(dstf + (size_t)j * SBP, __float_as_uint(r));  // r >= 0: uint order
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mx[j] = -INFINITY;
+                };
+                int cur_item = -1;
+                for (uint32_t tl = ((uint32_t)par - kt) & 1u; tl < ntiles; tl += 2) {
                     const uint32_t k = kt + tl, acc = k & 7u;
+                    const int item = (int)tl / nti, q = (int)tl - item * nti;
+                    if (item != cur_item) {
+                        if (cur_item >= 0) flush(cur_item);
+                        cur_item = item;
+                    }
                     const long long w0 = now();
                     fxd::mbar_wait(&tfull[acc], (k >> 3) & 1);
                     const long long w1 = now();
                     tc_fence_after();
-                    uint32_t v[16], v2[16];
-                    tmem_ld16_nowait(tlane + acc * 64u, v);
-                    tmem_ld16_nowait(tlane + acc * 64u + 32u, v2);
-                    tmem_ld_wait();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[acc]);  // the accumulator is in registers: hand it back
-                    const long long w2 = now();
-                    if (!(PROF && (p.dbg & 4)) && 16 * q + c < T) {  // rows past the sequence exist only in its last tile
+                    const bool valid = !(PROF && (p.dbg & 4)) && 16 * q + c < T;  // rows past the sequence: last tile only
 #pragma unroll
-                        for (int j = 0; j < 16; j += 2) {
-                            float a0, a1;
-                            add_f32x2(a0, a1, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v2[j]),
-                                      __uint_as_float(v2[j + 1]));
-                            mx[j] = fmaxf(mx[j], a0);
-                            mx[j + 1] = fmaxf(mx[j + 1], a1);
+                    for (int hf = 0; hf < 2; ++hf) {
+                        uint32_t v[16], v2[16];
+                        tmem_ld16_nowait(tlane + acc * 64u + (uint32_t)(hf * 16), v);
+                        tmem_ld16_nowait(tlane + acc * 64u + 32u + (uint32_t)(hf * 16), v2);
+                        tmem_ld_wait();
+                        if (hf == 1) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tempty[acc]);  // the accumulator is in registers: hand it back
+                        }
+                        if (valid) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 2) {
+                                float a0, a1;
+                                add_f32x2(a0, a1, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v2[j]),
+                                          __uint_as_float(v2[j + 1]));
+                                mx[hf * 16 + j] = fmaxf(mx[hf * 16 + j], a0);
+                                mx[hf * 16 + j + 1] = fmaxf(mx[hf * 16 + j + 1], a1);
+                            }
                         }
                     }
-                    if (++q == nti) {
-                        // GlobalMaxPooling1D: the 4 lanes of stream b merge their maxima with a halving butterfly — after
-                        // the xor-8 step a lane keeps filters 8 (lane bit 3) + 0..7, after the xor-16 step 4 of those —
-                        // then scale, bias and ReLU, and the 4 warps of this half meet in shared memory
-                        const int sl = item * 8 + b;
-                        const bool up8 = (lane & 8) != 0, up16 = (lane & 16) != 0;
-                        float k8[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float send = up8 ? mx[j] : mx[j + 8], keep = up8 ? mx[j + 8] : mx[j];
-                            k8[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
-                        }
-                        const int f0 = ch * 16 + (up8 ? 8 : 0) + (up16 ? 4 : 0);
-                        unsigned int *dstf = reinterpret_cast<unsigned int *>(featT) + (size_t)f0 * SBP + sl;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float send = up16 ? k8[j] : k8[j + 4], keep = up16 ? k8[j + 4] : k8[j];
-                            const float t = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 16));
-                            const float r = fmaxf(fmaf(t, inv3, b3[f0 + j]), 0.f);
-                            if (sl < s_grp) atomicMax(dstf + (size_t)j * SBP, __float_as_uint(r));  // r >= 0: uint order
-                        }
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) mx[j] = -INFINITY;
-                        q = 0; ++item;
-                    }
-                    if (PROF && tid == 8 * 32) { pt[4] += w1 - w0; pt[8] += w2 - w1; pt[9] += now() - w2; }
+                    if (PROF && tid == 8 * 32) { pt[4] += w1 - w0; pt[9] += now() - w1; }
                 }
+                if (cur_item >= 0) flush(cur_item);
             } else {
                 // =========================== MMA issuers ===========================
                 // Two warps take alternate tiles: issuing a tile (two barrier waits, 12 MMAs, two commits) costs more
@@ -519,9 +549,9 @@ int launch_cnn_k9(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out,
         for (int b = 0; b < grid; ++b) for (int i = 0; i < 16; ++i) a[i] += (double)h[(size_t)b * 16 + i] / grid;
         const double nt = a[7] > 0 ? a[7] : 1;
         fprintf(stderr, "[k9 prof] n=%lld grid=%d tiles/CTA=%.0f | cycles per tile: pipeline %.0f, dense+drain %.0f | "
-                        "producer warp 0 (per own tile = 1/8 of tiles): wait slot %.0f, gather %.0f | epilogue warp 8: wait MMA %.0f, tmem ld %.0f, math+flush %.0f | "
+                        "producer warp 0 (per own tile = 1/8 of tiles): wait slot %.0f, gather %.0f | epilogue warp 8 (per own tile = 1/2 of tiles): wait MMA %.0f, load+max+flush %.0f | "
                         "MMA warp 16 (per own tile = 1/2 of tiles): wait operands %.0f, wait accumulator %.0f\n",
-                (long long)n, grid, a[7], a[0] / nt, a[1] / nt, a[2] / nt * 8, a[3] / nt * 8, a[4] / nt, a[8] / nt, a[9] / nt, a[5] / nt * 2, a[6] / nt * 2);
+                (long long)n, grid, a[7], a[0] / nt, a[1] / nt, a[2] / nt * 8, a[3] / nt * 8, a[4] / nt * 2, a[9] / nt * 2, a[5] / nt * 2, a[6] / nt * 2);
     }
     // fp16 range guard: the gated FFMA kernel recomputes the batch iff the flag was raised
     return launch_cnn_tiled_gated(m, d_idx, n, d_out, m->d_flag, s);
