@@ -131,6 +131,7 @@ void flexs_model_destroy(flexs_model_t *m) {
     cudaFree(m->d_umma2_w);
     cudaFree(m->d_k9_tab);
     cudaFree(m->d_k9_ovf);
+    for (auto &w : m->k9_ws) cudaFree(w.ptr);
     cudaFree(m->d_flag);
     cudaFree(m->d_adam_m);
     cudaFree(m->d_adam_v);
@@ -191,7 +192,7 @@ int flexs_model_set_variant(flexs_model_t *m, int variant) {
     if (m->kind == FLEXS_KIND_CNN) {
         if (variant == FLEXS_VARIANT_TILED) FX_REQUIRE(cnn_tiled_supported(m), "TILED variant needs F=32, k=5, A in {4,20}");
         if (variant == FLEXS_VARIANT_UMMA) FX_REQUIRE(cnn_umma_supported(m), "UMMA variant not available for this shape");
-        if (variant == FLEXS_VARIANT_UMMA_LUT) FX_REQUIRE(cnn_k9_supported(m), "UMMA_LUT variant needs A=4, F=32, k=5, H<=112, 20 <= L <~ 190");
+        if (variant == FLEXS_VARIANT_UMMA_LUT) FX_REQUIRE(cnn_k9_supported(m), "UMMA_LUT variant needs A=4, F=32, k=5, H<=112, 20 <= L <= ~175");
     } else {
         FX_REQUIRE(variant == FLEXS_VARIANT_AUTO, "MLP has a single kernel");
     }

@@ -15,9 +15,12 @@
 // a thread of the epilogue sees ONE sequence for the whole item, so GlobalMaxPooling1D is a running fmaxf in registers
 // (two shuffles and four shared atomics per item instead of a REDUX round per tile and sequence).
 //
-// Roles (17 warps): 0-7 producers (warp w owns ring slot w: residues -> table index -> gathers), 8-15 conv3 epilogue,
-// 16 issues the MMAs.  Eight operand slots and eight TMEM accumulators (64 columns each) keep all three busy; every
-// 128 sequences the pipeline drains and the dense head (u2::dense_head_umma) runs on the idle ring memory.
+// Roles (18 warps): 0-7 producers (warp w owns ring slot w: packed residues -> table index -> 128-byte gathers into a
+// SWIZZLE_128B operand slot), 8-15 conv3 epilogue (alternate tiles, running max in registers), 16-17 issue the MMAs of
+// alternate tiles.  Eight operand slots and eight TMEM accumulators (64 columns each); the roles only meet through
+// mbarriers, there is no CTA-wide barrier inside the kernel.  The pooled features of every 128 sequences leave as a
+// [32][128] fp32 tile (16 KB); cnn_k9_dense_kernel turns those tiles into scores with two tcgen05 GEMMs per tile,
+// its weights staged once per CTA.
 #include <cuda_fp16.h>
 
 #include <algorithm>
@@ -39,7 +42,6 @@ constexpr int CM = 16 + K3 - 1;         // 8-row groups per tile (16 positions +
 constexpr int SLOT = CM * 1024;         // rows of 128 B = one table entry: hi ch 0-15 | hi 16-31 | lo 0-15 | lo 16-31,
                                         // K-major SWIZZLE_128B (16-byte chunk j of row r sits at chunk j ^ (r & 7))
 constexpr int GS = DSLOTS, SBP = GS + 4;  // sequences per dense-head batch, padded feature row
-static_assert(RING * SLOT >= DS_TOTAL, "dense scratch must fit the operand ring");
 
 // table segments (entries of 128 B): interior | o = 0 | o = 1 | o = T-2 | o = T-1
 constexpr int N_MAIN = 1 << 18, N_E7 = 1 << 14, N_E8 = 1 << 16;
@@ -48,22 +50,31 @@ constexpr int N_ENT = ENT_ER0 + N_E7;
 constexpr size_t TAB_BYTES = (size_t)N_ENT * 128;
 
 struct K9Params {
-    const uint8_t *idx;
-    float *out;
-    const float *weights;
-    const unsigned char *uw;   // cnn_umma2's operand blob (UW3, scales, dense planes)
-    const unsigned char *tab;  // [M][N_ENT][128 B]
+    const uint8_t *idx;        // [n][L] residues of this launch
+    float *feat;               // [n_groups][32][128] pooled features (workspace)
+    const float *weights;      // this member's fp32 block (b3)
+    const unsigned char *uw;   // this member's operand blob of cnn_umma2 (UW3, scales)
+    const unsigned char *tab;  // this member's table [N_ENT][128 B]
     const int *tab_ovf;        // raised by the builder when an entry left the fp16 window
     int *overflow_flag;
-    int64_t n, n_groups, member_floats, uw_member_bytes;
+    int64_t n, n_groups;
     fx::CnnOffsets o;
-    int M, L, T, nti, idx_slot, nwp;
+    int L, T, nti, idx_slot, nwp;
     long long *prof;
-    int dbg;  // profiling knobs (FLEXS_UMMA_DBG bitmask): 1 skip the MMAs, 2 skip the gathers, 4 skip the epilogue math
+    int dbg;  // profiling knobs (FLEXS_UMMA_DBG bitmask, PROF build only): 1 skip the MMAs, 2 skip the gathers, 4 skip the epilogue math
+};
+
+struct DenseParams {
+    const float *feat;
+    float *out;
+    const unsigned char *uw;
+    int *overflow_flag;
+    int64_t n, n_groups;
+    int mem, M;
 };
 
 struct Offs {
-    int mbar, tm, b3, uw3, i0, i1, pw, feat, ring;
+    int mbar, tm, b3, uw3, idx, pw, feat, ring;
     size_t total;
 };
 
@@ -80,9 +91,9 @@ __host__ __device__ inline Offs carve(const K9Params &p) {
     };
     o.mbar = take(64 * 8, 16); o.tm = take(16, 16); o.b3 = take(F * 4, 16);
     o.uw3 = take((size_t)K3 * UWTAP, 128);
-    o.i0 = take(p.idx_slot, 16); o.i1 = take(p.idx_slot, 16);
-    o.pw = take((size_t)GS * p.nwp * 4, 16);
-    o.feat = take((size_t)F * SBP * 4, 16);
+    o.idx = take(p.idx_slot, 16);
+    o.pw = take((size_t)2 * GS * p.nwp * 4, 16);
+    o.feat = take((size_t)2 * F * SBP * 4, 16);
     o.ring = take((size_t)RING * SLOT, 1024);
     o.total = off;
     return o;
@@ -144,7 +155,17 @@ __global__ void __launch_bounds__(256) k9_build_kernel(const float *__restrict__
     if (bad) atomicExch(ovf, 1);
 }
 
-// ---- forward -------------------------------------------------------------------------------------------------
+// ---- forward: conv kernel -----------------------------------------------------------------------------------
+// packed fp32 add (sm_100 FADD2): two accumulator halves of two filters per instruction
+__device__ __forceinline__ void add_f32x2(float &x0, float &x1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 rc, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rc;\n\t}"
+        : "=f"(x0), "=f"(x1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
+
 // A operand: K-major SWIZZLE_128B, the canonical UMMA layout: 8-row groups of 1024 B (SBO), a K step of 16 channels is
 // 32 B further into the row (start address + 32 B; the hardware applies the XOR to the final address), a tap is one
 // group = +1024 B.  hi word: SBO = 1024 B, version 1, layout type 2 (bits 61-63).
@@ -165,16 +186,6 @@ __device__ __forceinline__ void issue_conv3_tile(uint32_t a_slot_addr, uint32_t 
         }
     }
 }
-
-// packed fp32 add (sm_100 FADD2): two accumulator halves of two filters per instruction
-__device__ __forceinline__ void add_f32x2(float &x0, float &x1, float a0, float a1, float b0, float b1) {
-    asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
-        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
-        "add.rn.f32x2 rc, ra, rb;\n\t"
-        "mov.b64 {%0, %1}, rc;\n\t}"
-        : "=f"(x0), "=f"(x1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
-}
-
 
 __device__ __forceinline__ void issue_idx_load(const K9Params &p, uint8_t *dst, uint64_t *bar, int64_t group) {
     const int64_t first = group * GS;
@@ -199,19 +210,18 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const Offs of = carve(p);
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + of.mbar);
-    uint64_t *mbar_idx = mbar, *dbar = mbar + 2, *full = mbar + 8, *empty = mbar + 16, *tfull = mbar + 24, *tempty = mbar + 32;
+    uint64_t *mbar_idx = mbar, *full = mbar + 8, *empty = mbar + 16, *tfull = mbar + 24, *tempty = mbar + 32;
     uint32_t *tmem_addr_s = reinterpret_cast<uint32_t *>(smem_raw + of.tm);
     float *b3 = reinterpret_cast<float *>(smem_raw + of.b3);
     unsigned char *uw3 = smem_raw + of.uw3;
-    float *featT = reinterpret_cast<float *>(smem_raw + of.feat);
+    float *feat_s = reinterpret_cast<float *>(smem_raw + of.feat);
     unsigned char *ring = smem_raw + of.ring;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int L = p.L, T = p.T, nti = p.nti;
 
     if (tid == 0) {
-        fxd::mbar_init(&mbar_idx[0], 1); fxd::mbar_init(&mbar_idx[1], 1);
-        fxd::mbar_init(dbar, 1);
+        fxd::mbar_init(mbar_idx, 1);
         for (int i = 0; i < RING; ++i) {
             fxd::mbar_init(&full[i], 1); fxd::mbar_init(&empty[i], 1);
             fxd::mbar_init(&tfull[i], 1); fxd::mbar_init(&tempty[i], 4);
@@ -219,247 +229,288 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
         fxd::fence_mbar_init();
     }
     if (wid == 0) tmem_alloc(tmem_addr_s, 512);
-    for (int i = tid; i < F * SBP; i += NT) featT[i] = 0.f;
+    for (int i = tid; i < 2 * F * SBP; i += NT) feat_s[i] = 0.f;
+    const float inv3 = __ldg(reinterpret_cast<const float *>(p.uw + OFF_SCAL) + 1);
+    for (int i = tid; i < F; i += NT) b3[i] = __ldg(p.weights + p.o.b3 + i);
+    for (int i = tid; i < K3 * UWTAP / 16; i += NT)
+        reinterpret_cast<uint4 *>(uw3)[i] = __ldg(reinterpret_cast<const uint4 *>(p.uw + OFF_UW3) + i);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_addr_s;
     const uint32_t ring_addr = fxd::smem_u32(ring), uw3_addr = fxd::smem_u32(uw3);
+    if (tid == 0) issue_idx_load(p, smem_raw + of.idx, mbar_idx, blockIdx.x);
 
-    uint32_t kt = 0;   // tiles done (running over groups and members): slot = accumulator = kt & 7
-    uint32_t gi = 0;   // groups done: residue buffer = gi & 1
-    uint32_t dph = 0;  // completed phases of the dense-head barrier
-    float xmax = 0.f;  // largest dense-head activation written as fp16 (range guard)
-    long long pt[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t kt = 0;  // tiles before the current group: tile k uses slot = accumulator = k & 7
+    uint32_t gi = 0;  // groups before the current one: packed-residue / feature buffer = gi & 1
+    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long t_begin = now();
 
-    for (int mem = 0; mem < p.M; ++mem) {
-        const float *w = p.weights + (int64_t)mem * p.member_floats;
-        const unsigned char *uw = p.uw + (int64_t)mem * p.uw_member_bytes;
-        const unsigned char *tab = p.tab + (size_t)mem * TAB_BYTES;
-        const float inv3 = __ldg(reinterpret_cast<const float *>(uw + OFF_SCAL) + 1);
-        __syncthreads();
-        for (int i = tid; i < F; i += NT) b3[i] = __ldg(w + p.o.b3 + i);
-        for (int i = tid; i < K3 * UWTAP / 16; i += NT)
-            reinterpret_cast<uint4 *>(uw3)[i] = __ldg(reinterpret_cast<const uint4 *>(uw + OFF_UW3) + i);
-        fence_async_smem();
-        __syncthreads();
-        if (tid == 0 && (int64_t)blockIdx.x < p.n_groups)
-            issue_idx_load(p, smem_raw + ((gi & 1) ? of.i1 : of.i0), &mbar_idx[gi & 1], blockIdx.x);
-
+    if (wid < NPROD) {
+        // =========================== producers: residues -> table rows -> operand slot ===========================
+        // lane = 8 rr + j moves 16-byte chunk j of the rows of streams rr and rr + 4: eight adjacent lanes read one whole
+        // 128-byte entry (one L2 request of 4 sectors) and write the 8 chunks of one swizzled row = 8 bank groups.
+        const int rr = lane >> 3, jch = lane & 7;
+        const uint32_t slot_addr = ring_addr + (uint32_t)wid * SLOT;
+        const uint32_t dst0 = (uint32_t)(rr * 128 + ((jch ^ rr) << 4));
+        const uint32_t dst1 = (uint32_t)((rr + 4) * 128 + ((jch ^ (rr + 4)) << 4));
+        const unsigned char *tabj = p.tab + jch * 16;
+        const int nwp = p.nwp;
         for (int64_t g = blockIdx.x; g < p.n_groups; g += gridDim.x, ++gi) {
             const int64_t first = g * GS;
             const int s_grp = (int)min((int64_t)GS, p.n - first);
             const uint32_t ntiles = (uint32_t)(((s_grp + 7) >> 3) * nti);
-            const int buf = gi & 1;
-            const long long tg0 = now();
-
-            if (wid < NPROD) {
-                // =========================== producers: residues -> table rows -> operand slot ===========================
-                // lane = 8 rr + j moves 16-byte chunk j of the rows of streams rr and rr + 4: eight adjacent lanes read one
-                // whole 128-byte entry (one L2 request of 4 sectors) and write the 8 chunks of one swizzled row = 8
-                // different bank groups.
-                const int rr = lane >> 3, jch = lane & 7;
-                const uint32_t slot_addr = ring_addr + (uint32_t)wid * SLOT;
-                uint32_t *pw = reinterpret_cast<uint32_t *>(smem_raw + of.pw);
-                const int nwp = p.nwp;
-                fxd::mbar_wait(&mbar_idx[buf], (gi >> 1) & 1);
-                const uint8_t *sidx = smem_raw + (buf ? of.i1 : of.i0) +
-                                      ((reinterpret_cast<uintptr_t>(p.idx) + (uintptr_t)(first * L)) & 15);
-                // residues -> 2 bits each, 16 per word, first residue in the top bits; a zero word on either side
-                for (int i = tid; i < s_grp * nwp; i += NPROD * 32) {
-                    const int sq = i / nwp, wv = i - sq * nwp - 1;
-                    uint32_t word = 0;
-                    if (wv >= 0 && wv * 16 < L) {
-                        const uint8_t *src = sidx + sq * L + wv * 16;
-                        const int cnt = min(16, L - wv * 16);
+            uint32_t *pw = reinterpret_cast<uint32_t *>(smem_raw + of.pw) + (gi & 1) * GS * nwp;
+            fxd::mbar_wait(mbar_idx, gi & 1);
+            const uint8_t *sidx = smem_raw + of.idx + ((reinterpret_cast<uintptr_t>(p.idx) + (uintptr_t)(first * L)) & 15);
+            // residues -> 2 bits each, 16 per word, first residue in the top bits; a zero word on either side
+            for (int i = tid; i < s_grp * nwp; i += NPROD * 32) {
+                const int sq = i / nwp, wv = i - sq * nwp - 1;
+                uint32_t word = 0;
+                if (wv >= 0 && wv * 16 < L) {
+                    const uint8_t *src = sidx + sq * L + wv * 16;
+                    const int cnt = min(16, L - wv * 16);
 #pragma unroll
-                        for (int r = 0; r < 16; ++r)
-                            word = (word << 2) | (r < cnt ? (uint32_t)(src[r] & 3) : 0u);
-                    }
-                    pw[i] = word;
+                    for (int r = 0; r < 16; ++r) word = (word << 2) | (r < cnt ? (uint32_t)(src[r] & 3) : 0u);
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(NPROD * 32) : "memory");
-                // per-lane constants of the copy: destination bytes of the two rows inside a group
-                const uint32_t dst0 = (uint32_t)(rr * 128 + ((jch ^ rr) << 4));
-                const uint32_t dst1 = (uint32_t)((rr + 4) * 128 + ((jch ^ (rr + 4)) << 4));
-                for (uint32_t tl = ((uint32_t)wid - kt) & 7u; tl < ntiles; tl += NPROD) {
-                    const uint32_t use = (kt + tl) >> 3;
-                    const long long q0 = now();
-                    if (use > 0) fxd::mbar_wait(&empty[wid], (use - 1) & 1);  // the MMAs that read this slot retired
-                    const long long q1 = now();
-                    const int item = (int)tl / nti, q = (int)tl - item * nti;
-                    if (PROF && (p.dbg & 2)) { if (lane == 0) mbar_arrive(&full[wid]); continue; }
-                    // residues 16(q-1) .. 16(q+2)-1 of the lane's two streams (word index + 1 in the padded array)
-                    const int sl0 = item * 8 + rr, sl1 = sl0 + 4;
-                    const bool ok0 = sl0 < s_grp, ok1 = sl1 < s_grp;
-                    const uint32_t *ws0 = pw + (ok0 ? sl0 : 0) * nwp + q, *ws1 = pw + (ok1 ? sl1 : 0) * nwp + q;
-                    const uint32_t u0 = ws0[0], u1 = ws0[1], u2 = ws0[2];
-                    const uint32_t v0 = ws1[0], v1 = ws1[1], v2 = ws1[2];
-                    const unsigned char *tabj = tab + jch * 16;
-                    // the window of input row c (h2 position o = 16 q + c - 1) starts at residue o - 2, i.e. 2 (c + 13) bits
-                    // into w0:w1:w2 — a compile-time shift
-                    auto code_of = [](int c, uint32_t x0, uint32_t x1, uint32_t x2) -> uint32_t {
-                        if (c < 3) return __funnelshift_l(x1, x0, 2 * (c + 13)) >> 14;
-                        if (c <= 10) return (x1 << (2 * (c - 3))) >> 14;
-                        return __funnelshift_l(x2, x1, 2 * (c - 3)) >> 14;
-                    };
-                    if (q > 0 && 16 * q + 16 <= T - 3 && item * 8 + 7 < s_grp) {
-                        // interior tile of a complete item (4 of 6 tiles of a 100-mer): every row is a full 9-residue
-                        // window of an existing sequence — code, one multiply-add for the address, copy
-#pragma unroll
-                        for (int c = 0; c < CM; ++c) {
-                            const unsigned char *src0 = tabj + (size_t)code_of(c, u0, u1, u2) * 128;
-                            const unsigned char *src1 = tabj + (size_t)code_of(c, v0, v1, v2) * 128;
-                            const uint32_t grp = slot_addr + (uint32_t)(c * 1024);
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(grp + dst0), "l"(src0) : "memory");
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(grp + dst1), "l"(src1) : "memory");
-                        }
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < CM; ++c) {
-                            const int o = 16 * q + c - 1;
-                            const uint32_t code0 = code_of(c, u0, u1, u2), code1 = code_of(c, v0, v1, v2);
-                            // truncated windows: o = 0, 1 read zeros in front (the code is already that of the short
-                            // window), o = T-2, T-1 drop the residues past the end
-                            uint32_t base = 0, rsh = 0;
-                            if (o <= 1) base = (o == 0 ? ENT_EL0 : ENT_EL1);
-                            if (o >= T - 2) { base = (o == T - 2) ? ENT_ER1 : ENT_ER0; rsh = (o == T - 2) ? 2 : 4; }
-                            const bool pos_ok = o >= 0 && o < T;
-                            const bool r0 = pos_ok && ok0, r1 = pos_ok && ok1;
-                            const unsigned char *src0 = tabj + (r0 ? (size_t)(base + (code0 >> rsh)) * 128 : (size_t)0);
-                            const unsigned char *src1 = tabj + (r1 ? (size_t)(base + (code1 >> rsh)) * 128 : (size_t)0);
-                            const uint32_t grp = slot_addr + (uint32_t)(c * 1024);
-                            // src-size 0 -> cp.async zero-fills ("same" padding of conv3, rows past the sequence, absent streams)
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(grp + dst0), "l"(src0), "r"(r0 ? 16u : 0u) : "memory");
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(grp + dst1), "l"(src1), "r"(r1 ? 16u : 0u) : "memory");
-                        }
-                    }
-                    asm volatile("cp.async.wait_all;" ::: "memory");
-                    fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&full[wid]);
-                    if (PROF && tid == 0) { pt[2] += q1 - q0; pt[3] += now() - q1; }
-                }
-            } else if (wid < MMAW) {
-                // =========================== conv3 epilogue: running max per sequence ===========================
-                // Warp (lq, par) owns TMEM lanes 32 lq .. 32 lq + 31 of the tiles of parity par and all 32 filters: the
-                // fixed cost of a visit (barrier wake-up, TMEM load latency) is paid once per two tiles.
-                // max_t relu(a_t * inv3 + b) == relu(max_t(a_t) * inv3 + b) (inv3 > 0): per tile only one packed add of
-                // the two accumulator halves and one fmaxf per filter; scale, bias and ReLU wait for the item's end.
-                const int lq = wid & 3, par = (wid >> 2) & 1;
-                // TMEM lane 32 lq + lane is MMA row 8 c + b: position c of stream b
-                const int c = 4 * lq + (lane >> 3), b = lane & 7;
-                const uint32_t tlane = tmem_base + ((uint32_t)(lq * 32) << 16);
-                const bool up8 = (lane & 8) != 0, up16 = (lane & 16) != 0;
-                float mx[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) mx[j] = -INFINITY;
-                // GlobalMaxPooling1D: the 4 lanes of stream b merge their maxima with a halving butterfly — after the
-                // xor-8 step a lane keeps filters 16 (lane bit 3) + 0..15, after the xor-16 step 8 of those — then scale,
-                // bias and ReLU, and the warps that saw the item meet in shared memory
-                auto flush = [&](int item) {
-                    const int sl = item * 8 + b;
-                    float k16[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float send = up8 ? mx[j] : mx[j + 16], keep = up8 ? mx[j + 16] : mx[j];
-                        k16[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
-                    }
-                    const int f0 = (up8 ? 16 : 0) + (up16 ? 8 : 0);
-                    unsigned int *dstf = reinterpret_cast<unsigned int *>(featT) + (size_t)f0 * SBP + sl;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float send = up16 ? k16[j] : k16[j + 8], keep = up16 ? k16[j + 8] : k16[j];
-                        const float t = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 16));
-                        const float r = fmaxf(fmaf(t, inv3, b3[f0 + j]), 0.f);
-                        if (sl < s_grp) atomicMax(dstf + (size_t)j * SBP, __float_as_uint(r));  // r >= 0: uint order
-                    }
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) mx[j] = -INFINITY;
+                pw[i] = word;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NPROD * 32) : "memory");
+            // every producer has packed: the staging buffer is free for the next group's residues
+            if (tid == 0 && g + gridDim.x < p.n_groups) issue_idx_load(p, smem_raw + of.idx, mbar_idx, g + gridDim.x);
+            for (uint32_t tl = ((uint32_t)wid - kt) & 7u; tl < ntiles; tl += NPROD) {
+                const uint32_t use = (kt + tl) >> 3;
+                const long long q0 = now();
+                if (use > 0) fxd::mbar_wait(&empty[wid], (use - 1) & 1);  // the MMAs that read this slot retired
+                const long long q1 = now();
+                const int item = (int)tl / nti, q = (int)tl - item * nti;
+                if (PROF && (p.dbg & 2)) { if (lane == 0) mbar_arrive(&full[wid]); continue; }
+                // residues 16(q-1) .. 16(q+2)-1 of the lane's two streams (word index + 1 in the padded array)
+                const int sl0 = item * 8 + rr, sl1 = sl0 + 4;
+                const bool ok0 = sl0 < s_grp, ok1 = sl1 < s_grp;
+                const uint32_t *ws0 = pw + (ok0 ? sl0 : 0) * nwp + q, *ws1 = pw + (ok1 ? sl1 : 0) * nwp + q;
+                const uint32_t u0 = ws0[0], u1 = ws0[1], u2 = ws0[2];
+                const uint32_t v0 = ws1[0], v1 = ws1[1], v2 = ws1[2];
+                // the window of input row c (h2 position o = 16 q + c - 1) starts at residue o - 2, i.e. 2 (c + 13) bits
+                // into w0:w1:w2 — a compile-time shift
+                auto code_of = [](int c, uint32_t x0, uint32_t x1, uint32_t x2) -> uint32_t {
+                    if (c < 3) return __funnelshift_l(x1, x0, 2 * (c + 13)) >> 14;
+                    if (c <= 10) return (x1 << (2 * (c - 3))) >> 14;
+                    return __funnelshift_l(x2, x1, 2 * (c - 3)) >> 14;
                 };
-                int cur_item = -1;
-                for (uint32_t tl = ((uint32_t)par - kt) & 1u; tl < ntiles; tl += 2) {
-                    const uint32_t k = kt + tl, acc = k & 7u;
-                    const int item = (int)tl / nti, q = (int)tl - item * nti;
-                    if (item != cur_item) {
-                        if (cur_item >= 0) flush(cur_item);
-                        cur_item = item;
-                    }
-                    const long long w0 = now();
-                    fxd::mbar_wait(&tfull[acc], (k >> 3) & 1);
-                    const long long w1 = now();
-                    tc_fence_after();
-                    const bool valid = !(PROF && (p.dbg & 4)) && 16 * q + c < T;  // rows past the sequence: last tile only
+                if (q > 0 && 16 * q + 16 <= T - 3 && item * 8 + 7 < s_grp) {
+                    // interior tile of a complete item (4 of 6 tiles of a 100-mer): every row is a full 9-residue window
+                    // of an existing sequence — code, one multiply-add for the address, copy
 #pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-                        uint32_t v[16], v2[16];
-                        tmem_ld16_nowait(tlane + acc * 64u + (uint32_t)(hf * 16), v);
-                        tmem_ld16_nowait(tlane + acc * 64u + 32u + (uint32_t)(hf * 16), v2);
-                        tmem_ld_wait();
-                        if (hf == 1) {
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&tempty[acc]);  // the accumulator is in registers: hand it back
-                        }
-                        if (valid) {
-#pragma unroll
-                            for (int j = 0; j < 16; j += 2) {
-                                float a0, a1;
-                                add_f32x2(a0, a1, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v2[j]),
-                                          __uint_as_float(v2[j + 1]));
-                                mx[hf * 16 + j] = fmaxf(mx[hf * 16 + j], a0);
-                                mx[hf * 16 + j + 1] = fmaxf(mx[hf * 16 + j + 1], a1);
-                            }
-                        }
+                    for (int c = 0; c < CM; ++c) {
+                        const unsigned char *src0 = tabj + (size_t)code_of(c, u0, u1, u2) * 128;
+                        const unsigned char *src1 = tabj + (size_t)code_of(c, v0, v1, v2) * 128;
+                        const uint32_t grp = slot_addr + (uint32_t)(c * 1024);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(grp + dst0), "l"(src0) : "memory");
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(grp + dst1), "l"(src1) : "memory");
                     }
-                    if (PROF && tid == 8 * 32) { pt[4] += w1 - w0; pt[9] += now() - w1; }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < CM; ++c) {
+                        const int o = 16 * q + c - 1;
+                        const uint32_t code0 = code_of(c, u0, u1, u2), code1 = code_of(c, v0, v1, v2);
+                        // truncated windows: o = 0, 1 read zeros in front (the code is already that of the short window),
+                        // o = T-2, T-1 drop the residues past the end
+                        uint32_t base = 0, rsh = 0;
+                        if (o <= 1) base = (o == 0 ? ENT_EL0 : ENT_EL1);
+                        if (o >= T - 2) { base = (o == T - 2) ? ENT_ER1 : ENT_ER0; rsh = (o == T - 2) ? 2 : 4; }
+                        const bool pos_ok = o >= 0 && o < T;
+                        const bool r0 = pos_ok && ok0, r1 = pos_ok && ok1;
+                        const unsigned char *src0 = tabj + (r0 ? (size_t)(base + (code0 >> rsh)) * 128 : (size_t)0);
+                        const unsigned char *src1 = tabj + (r1 ? (size_t)(base + (code1 >> rsh)) * 128 : (size_t)0);
+                        const uint32_t grp = slot_addr + (uint32_t)(c * 1024);
+                        // src-size 0 -> cp.async zero-fills ("same" padding of conv3, rows past the sequence, absent streams)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(grp + dst0), "l"(src0), "r"(r0 ? 16u : 0u) : "memory");
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(grp + dst1), "l"(src1), "r"(r1 ? 16u : 0u) : "memory");
+                    }
                 }
-                if (cur_item >= 0) flush(cur_item);
-            } else {
-                // =========================== MMA issuers ===========================
-                // Two warps take alternate tiles: issuing a tile (two barrier waits, 12 MMAs, two commits) costs more
-                // issue time than the tensor pipe needs to run it, and tiles are independent (own slot, own accumulator;
-                // a commit tracks the MMAs of the committing thread).
-                const uint32_t me = (uint32_t)(wid - MMAW);
-                if (me == 0) {
-                    // prefetch the next group's residues into the other buffer: its last readers (the producers of the
-                    // previous group) finished before the dense-head barrier this warp has passed
-                    const int64_t next = g + gridDim.x;
-                    if (lane == 0 && next < p.n_groups)
-                        issue_idx_load(p, smem_raw + (buf ? of.i0 : of.i1), &mbar_idx[buf ^ 1], next);
-                    __syncwarp();
-                }
-                for (uint32_t tl = (me - kt) & (NMMA - 1); tl < ntiles; tl += NMMA) {
-                    const uint32_t k = kt + tl, s = k & 7u, use = k >> 3;
-                    const long long m0 = now();
-                    fxd::mbar_wait(&full[s], use & 1);
-                    const long long m1 = now();
-                    if (use > 0) fxd::mbar_wait(&tempty[s], (use - 1) & 1);  // accumulator drained by the epilogue
-                    if (PROF && lane == 0 && wid == MMAW) { pt[5] += m1 - m0; pt[6] += now() - m1; }
-                    tc_fence_after();
-                    if (!(PROF && (p.dbg & 1))) issue_conv3_tile(ring_addr + s * SLOT, uw3_addr, tmem_base + s * 64u);
-                    umma_commit_elect(&tfull[s]);
-                    umma_commit_elect(&empty[s]);
-                }
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[wid]);
+                if (PROF && tid == 0) { pt[2] += q1 - q0; pt[3] += now() - q1; }
             }
             kt += ntiles;
-            // ---- drain, dense head on the group's features, reset featT ----
-            tc_fence_before();
-            __syncthreads();
-            const long long tg1 = now();
-            dense_head_umma<NT, MMAW>(ring, featT, SBP, GS, s_grp, uw, tmem_base, dbar, dph, xmax, mem, p.M, p.out,
-                                      [first](int sl) { return (long long)(first + sl); });
-            for (int i = tid; i < F * SBP; i += NT) featT[i] = 0.f;
-            __syncthreads();
-            if (PROF && tid == 0) { pt[0] += tg1 - tg0; pt[1] += now() - tg1; pt[7] += ntiles; }
+            if (PROF && tid == 0) pt[7] += ntiles;
+        }
+    } else if (wid < MMAW) {
+        // =========================== conv3 epilogue: running max per sequence ===========================
+        // Warp (lq, par) owns TMEM lanes 32 lq .. 32 lq + 31 of the tiles of parity par and all 32 filters: the fixed cost
+        // of a visit (barrier wake-up, TMEM load latency) is paid once per two tiles.
+        // max_t relu(a_t * inv3 + b) == relu(max_t(a_t) * inv3 + b) (inv3 > 0): per tile only one packed add of the two
+        // accumulator halves and one fmaxf per filter; scale, bias and ReLU wait for the item's end.
+        const int lq = wid & 3, par = (wid >> 2) & 1;
+        // TMEM lane 32 lq + lane is MMA row 8 c + b: position c of stream b
+        const int c = 4 * lq + (lane >> 3), b = lane & 7;
+        const uint32_t tlane = tmem_base + ((uint32_t)(lq * 32) << 16);
+        const bool up8 = (lane & 8) != 0, up16 = (lane & 16) != 0;
+        const int et = tid - NPROD * 32;  // thread index among the 256 epilogue threads
+        float mx[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mx[j] = -INFINITY;
+        for (int64_t g = blockIdx.x; g < p.n_groups; g += gridDim.x, ++gi) {
+            const int s_grp = (int)min((int64_t)GS, p.n - g * GS);
+            const uint32_t ntiles = (uint32_t)(((s_grp + 7) >> 3) * nti);
+            float *featT = feat_s + (gi & 1) * F * SBP;
+            // GlobalMaxPooling1D: the 4 lanes of stream b merge their maxima with a halving butterfly — after the xor-8
+            // step a lane keeps filters 16 (lane bit 3) + 0..15, after the xor-16 step 8 of those — then scale, bias and
+            // ReLU, and the warps that saw the item meet in shared memory
+            auto flush = [&](int item) {
+                const int sl = item * 8 + b;
+                float k16[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float send = up8 ? mx[j] : mx[j + 16], keep = up8 ? mx[j + 16] : mx[j];
+                    k16[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+                }
+                const int f0 = (up8 ? 16 : 0) + (up16 ? 8 : 0);
+                unsigned int *dstf = reinterpret_cast<unsigned int *>(featT) + (size_t)f0 * SBP + sl;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float send = up16 ? k16[j] : k16[j + 8], keep = up16 ? k16[j + 8] : k16[j];
+                    const float t = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+                    const float r = fmaxf(fmaf(t, inv3, b3[f0 + j]), 0.f);
+                    if (sl < s_grp) atomicMax(dstf + (size_t)j * SBP, __float_as_uint(r));  // r >= 0: uint order
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) mx[j] = -INFINITY;
+            };
+            int cur_item = -1;
+            for (uint32_t tl = ((uint32_t)par - kt) & 1u; tl < ntiles; tl += 2) {
+                const uint32_t k = kt + tl, acc = k & 7u;
+                const int item = (int)tl / nti, q = (int)tl - item * nti;
+                if (item != cur_item) {
+                    if (cur_item >= 0) flush(cur_item);
+                    cur_item = item;
+                }
+                const long long w0 = now();
+                fxd::mbar_wait(&tfull[acc], (k >> 3) & 1);
+                const long long w1 = now();
+                tc_fence_after();
+                const bool valid = !(PROF && (p.dbg & 4)) && 16 * q + c < T;  // rows past the sequence: last tile only
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t v[16], v2[16];
+                    tmem_ld16_nowait(tlane + acc * 64u + (uint32_t)(hf * 16), v);
+                    tmem_ld16_nowait(tlane + acc * 64u + 32u + (uint32_t)(hf * 16), v2);
+                    tmem_ld_wait();
+                    if (hf == 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[acc]);  // the accumulator is in registers: hand it back
+                    }
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2) {
+                            float a0, a1;
+                            add_f32x2(a0, a1, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v2[j]),
+                                      __uint_as_float(v2[j + 1]));
+                            mx[hf * 16 + j] = fmaxf(mx[hf * 16 + j], a0);
+                            mx[hf * 16 + j + 1] = fmaxf(mx[hf * 16 + j + 1], a1);
+                        }
+                    }
+                }
+                if (PROF && tid == 8 * 32) { pt[4] += w1 - w0; pt[1] += now() - w1; }
+            }
+            if (cur_item >= 0) flush(cur_item);
+            kt += ntiles;
+            // the group's features are complete once all 8 epilogue warps are here: copy the [32][128] tile out and
+            // clear the buffer for the group after next
+            asm volatile("bar.sync 2, %0;" ::"n"(8 * 32) : "memory");
+            float4 *dst = reinterpret_cast<float4 *>(p.feat + (size_t)g * F * GS);
+#pragma unroll
+            for (int i = et; i < F * GS / 4; i += 8 * 32) {
+                const int row = i >> 5, col = (i & 31) * 4;
+                float4 *srcp = reinterpret_cast<float4 *>(featT + row * SBP + col);
+                dst[i] = *srcp;
+                *srcp = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    } else {
+        // =========================== MMA issuers ===========================
+        // Two warps take alternate tiles: issuing a tile (two barrier waits, 12 MMAs, two commits) costs more issue time
+        // than the tensor pipe needs to run it, and tiles are independent (own slot, own accumulator; a commit tracks
+        // the MMAs of the committing thread).
+        const uint32_t me = (uint32_t)(wid - MMAW);
+        for (int64_t g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
+            const int s_grp = (int)min((int64_t)GS, p.n - g * GS);
+            const uint32_t ntiles = (uint32_t)(((s_grp + 7) >> 3) * nti);
+            for (uint32_t tl = (me - kt) & (NMMA - 1); tl < ntiles; tl += NMMA) {
+                const uint32_t k = kt + tl, s = k & 7u, use = k >> 3;
+                const long long m0 = now();
+                fxd::mbar_wait(&full[s], use & 1);
+                const long long m1 = now();
+                if (use > 0) fxd::mbar_wait(&tempty[s], (use - 1) & 1);  // accumulator drained by the epilogue
+                if (PROF && lane == 0 && wid == MMAW) { pt[5] += m1 - m0; pt[6] += now() - m1; }
+                tc_fence_after();
+                if (!(PROF && (p.dbg & 1))) issue_conv3_tile(ring_addr + s * SLOT, uw3_addr, tmem_base + s * 64u);
+                umma_commit_elect(&tfull[s]);
+                umma_commit_elect(&empty[s]);
+            }
+            kt += ntiles;
         }
     }
-    if (xmax > 60000.f) atomicExch(p.overflow_flag, 1);
+    if (PROF && tid == 0) pt[0] = now() - t_begin;
     if (blockIdx.x == 0 && tid == 0 && __ldg(p.tab_ovf) != 0) atomicExch(p.overflow_flag, 1);
     if (PROF && p.prof != nullptr && (tid == 0 || tid == 8 * 32 || tid == MMAW * 32))
-        for (int i = 0; i < 16; ++i)
-            if (pt[i]) atomicAdd(reinterpret_cast<unsigned long long *>(&p.prof[(size_t)blockIdx.x * 16 + i]), (unsigned long long)pt[i]);
+        for (int i = 0; i < 8; ++i)
+            if (pt[i]) atomicAdd(reinterpret_cast<unsigned long long *>(&p.prof[(size_t)blockIdx.x * 8 + i]), (unsigned long long)pt[i]);
+    tc_fence_before();
+    __syncthreads();
+    if (wid == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- forward: dense head kernel -----------------------------------------------------------------------------
+// One [32][128] feature tile per step: Dense(H,relu) -> Dense(H,relu) -> Dense(1) -> nan_to_num -> ensemble accumulate
+// (u2::dense_head_umma: two tcgen05 GEMMs with the fp16 hi/lo split).  Weights are staged once per CTA; the next tile
+// arrives by bulk async copy while this one is computed.
+constexpr int DNT = 288, DMMAW = 8;
+constexpr int D_OFF_MBAR = 0, D_OFF_TM = 64, D_OFF_FT = 1024, D_OFF_SCR = D_OFF_FT + 2 * F * GS * 4;
+constexpr int D_SMEM = D_OFF_SCR + DS_TOTAL + 1024;
+static_assert(D_OFF_SCR % 1024 == 0, "dense scratch must be 1024-byte aligned");
+
+__global__ void __launch_bounds__(DNT, 1) cnn_k9_dense_kernel(const DenseParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + D_OFF_MBAR);  // [0], [1]: feature tiles, [2]: dense MMAs
+    uint32_t *tmem_addr_s = reinterpret_cast<uint32_t *>(smem_raw + D_OFF_TM);
+    float *ft = reinterpret_cast<float *>(smem_raw + D_OFF_FT);
+    unsigned char *scratch = smem_raw + D_OFF_SCR;
+    const int tid = threadIdx.x, wid = tid >> 5;
+    if (tid == 0) {
+        fxd::mbar_init(&mbar[0], 1); fxd::mbar_init(&mbar[1], 1); fxd::mbar_init(&mbar[2], 1);
+        fxd::fence_mbar_init();
+    }
+    if (wid == 0) tmem_alloc(tmem_addr_s, 512);
+    dense_stage_weights<DNT>(scratch, p.uw);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_addr_s;
+    auto load_tile = [&](int64_t g, int buf) {
+        fxd::mbar_arrive_expect_tx(&mbar[buf], F * GS * 4);
+        fxd::bulk_g2s(ft + buf * F * GS, p.feat + (size_t)g * F * GS, F * GS * 4, &mbar[buf]);
+    };
+    if (tid == 0 && (int64_t)blockIdx.x < p.n_groups) load_tile(blockIdx.x, 0);
+    uint32_t it = 0, dph = 0;
+    float xmax = 0.f;  // largest activation written as fp16 (range guard)
+    for (int64_t g = blockIdx.x; g < p.n_groups; g += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int64_t first = g * GS;
+        const int s_grp = (int)min((int64_t)GS, p.n - first);
+        // the other buffer's last reader was the previous step, which ended with a CTA barrier
+        if (tid == 0 && g + gridDim.x < p.n_groups) load_tile(g + gridDim.x, buf ^ 1);
+        fxd::mbar_wait(&mbar[buf], (it >> 1) & 1);
+        dense_head_umma<DNT, DMMAW, false>(scratch, ft + buf * F * GS, GS, GS, s_grp, p.uw, tmem_base, &mbar[2], dph, xmax,
+                                           p.mem, p.M, p.out, [first](int sl) { return (long long)(first + sl); });
+    }
+    if (xmax > 60000.f) atomicExch(p.overflow_flag, 1);
     tc_fence_before();
     __syncthreads();
     if (wid == 0) tmem_dealloc(tmem_base, 512);
@@ -467,15 +518,12 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
 
 static bool plan(const flexs_model *m, K9Params &p) {
     p.o = fx::cnn_offsets(m);
-    p.M = m->M;
     p.L = m->L;
     p.T = m->L - m->K + 1;
     p.nti = (p.T + 15) / 16;
-    p.member_floats = m->member_floats;
-    p.uw_member_bytes = UW_MEMBER_BYTES;
     p.idx_slot = (int)align_up((size_t)GS * m->L + 32, 16);
     p.nwp = (m->L + 15) / 16 + 2;  // packed residues: a zero word, ceil(L/16) words of 16 residues, a zero word
-    return (int64_t)carve(p).total + 1024 <= m->max_smem_optin;
+    return (int64_t)carve(p).total + 1024 <= m->max_smem_optin && D_SMEM <= m->max_smem_optin;
 }
 
 static int prepare(flexs_model *m, cudaStream_t s) {
@@ -519,39 +567,67 @@ int launch_cnn_k9(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out,
     int rc = prepare(m, s);
     if (rc != FLEXS_OK) return rc;
     if (!m->umma_weights_ok) return launch_cnn_tiled(m, d_idx, n, d_out, s);  // non-finite weights: fp32 path
-    p.idx = d_idx; p.out = d_out; p.weights = m->d_weights; p.n = n;
-    p.uw = reinterpret_cast<const unsigned char *>(m->d_umma2_w);
-    p.tab = reinterpret_cast<const unsigned char *>(m->d_k9_tab);
-    p.tab_ovf = m->d_k9_ovf;
-    p.overflow_flag = m->d_flag;
-    p.n_groups = (n + GS - 1) / GS;
-    const size_t smem = carve(p).total + 1024;
-    const int grid = (int)std::min<int64_t>(p.n_groups, m->sm_count);
+    // feature workspace of this stream: one [32][128] fp32 tile per group of a chunk.  A chunk is a whole number of
+    // waves of the persistent grid (56 groups per SM, ~1.06 M sequences, 136 MB).
+    const int64_t chunk_groups = (int64_t)m->sm_count * 56;
+    const int64_t n_groups = (n + GS - 1) / GS;
+    const size_t ws_bytes = (size_t)std::min(n_groups, chunk_groups) * F * GS * sizeof(float);
+    flexs_model::K9Workspace *ws = nullptr;
+    for (auto &w : m->k9_ws) if (w.stream == s) ws = &w;
+    if (!ws) { m->k9_ws.push_back({s, nullptr, 0}); ws = &m->k9_ws.back(); }
+    if (ws->bytes < ws_bytes) {
+        FX_CUDA(cudaStreamSynchronize(s));
+        if (ws->ptr) FX_CUDA(cudaFree(ws->ptr));
+        ws->ptr = nullptr; ws->bytes = 0;
+        FX_CUDA(cudaMalloc(&ws->ptr, ws_bytes));
+        ws->bytes = ws_bytes;
+    }
     static const bool prof = std::getenv("FLEXS_UMMA_PROF") && std::getenv("FLEXS_UMMA_PROF")[0] == '1';
     p.dbg = std::getenv("FLEXS_UMMA_DBG") ? std::atoi(std::getenv("FLEXS_UMMA_DBG")) : 0;
-    p.prof = nullptr;
-    if (prof) {
-        FX_CUDA(cudaMalloc(&p.prof, (size_t)grid * 16 * sizeof(long long)));
-        FX_CUDA(cudaMemset(p.prof, 0, (size_t)grid * 16 * sizeof(long long)));
-    }
-    FX_CUDA(cudaMemsetAsync(m->d_flag, 0, sizeof(int), s));
+    p.feat = reinterpret_cast<float *>(ws->ptr);
+    p.tab_ovf = m->d_k9_ovf;
+    p.overflow_flag = m->d_flag;
+    const size_t smem = carve(p).total + 1024;
     auto kernel = prof ? cnn_k9_kernel<true> : cnn_k9_kernel<false>;
     FX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kernel<<<grid, NT, smem, s>>>(p);
-    FX_CUDA(cudaGetLastError());
-    m->launches += 1;
-    if (prof) {
-        FX_CUDA(cudaStreamSynchronize(s));
-        std::vector<long long> h((size_t)grid * 16);
-        FX_CUDA(cudaMemcpy(h.data(), p.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-        cudaFree(p.prof);
-        double a[16] = {0};
-        for (int b = 0; b < grid; ++b) for (int i = 0; i < 16; ++i) a[i] += (double)h[(size_t)b * 16 + i] / grid;
-        const double nt = a[7] > 0 ? a[7] : 1;
-        fprintf(stderr, "[k9 prof] n=%lld grid=%d tiles/CTA=%.0f | cycles per tile: pipeline %.0f, dense+drain %.0f | "
-                        "producer warp 0 (per own tile = 1/8 of tiles): wait slot %.0f, gather %.0f | epilogue warp 8 (per own tile = 1/2 of tiles): wait MMA %.0f, load+max+flush %.0f | "
-                        "MMA warp 16 (per own tile = 1/2 of tiles): wait operands %.0f, wait accumulator %.0f\n",
-                (long long)n, grid, a[7], a[0] / nt, a[1] / nt, a[2] / nt * 8, a[3] / nt * 8, a[4] / nt * 2, a[9] / nt * 2, a[5] / nt * 2, a[6] / nt * 2);
+    FX_CUDA(cudaFuncSetAttribute(cnn_k9_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM));
+    FX_CUDA(cudaMemsetAsync(m->d_flag, 0, sizeof(int), s));
+    for (int64_t g0 = 0; g0 < n_groups; g0 += chunk_groups) {
+        const int64_t first = g0 * GS, cnt = std::min(n - first, chunk_groups * GS);
+        p.idx = d_idx + first * m->L;
+        p.n = cnt;
+        p.n_groups = (cnt + GS - 1) / GS;
+        const int grid = (int)std::min<int64_t>(p.n_groups, m->sm_count);
+        for (int mem = 0; mem < m->M; ++mem) {
+            p.weights = m->d_weights + (int64_t)mem * m->member_floats;
+            p.uw = reinterpret_cast<const unsigned char *>(m->d_umma2_w) + (size_t)mem * UW_MEMBER_BYTES;
+            p.tab = reinterpret_cast<const unsigned char *>(m->d_k9_tab) + (size_t)mem * TAB_BYTES;
+            p.prof = nullptr;
+            if (prof) {
+                FX_CUDA(cudaMalloc(&p.prof, (size_t)grid * 8 * sizeof(long long)));
+                FX_CUDA(cudaMemset(p.prof, 0, (size_t)grid * 8 * sizeof(long long)));
+            }
+            kernel<<<grid, NT, smem, s>>>(p);
+            FX_CUDA(cudaGetLastError());
+            DenseParams dp{p.feat, d_out + first, p.uw, m->d_flag, cnt, p.n_groups, mem, m->M};
+            cnn_k9_dense_kernel<<<grid, DNT, D_SMEM, s>>>(dp);
+            FX_CUDA(cudaGetLastError());
+            m->launches += 2;
+            if (prof) {
+                FX_CUDA(cudaStreamSynchronize(s));
+                std::vector<long long> h((size_t)grid * 8);
+                FX_CUDA(cudaMemcpy(h.data(), p.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+                cudaFree(p.prof);
+                double a[8] = {0};
+                for (int b = 0; b < grid; ++b) for (int i = 0; i < 8; ++i) a[i] += (double)h[(size_t)b * 8 + i] / grid;
+                const double nt = a[7] > 0 ? a[7] : 1;
+                fprintf(stderr, "[k9 prof] n=%lld grid=%d tiles/CTA=%.0f | cycles per tile %.0f | producer warp 0 (per own tile = 1/8 "
+                                "of tiles): wait slot %.0f, gather %.0f | epilogue warp 8 (per own tile = 1/2 of tiles): wait MMA %.0f, "
+                                "load+max+flush %.0f | MMA warp 16 (per own tile = 1/2 of tiles): wait operands %.0f, wait accumulator %.0f\n",
+                        (long long)cnt, grid, a[7], a[0] / nt, a[2] / nt * 8, a[3] / nt * 8, a[4] / nt * 2, a[1] / nt * 2,
+                        a[5] / nt * 2, a[6] / nt * 2);
+            }
+        }
     }
     // fp16 range guard: the gated FFMA kernel recomputes the batch iff the flag was raised
     return launch_cnn_tiled_gated(m, d_idx, n, d_out, m->d_flag, s);

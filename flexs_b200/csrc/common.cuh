@@ -66,6 +66,8 @@ struct flexs_model {
     void *d_k9_tab = nullptr;        // cnn_k9.cu: conv1 o conv2 as a table over 9 residues, [M][425984][128 B]
     int *d_k9_ovf = nullptr;         // raised by the table builder when an entry left the fp16 window
     bool k9_ready = false;
+    struct K9Workspace { cudaStream_t stream; void *ptr; size_t bytes; };
+    std::vector<K9Workspace> k9_ws;  // pooled-feature tiles between the conv and dense kernels, one per stream in use
     int *d_flag = nullptr;           // fp16-overflow flag raised by the UMMA kernel
 
     // Adam state for K4 (same layout as d_weights) and the 1-based step counter per member

@@ -137,7 +137,22 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4 &hi4, uint4 &l
 // ensemble.py:54-59) as two UMMA GEMMs with the fp16 hi/lo split.  `scratch` (>= DS_TOTAL bytes, 1024-aligned) is
 // the idle activation memory; TMEM columns 0..223 and 256..479 must be free.  Every thread of the CTA calls this
 // (it contains __syncthreads); warps 0-7 run the epilogues, warp MMAW issues.  seq_of(slot) -> global sequence.
-template <int NT, int MMAW, class SeqOf>
+// Stage the dense weight planes and the bias / output-weight vectors of one member into the scratch.
+template <int NT>
+__device__ __forceinline__ void dense_stage_weights(unsigned char *scratch, const unsigned char *uw) {
+    const int tid = threadIdx.x;
+    const float *gdv = reinterpret_cast<const float *>(uw + OFF_DV);
+    float *dv = reinterpret_cast<float *>(scratch + DS_DV);
+    for (int i = tid; i < 3 * DH; i += NT) dv[i] = __ldg(gdv + i);
+    for (int i = tid; i < 4 * DBK / 16; i += NT)
+        reinterpret_cast<uint4 *>(scratch + DS_B1)[i] = __ldg(reinterpret_cast<const uint4 *>(uw + OFF_DB1) + i);
+    for (int i = tid; i < 14 * DBK / 16; i += NT)
+        reinterpret_cast<uint4 *>(scratch + DS_B2)[i] = __ldg(reinterpret_cast<const uint4 *>(uw + OFF_DB2) + i);
+}
+
+// STAGE: stage the weights on every call (the scratch is shared with other work between calls); otherwise the
+// caller ran dense_stage_weights once and the scratch is dedicated.
+template <int NT, int MMAW, bool STAGE, class SeqOf>
 __device__ __forceinline__ void dense_head_umma(unsigned char *scratch, const float *featT, int sbp, int sbcap,
                                                 int g_slots, const unsigned char *uw, uint32_t tmem_base,
                                                 uint64_t *dbar, uint32_t &dph, float &xmax, int mem, int M,
@@ -148,14 +163,10 @@ __device__ __forceinline__ void dense_head_umma(unsigned char *scratch, const fl
     const float *gdv = reinterpret_cast<const float *>(uw + OFF_DV);
     float *dv = reinterpret_cast<float *>(scratch + DS_DV);  // bias / output-weight vectors, staged in smem
     const float inv_d1s = __ldg(gdv + 3 * DH), inv_d2 = __ldg(gdv + 3 * DH + 1), bd3v = __ldg(gdv + 3 * DH + 2);
-    for (int i = tid; i < 3 * DH; i += NT) dv[i] = __ldg(gdv + i);
     // (1) stage the dense weight planes, turn the features into the A operand of layer 1
-    for (int i = tid; i < 4 * DBK / 16; i += NT)
-        reinterpret_cast<uint4 *>(db1)[i] = __ldg(reinterpret_cast<const uint4 *>(uw + OFF_DB1) + i);
-    for (int i = tid; i < 14 * DBK / 16; i += NT)
-        reinterpret_cast<uint4 *>(db2)[i] = __ldg(reinterpret_cast<const uint4 *>(uw + OFF_DB2) + i);
-    if (tid < 4 * DSLOTS) {
-        const int slot = tid & (DSLOTS - 1), cchunk = tid >> 7;
+    if (STAGE) dense_stage_weights<NT>(scratch, uw);
+    for (int t = tid; t < 4 * DSLOTS; t += NT) {
+        const int slot = t & (DSLOTS - 1), cchunk = t >> 7;
         float x[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) x[q] = (slot < sbcap) ? featT[(cchunk * 8 + q) * sbp + slot] * ASCALE : 0.f;

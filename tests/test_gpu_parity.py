@@ -181,7 +181,7 @@ def test_cnn_full_size_properties():
         m.close()
 
 
-@pytest.mark.parametrize("L,n", [(20, 1000), (21, 259), (37, 1031), (100, 128 * 148 + 77), (120, 515), (180, 300)])
+@pytest.mark.parametrize("L,n", [(20, 1000), (21, 259), (37, 1031), (100, 128 * 148 + 77), (120, 515), (170, 300)])
 def test_cnn_table_kernel_lengths_and_ragged_groups(L, n):
     """cnn_k9.cu (conv1+conv2 as an L2-resident table over 9 residues): lengths whose conv positions do and do not
     fill the last 16-row tile, batches that end inside a group of 128 / an item of 8 sequences, unaligned pointers."""
