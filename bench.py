@@ -64,9 +64,12 @@ def plugin_api_timings(device):
         labels = rng.random(1000)
         model.train(seqs[:64], labels[:64])          # warm-up: workspace allocation
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        model.train(seqs, labels)
-        fit_s = time.perf_counter() - t0
+        fits = []
+        for _ in range(3):  # the first full-size fit also grows the training workspace: report the median
+            t0 = time.perf_counter()
+            model.train(seqs, labels)
+            fits.append(time.perf_counter() - t0)
+        fit_s = float(np.median(fits))
         small = seqs[:20]
         for _ in range(5):
             model.get_fitness(small)
@@ -432,7 +435,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="candidates per GPU per step")
-    ap.add_argument("--variant", default="auto", choices=["auto", "simple", "tiled", "umma"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "simple", "tiled", "umma", "lut"])
     ap.add_argument("--skip-extras", action="store_true", help="skip cpu_baseline / e2e / other workloads")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -459,7 +462,7 @@ def main():
 
     peaks, peak_src = load_peaks()
     screen = Screen(L_NS, A_NS, F_NS, H_NS, K_NS, 1, args.batch, rank, world, device)
-    variant = {"auto": 0, "simple": 1, "tiled": 2, "umma": 3}[args.variant]
+    variant = {"auto": 0, "simple": 1, "tiled": 2, "umma": 3, "lut": 4}[args.variant]
     screen.model.set_variant(variant)
     ms, clocks = timed_steps(screen, args.steps, args.warmup, world, device)
     total_seqs = world * args.batch * args.steps
@@ -502,7 +505,10 @@ def main():
                                             "aav90_cnn (AAV registry window)": (90, 20, 1, 1 << 18),
                                             "gfp237_cnn (configs[4], per-GPU shard)": (237, 20, 1, 1 << 17)}.items():
             sc = Screen(L, A, F_NS, H_NS, K_NS, members, batch, rank, world, device)
-            sc.model.set_variant(variant)
+            try:
+                sc.model.set_variant(variant)
+            except ValueError:  # a forced variant that this shape does not have: let the library choose
+                sc.model.set_variant(0)
             oms, _ = timed_steps(sc, max(3, args.steps), args.warmup, world, device)
             st = max(3, args.steps)
             others[tag] = {"value": world * batch * st / (oms / 1e3), "unit": UNIT, "ms_per_step": oms / st,

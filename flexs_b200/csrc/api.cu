@@ -136,7 +136,7 @@ void flexs_model_destroy(flexs_model_t *m) {
     cudaFree(m->d_adam_m);
     cudaFree(m->d_adam_v);
     cudaFree(m->train_ws);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < flexs_model::NSLOT; ++i) {
         if (m->streams[i]) cudaStreamDestroy(m->streams[i]);
         if (m->slot_done[i]) cudaEventDestroy(m->slot_done[i]);
         cudaFreeHost(m->h_pin_chars[i]);
@@ -239,25 +239,39 @@ int flexs_model_forward_dev(flexs_model_t *m, const uint8_t *d_idx, int64_t n, f
 }
 
 // Host-buffer scoring: chunk the batch, and for each chunk H2D(chars) -> encode -> forward ->
-// D2H(scores), alternating between two slots/streams so copies overlap compute.
-static int ensure_host_staging(flexs_model *m) {
-    if (m->streams[0]) return FLEXS_OK;
-    // chunk sized so a slot's chars are ~8 MiB: large enough to amortise launches, small
-    // enough that the first copy does not serialise the pipeline.
-    int64_t chunk = (8ll << 20) / std::max(1, m->L);
-    chunk = std::max<int64_t>(1024, std::min<int64_t>(chunk, 1 << 20));
-    m->host_chunk = chunk;
-    for (int i = 0; i < 2; ++i) {
-        FX_CUDA(cudaStreamCreateWithFlags(&m->streams[i], cudaStreamNonBlocking));
-        FX_CUDA(cudaEventCreateWithFlags(&m->slot_done[i], cudaEventDisableTiming));
+// D2H(scores), rotating over NSLOT slots/streams so copies overlap compute.
+static int ensure_host_staging(flexs_model *m, int64_t n) {
+    // A slot holds up to ~32 MiB of residue characters: large enough that launch overheads and the tail wave of the
+    // persistent kernels stay below a few percent of a chunk, small enough that the first copy (which nothing
+    // overlaps) is a small part of a multi-million-sequence call.  Slots grow on demand: a model that only ever
+    // scores an explorer's 20-string batches pins a few KB, not 64 MiB.
+    int64_t cap = (32ll << 20) / std::max(1, m->L);
+    cap = std::max<int64_t>(1024, std::min<int64_t>(cap, 1 << 20)) / 128 * 128;
+    const int64_t chunk = std::min(cap, std::max<int64_t>(1024, (n + 127) / 128 * 128));
+    if (!m->streams[0]) {
+        for (int i = 0; i < flexs_model::NSLOT; ++i) {
+            FX_CUDA(cudaStreamCreateWithFlags(&m->streams[i], cudaStreamNonBlocking));
+            FX_CUDA(cudaEventCreateWithFlags(&m->slot_done[i], cudaEventDisableTiming));
+        }
+        FX_CUDA(cudaMalloc(&m->d_status, 2 * flexs_model::NSLOT * sizeof(int64_t)));
+        FX_CUDA(cudaMallocHost(&m->h_status, 2 * flexs_model::NSLOT * sizeof(int64_t)));
+    }
+    if (chunk <= m->host_chunk) return FLEXS_OK;
+    for (int i = 0; i < flexs_model::NSLOT; ++i) {
+        FX_CUDA(cudaStreamSynchronize(m->streams[i]));
+        cudaFreeHost(m->h_pin_chars[i]); cudaFreeHost(m->h_pin_out[i]);
+        cudaFree(m->d_chars[i]); cudaFree(m->d_idx[i]); cudaFree(m->d_out[i]);
+        m->h_pin_chars[i] = nullptr; m->h_pin_out[i] = nullptr; m->d_chars[i] = nullptr; m->d_idx[i] = nullptr; m->d_out[i] = nullptr;
+    }
+    m->host_chunk = 0;
+    for (int i = 0; i < flexs_model::NSLOT; ++i) {
         FX_CUDA(cudaMallocHost(&m->h_pin_chars[i], chunk * m->L));
         FX_CUDA(cudaMallocHost(&m->h_pin_out[i], chunk * sizeof(float)));
         FX_CUDA(cudaMalloc(&m->d_chars[i], chunk * m->L + 16));
         FX_CUDA(cudaMalloc(&m->d_idx[i], chunk * m->L + 16));
         FX_CUDA(cudaMalloc(&m->d_out[i], chunk * sizeof(float)));
     }
-    FX_CUDA(cudaMalloc(&m->d_status, 4 * sizeof(int64_t)));
-    FX_CUDA(cudaMallocHost(&m->h_status, 4 * sizeof(int64_t)));
+    m->host_chunk = chunk;
     return FLEXS_OK;
 }
 
@@ -269,9 +283,13 @@ int flexs_model_score_host(flexs_model_t *m, const char *h_chars, int64_t n, con
     if (n == 0) return FLEXS_OK;
     FX_REQUIRE(h_chars && h_out, "null buffer");
     FX_CUDA(cudaSetDevice(m->device));
-    int rc = ensure_host_staging(m);
+    int rc = ensure_host_staging(m, n);
     if (rc != FLEXS_OK) return rc;
-    const int64_t chunk = m->host_chunk, L = m->L;
+    // equal chunks (a multiple of 128 sequences, the kernels' group size) instead of full slots plus a remainder:
+    // every chunk takes the same kernel path, so scores do not depend on where a sequence falls in the batch
+    const int64_t L = m->L;
+    const int64_t want = (n + m->host_chunk - 1) / m->host_chunk;
+    const int64_t chunk = std::min<int64_t>(m->host_chunk, ((n + want - 1) / want + 127) / 128 * 128);
     // Buffers the caller already page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) are used
     // directly by the async copies; pageable ones go through the model's pinned staging slots.
     auto is_pinned = [](const void *ptr) {
@@ -283,7 +301,8 @@ int flexs_model_score_host(flexs_model_t *m, const char *h_chars, int64_t n, con
     const int64_t nchunks = (n + chunk - 1) / chunk;
     int64_t first_bad = std::numeric_limits<int64_t>::max();
     // slot bookkeeping: what is in flight in each slot
-    int64_t inflight_start[2] = {-1, -1}, inflight_cnt[2] = {0, 0};
+    int64_t inflight_start[flexs_model::NSLOT], inflight_cnt[flexs_model::NSLOT];
+    for (int i = 0; i < flexs_model::NSLOT; ++i) { inflight_start[i] = -1; inflight_cnt[i] = 0; }
     auto drain = [&](int slot) -> int {
         if (inflight_start[slot] < 0) return FLEXS_OK;
         FX_CUDA(cudaEventSynchronize(m->slot_done[slot]));
@@ -294,7 +313,7 @@ int flexs_model_score_host(flexs_model_t *m, const char *h_chars, int64_t n, con
         return FLEXS_OK;
     };
     for (int64_t c = 0; c < nchunks; ++c) {
-        const int slot = (int)(c & 1);
+        const int slot = (int)(c % flexs_model::NSLOT);
         rc = drain(slot);
         if (rc != FLEXS_OK) return rc;
         const int64_t start = c * chunk, cnt = std::min(chunk, n - start);
@@ -313,7 +332,7 @@ int flexs_model_score_host(flexs_model_t *m, const char *h_chars, int64_t n, con
         FX_CUDA(cudaEventRecord(m->slot_done[slot], s));
         inflight_start[slot] = start; inflight_cnt[slot] = cnt;
     }
-    for (int slot = 0; slot < 2; ++slot) {
+    for (int slot = 0; slot < flexs_model::NSLOT; ++slot) {
         rc = drain(slot);
         if (rc != FLEXS_OK) return rc;
     }

@@ -76,15 +76,16 @@ struct flexs_model {
     void *train_ws = nullptr;        // training workspace (activations + grads)
     int64_t train_ws_bytes = 0;
 
-    // score_host staging: two slots of pinned host + device buffers and two streams
-    cudaStream_t streams[2] = {nullptr, nullptr};
-    cudaEvent_t slot_done[2] = {nullptr, nullptr};
-    uint8_t *h_pin_chars[2] = {nullptr, nullptr};
-    float *h_pin_out[2] = {nullptr, nullptr};
-    uint8_t *d_chars[2] = {nullptr, nullptr};
-    uint8_t *d_idx[2] = {nullptr, nullptr};
-    float *d_out[2] = {nullptr, nullptr};
-    int64_t *d_status = nullptr;     // [2 slots][2]
+    // score_host staging: slots of pinned host + device buffers, one stream each
+    static constexpr int NSLOT = 3;  // three chunks in flight: copy in, compute, copy out, with slack for jitter
+    cudaStream_t streams[NSLOT] = {};
+    cudaEvent_t slot_done[NSLOT] = {};
+    uint8_t *h_pin_chars[NSLOT] = {};
+    float *h_pin_out[NSLOT] = {};
+    uint8_t *d_chars[NSLOT] = {};
+    uint8_t *d_idx[NSLOT] = {};
+    float *d_out[NSLOT] = {};
+    int64_t *d_status = nullptr;     // [NSLOT][2]
     int64_t *h_status = nullptr;     // pinned mirror
     int64_t host_chunk = 0;          // sequences per staging slot
 };

@@ -370,7 +370,7 @@ def test_score_host_multi_chunk_pipeline():
     """More sequences than one staging slot holds: chunks alternate between the two streams."""
     import flexs_b200 as flexs
 
-    L, n = 100, 200_000
+    L, n = 100, 700_000  # three equal chunks of 233 344 sequences (a staging slot holds 335 488 100-mers)
     cnn = flexs.baselines.models.CNN(L, 32, 100, su.DNAA, seed=1)
     idx = np.random.default_rng(0).integers(0, 4, size=(n, L), dtype=np.uint8)
     chars = np.frombuffer(su.DNAA.encode(), dtype=np.uint8)[idx]
