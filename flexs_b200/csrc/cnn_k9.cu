@@ -74,7 +74,7 @@ struct DenseParams {
 };
 
 struct Offs {
-    int mbar, tm, b3, uw3, idx, pw, feat, ring;
+    int mbar, tm, b3, uw3, idx, pw, feat, stage, ring;
     size_t total;
 };
 
@@ -93,7 +93,8 @@ __host__ __device__ inline Offs carve(const K9Params &p) {
     o.uw3 = take((size_t)K3 * UWTAP, 128);
     o.idx = take(p.idx_slot, 16);
     o.pw = take((size_t)2 * GS * p.nwp * 4, 16);
-    o.feat = take((size_t)2 * F * SBP * 4, 16);
+    o.feat = take((size_t)F * SBP * 4, 16);
+    o.stage = take((size_t)2 * 8 * 256 * 4, 16);  // epilogue merge buffers: [double buffer][8 warps][256 maxima]
     o.ring = take((size_t)RING * SLOT, 1024);
     o.total = off;
     return o;
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
         fxd::fence_mbar_init();
     }
     if (wid == 0) tmem_alloc(tmem_addr_s, 512);
-    for (int i = tid; i < 2 * F * SBP; i += NT) feat_s[i] = 0.f;
+    for (int i = tid; i < F * SBP; i += NT) feat_s[i] = 0.f;
     const float inv3 = __ldg(reinterpret_cast<const float *>(p.uw + OFF_SCAL) + 1);
     for (int i = tid; i < F; i += NT) b3[i] = __ldg(p.weights + p.o.b3 + i);
     for (int i = tid; i < K3 * UWTAP / 16; i += NT)
@@ -341,95 +342,104 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
         }
     } else if (wid < MMAW) {
         // =========================== conv3 epilogue: running max per sequence ===========================
-        // Warp (lq, par) owns TMEM lanes 32 lq .. 32 lq + 31 of the tiles of parity par and all 32 filters: the fixed cost
-        // of a visit (barrier wake-up, TMEM load latency) is paid once per two tiles.
+        // Warp (lq, par) owns TMEM lanes 32 lq .. 32 lq + 31 (positions 4 lq .. 4 lq + 3 of the 8 streams) of the tiles of
+        // parity par — i.e. of four of the eight accumulators, at every one of their uses, so no barrier phase is ever
+        // skipped — and all 32 filters.
         // max_t relu(a_t * inv3 + b) == relu(max_t(a_t) * inv3 + b) (inv3 > 0): per tile only one packed add of the two
         // accumulator halves and one fmaxf per filter; scale, bias and ReLU wait for the item's end.
-        const int lq = wid & 3, par = (wid >> 2) & 1;
+        const int lq = wid & 3, par = (wid >> 2) & 1, ew = wid - NPROD;
         // TMEM lane 32 lq + lane is MMA row 8 c + b: position c of stream b
         const int c = 4 * lq + (lane >> 3), b = lane & 7;
         const uint32_t tlane = tmem_base + ((uint32_t)(lq * 32) << 16);
         const bool up8 = (lane & 8) != 0, up16 = (lane & 16) != 0;
         const int et = tid - NPROD * 32;  // thread index among the 256 epilogue threads
+        float *stage_s = reinterpret_cast<float *>(smem_raw + of.stage);  // [2 buffers][8 warps][4 fg][8 b][8 f]
+        uint32_t nflush = 0;
         float mx[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) mx[j] = -INFINITY;
         for (int64_t g = blockIdx.x; g < p.n_groups; g += gridDim.x, ++gi) {
             const int s_grp = (int)min((int64_t)GS, p.n - g * GS);
-            const uint32_t ntiles = (uint32_t)(((s_grp + 7) >> 3) * nti);
-            float *featT = feat_s + (gi & 1) * F * SBP;
-            // GlobalMaxPooling1D: the 4 lanes of stream b merge their maxima with a halving butterfly — after the xor-8
-            // step a lane keeps filters 16 (lane bit 3) + 0..15, after the xor-16 step 8 of those — then scale, bias and
-            // ReLU, and the warps that saw the item meet in shared memory
-            auto flush = [&](int item) {
-                const int sl = item * 8 + b;
+            const int nitems = (s_grp + 7) >> 3;
+            const uint32_t ntiles = (uint32_t)(nitems * nti);
+            float *featT = feat_s;
+            for (int item = 0; item < nitems; ++item) {
+                const uint32_t k0 = kt + (uint32_t)(item * nti);
+                for (int q = (int)((k0 ^ (uint32_t)par) & 1u); q < nti; q += 2) {
+                    const uint32_t k = k0 + (uint32_t)q, acc = k & 7u;
+                    const long long w0 = now();
+                    fxd::mbar_wait(&tfull[acc], (k >> 3) & 1);
+                    const long long w1 = now();
+                    tc_fence_after();
+                    const bool valid = !(PROF && (p.dbg & 4)) && 16 * q + c < T;  // rows past the sequence: last tile only
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        uint32_t v[16], v2[16];
+                        tmem_ld16_nowait(tlane + acc * 64u + (uint32_t)(hf * 16), v);
+                        tmem_ld16_nowait(tlane + acc * 64u + 32u + (uint32_t)(hf * 16), v2);
+                        tmem_ld_wait();
+                        if (hf == 1) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tempty[acc]);  // the accumulator is in registers: hand it back
+                        }
+                        if (valid) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 2) {
+                                float a0, a1;
+                                add_f32x2(a0, a1, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v2[j]),
+                                          __uint_as_float(v2[j + 1]));
+                                mx[hf * 16 + j] = fmaxf(mx[hf * 16 + j], a0);
+                                mx[hf * 16 + j + 1] = fmaxf(mx[hf * 16 + j + 1], a1);
+                            }
+                        }
+                    }
+                    if (PROF && tid == 8 * 32) { pt[4] += w1 - w0; pt[1] += now() - w1; }
+                }
+                // GlobalMaxPooling1D.  (1) The 4 lanes of stream b merge with a halving butterfly: after the xor-8 step a
+                // lane keeps filters 16 (lane bit 3) + 0..15, after the xor-16 step 8 of those.  (2) The 8 epilogue warps
+                // (4 position quarters x 2 tile parities) meet in a double-buffered staging area: plain stores, one
+                // 256-thread barrier, and warp w reduces filters 4 w .. 4 w + 3.  (3) Scale, bias, ReLU, one plain store
+                // per feature: no atomics anywhere.
                 float k16[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const float send = up8 ? mx[j] : mx[j + 16], keep = up8 ? mx[j + 16] : mx[j];
                     k16[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
                 }
-                const int f0 = (up8 ? 16 : 0) + (up16 ? 8 : 0);
-                unsigned int *dstf = reinterpret_cast<unsigned int *>(featT) + (size_t)f0 * SBP + sl;
+                float k8[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float send = up16 ? k16[j] : k16[j + 8], keep = up16 ? k16[j + 8] : k16[j];
-                    const float t = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 16));
-                    const float r = fmaxf(fmaf(t, inv3, b3[f0 + j]), 0.f);
-                    if (sl < s_grp) atomicMax(dstf + (size_t)j * SBP, __float_as_uint(r));  // r >= 0: uint order
+                    k8[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 16));
                 }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) mx[j] = -INFINITY;
-            };
-            int cur_item = -1;
-            for (uint32_t tl = ((uint32_t)par - kt) & 1u; tl < ntiles; tl += 2) {
-                const uint32_t k = kt + tl, acc = k & 7u;
-                const int item = (int)tl / nti, q = (int)tl - item * nti;
-                if (item != cur_item) {
-                    if (cur_item >= 0) flush(cur_item);
-                    cur_item = item;
-                }
-                const long long w0 = now();
-                fxd::mbar_wait(&tfull[acc], (k >> 3) & 1);
-                const long long w1 = now();
-                tc_fence_after();
-                const bool valid = !(PROF && (p.dbg & 4)) && 16 * q + c < T;  // rows past the sequence: last tile only
+                float *stg = stage_s + (nflush & 1) * 8 * 256;
+                const int fg = (up8 ? 2 : 0) + (up16 ? 1 : 0);  // this lane holds filters 8 fg .. 8 fg + 7 of stream b
+                float4 *wr = reinterpret_cast<float4 *>(stg + ew * 256 + (fg * 8 + b) * 8);
+                wr[0] = make_float4(k8[0], k8[1], k8[2], k8[3]);
+                wr[1] = make_float4(k8[4], k8[5], k8[6], k8[7]);
+                asm volatile("bar.sync 2, %0;" ::"n"(8 * 32) : "memory");
+                // lane (b, fi) of warp ew takes filter f = 4 ew + fi of stream b from all 8 warps' slots
+                const int f = 4 * ew + (lane >> 3), sl = item * 8 + b;
+                const float *rd = stg + ((f >> 3) * 8 + b) * 8 + (f & 7);
+                float t = rd[0];
 #pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    uint32_t v[16], v2[16];
-                    tmem_ld16_nowait(tlane + acc * 64u + (uint32_t)(hf * 16), v);
-                    tmem_ld16_nowait(tlane + acc * 64u + 32u + (uint32_t)(hf * 16), v2);
-                    tmem_ld_wait();
-                    if (hf == 1) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tempty[acc]);  // the accumulator is in registers: hand it back
-                    }
-                    if (valid) {
-#pragma unroll
-                        for (int j = 0; j < 16; j += 2) {
-                            float a0, a1;
-                            add_f32x2(a0, a1, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v2[j]),
-                                      __uint_as_float(v2[j + 1]));
-                            mx[hf * 16 + j] = fmaxf(mx[hf * 16 + j], a0);
-                            mx[hf * 16 + j + 1] = fmaxf(mx[hf * 16 + j + 1], a1);
-                        }
-                    }
-                }
-                if (PROF && tid == 8 * 32) { pt[4] += w1 - w0; pt[1] += now() - w1; }
+                for (int w8 = 1; w8 < 8; ++w8) t = fmaxf(t, rd[w8 * 256]);
+                if (sl < s_grp) featT[f * SBP + sl] = fmaxf(fmaf(t, inv3, b3[f]), 0.f);
+                ++nflush;
             }
-            if (cur_item >= 0) flush(cur_item);
             kt += ntiles;
-            // the group's features are complete once all 8 epilogue warps are here: copy the [32][128] tile out and
-            // clear the buffer for the group after next
+            // the group's features are complete once all 8 epilogue warps are here: copy the [32][128] tile out
+            // (slots past the end of the batch keep stale values; the dense kernel never reports them).  The next
+            // write to the buffer follows the next item's barrier, which every warp reaches after its share of the copy.
             asm volatile("bar.sync 2, %0;" ::"n"(8 * 32) : "memory");
             float4 *dst = reinterpret_cast<float4 *>(p.feat + (size_t)g * F * GS);
 #pragma unroll
             for (int i = et; i < F * GS / 4; i += 8 * 32) {
                 const int row = i >> 5, col = (i & 31) * 4;
-                float4 *srcp = reinterpret_cast<float4 *>(featT + row * SBP + col);
-                dst[i] = *srcp;
-                *srcp = make_float4(0.f, 0.f, 0.f, 0.f);
+                dst[i] = *reinterpret_cast<const float4 *>(featT + row * SBP + col);
             }
         }
     } else {
