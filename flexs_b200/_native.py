@@ -18,8 +18,8 @@ _LIB_PATH = Path(__file__).resolve().parent / "libflexs_b200.so"
 _lib: Optional[ctypes.CDLL] = None
 
 OK, EINVAL, ECUDA, EALPHABET = 0, -1, -2, -3
-VARIANT_AUTO, VARIANT_SIMPLE, VARIANT_TILED, VARIANT_UMMA, VARIANT_UMMA_LUT = 0, 1, 2, 3, 4
-VARIANT_NAMES = {0: "auto", 1: "simple", 2: "tiled_ffma", 3: "umma_tcgen05", 4: "lut9_umma_tcgen05"}
+VARIANT_AUTO, VARIANT_SIMPLE, VARIANT_TILED, VARIANT_UMMA, VARIANT_UMMA_LUT, VARIANT_ENUM = 0, 1, 2, 3, 4, 5
+VARIANT_NAMES = {0: "auto", 1: "simple", 2: "tiled_ffma", 3: "umma_tcgen05", 4: "lut9_umma_tcgen05", 5: "enum_table"}
 
 #: every symbol include/flexs_b200.h declares: (name, restype, argtypes)
 _SIGNATURES = [

@@ -132,6 +132,7 @@ void flexs_model_destroy(flexs_model_t *m) {
     cudaFree(m->d_k9_tab);
     cudaFree(m->d_k9_ovf);
     for (auto &w : m->k9_ws) cudaFree(w.ptr);
+    cudaFree(m->d_enum_tab);
     cudaFree(m->d_flag);
     cudaFree(m->d_adam_m);
     cudaFree(m->d_adam_v);
@@ -170,6 +171,7 @@ int flexs_model_set_weights(flexs_model_t *m, int member, const float *const *h_
     m->umma_ready = false;
     m->umma2_ready = false;
     m->k9_ready = false;
+    m->enum_ready = false;
     return FLEXS_OK;
 }
 
@@ -188,26 +190,36 @@ int flexs_model_get_weights(flexs_model_t *m, int member, float *const *h_arrays
 
 int flexs_model_set_variant(flexs_model_t *m, int variant) {
     FX_REQUIRE(m, "null model");
-    FX_REQUIRE(variant >= FLEXS_VARIANT_AUTO && variant <= FLEXS_VARIANT_UMMA_LUT, "unknown variant");
+    FX_REQUIRE(variant >= FLEXS_VARIANT_AUTO && variant <= FLEXS_VARIANT_ENUM, "unknown variant");
+    if (variant == FLEXS_VARIANT_ENUM) FX_REQUIRE(enum_space(m) > 0, "ENUM variant needs A^L <= 2^20");
     if (m->kind == FLEXS_KIND_CNN) {
         if (variant == FLEXS_VARIANT_TILED) FX_REQUIRE(cnn_tiled_supported(m), "TILED variant needs F=32, k=5, A in {4,20}");
         if (variant == FLEXS_VARIANT_UMMA) FX_REQUIRE(cnn_umma_supported(m), "UMMA variant not available for this shape");
-        if (variant == FLEXS_VARIANT_UMMA_LUT) FX_REQUIRE(cnn_k9_supported(m), "UMMA_LUT variant needs A=4, F=32, k=5, H<=112, 20 <= L <= ~175");
+        if (variant == FLEXS_VARIANT_UMMA_LUT) FX_REQUIRE(cnn_k9_supported(m), "UMMA_LUT variant needs A=4, F=32, k=5, H<=112, 8 <= L <= ~175");
     } else {
-        FX_REQUIRE(variant == FLEXS_VARIANT_AUTO, "MLP has a single kernel");
+        FX_REQUIRE(variant == FLEXS_VARIANT_AUTO || variant == FLEXS_VARIANT_ENUM, "MLP has a single kernel (plus the whole-model table)");
     }
     m->variant = variant;
     return FLEXS_OK;
 }
 
-int flexs_model_active_variant(const flexs_model_t *m, int64_t n) {
-    if (!m) return FLEXS_EINVAL;
+// variant of the fused kernels (never ENUM)
+static int direct_variant(const flexs_model *m, int64_t n) {
     if (m->kind != FLEXS_KIND_CNN) return FLEXS_VARIANT_AUTO;
-    if (m->variant != FLEXS_VARIANT_AUTO) return m->variant;
+    if (m->variant != FLEXS_VARIANT_AUTO && m->variant != FLEXS_VARIANT_ENUM) return m->variant;
     if (cnn_k9_supported(m) && n >= (m->k9_ready ? K9_MIN_N_READY : K9_MIN_N)) return FLEXS_VARIANT_UMMA_LUT;
     if (cnn_umma_supported(m)) return FLEXS_VARIANT_UMMA;
     if (cnn_tiled_supported(m)) return FLEXS_VARIANT_TILED;
     return FLEXS_VARIANT_SIMPLE;
+}
+
+int flexs_model_active_variant(const flexs_model_t *m, int64_t n) {
+    if (!m) return FLEXS_EINVAL;
+    if (m->variant == FLEXS_VARIANT_ENUM) return FLEXS_VARIANT_ENUM;
+    // AUTO: a batch at least as large as the sequence space pays for scoring the whole space once
+    const int64_t space = enum_space(m);
+    if (m->variant == FLEXS_VARIANT_AUTO && space > 0 && (m->enum_ready || n >= space)) return FLEXS_VARIANT_ENUM;
+    return direct_variant(m, n);
 }
 
 int64_t flexs_model_launch_count(const flexs_model_t *m) { return m ? m->launches : FLEXS_EINVAL; }
@@ -229,14 +241,27 @@ int flexs_model_forward_dev(flexs_model_t *m, const uint8_t *d_idx, int64_t n, f
     if (n == 0) return FLEXS_OK;
     FX_REQUIRE(d_idx && d_out, "null buffer");
     cudaStream_t s = (cudaStream_t)stream;
+    if (flexs_model_active_variant(m, n) == FLEXS_VARIANT_ENUM) return launch_enum(m, d_idx, n, d_out, s);
+    return forward_direct(m, d_idx, n, d_out, s);
+}
+
+}  // extern "C"
+
+namespace fx {
+
+int forward_direct(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s) {
     if (m->kind == FLEXS_KIND_MLP) return launch_mlp(m, d_idx, n, d_out, s);
-    switch (flexs_model_active_variant(m, n)) {
+    switch (direct_variant(m, n)) {
         case FLEXS_VARIANT_UMMA_LUT: return launch_cnn_k9(m, d_idx, n, d_out, s);
         case FLEXS_VARIANT_UMMA: return launch_cnn_umma(m, d_idx, n, d_out, s);
         case FLEXS_VARIANT_TILED: return launch_cnn_tiled(m, d_idx, n, d_out, s);
         default: return launch_cnn_simple(m, d_idx, n, d_out, s);
     }
 }
+
+}  // namespace fx
+
+extern "C" {
 
 // Host-buffer scoring: chunk the batch, and for each chunk H2D(chars) -> encode -> forward ->
 // D2H(scores), rotating over NSLOT slots/streams so copies overlap compute.

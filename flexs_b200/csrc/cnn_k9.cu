@@ -1,5 +1,5 @@
-// K1e (tcgen05 + L2-resident table; A = 4, k = 5, k3 = 3, F = 32, H <= 112, T >= 16) — the large-batch kernel of the
-// north-star shape (100-mers over a 4-letter alphabet).
+// K1e (tcgen05 + L2-resident table; A = 4, k = 5, k3 = 3, F = 32, H <= 112, 8 <= L <= ~175) — the large-batch kernel of
+// the 4-letter-alphabet shapes (north star: 100-mers; also the 8-mer and 14-mer configurations).
 //
 // With a 4-letter alphabet the first two layers of cnn.py:23-40 are a function of 9 residues:
 //   h2[o, :] = relu(b2 + sum_j W2[j]^T relu(b1 + conv1(x[o+j-2 .. o+j+2])))   (conv1 valid, conv2 "same")
@@ -565,7 +565,7 @@ namespace fx {
 
 bool cnn_k9_supported(const flexs_model *m) {
     if (m->kind != FLEXS_KIND_CNN || m->F != 32 || m->K != 5 || m->A != 4 || m->H > DH) return false;
-    if (m->L - m->K + 1 < 16) return false;  // short sequences: cnn_umma2's dense row packing wastes fewer MMA rows
+    if (m->L - m->K + 1 < 4) return false;  // the four truncated-window tables assume distinct positions 0, 1, T-2, T-1
     if (!cnn_umma2_supported(m)) return false;  // operand blob, small-batch kernel and fp32 fall-back
     K9Params p;
     return plan(m, p);

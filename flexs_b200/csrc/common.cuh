@@ -66,6 +66,8 @@ struct flexs_model {
     void *d_k9_tab = nullptr;        // cnn_k9.cu: conv1 o conv2 as a table over 9 residues, [M][425984][128 B]
     int *d_k9_ovf = nullptr;         // raised by the table builder when an entry left the fp16 window
     bool k9_ready = false;
+    float *d_enum_tab = nullptr;     // enum_table.cu: scores of all A^L sequences (A^L <= 2^20)
+    bool enum_ready = false;
     struct K9Workspace { cudaStream_t stream; void *ptr; size_t bytes; };
     std::vector<K9Workspace> k9_ws;  // pooled-feature tiles between the conv and dense kernels, one per stream in use
     int *d_flag = nullptr;           // fp16-overflow flag raised by the UMMA kernel
@@ -118,6 +120,11 @@ int prepare_cnn_umma2(flexs_model *m);
 // AUTO picks the table kernel from this batch size on (building the table costs about as much as scoring
 // 3e4 sequences with cnn_umma2), or for any batch once the table of the current weights exists
 constexpr int64_t K9_MIN_N = 65536, K9_MIN_N_READY = 1024;
+// whole-model table over all A^L sequences (enum_table.cu); enum_space() is 0 when A^L > 2^20
+int64_t enum_space(const flexs_model *m);
+int launch_enum(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s);
+// the fused kernels, without the whole-model table in front of them
+int forward_direct(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s);
 int launch_mlp(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s);
 
 }  // namespace fx

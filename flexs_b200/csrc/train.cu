@@ -516,6 +516,7 @@ int train_step(flexs_model *m, int member, const uint8_t *d_idx, const float *d_
     m->umma_ready = false;
     m->umma2_ready = false;
     m->k9_ready = false;
+    m->enum_ready = false;
     return FLEXS_OK;
 }
 

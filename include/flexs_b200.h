@@ -53,8 +53,11 @@ enum {
     FLEXS_VARIANT_SIMPLE = 1, /* one CTA per sequence, any shape                          */
     FLEXS_VARIANT_TILED = 2,  /* register-tiled FP32 FFMA, F == 32                        */
     FLEXS_VARIANT_UMMA = 3,   /* tcgen05 (fp16 hi/lo split) convs, F == 32                */
-    FLEXS_VARIANT_UMMA_LUT = 4 /* A == 4: conv1+conv2 as an L2-resident table over 9 residues,
-                                * conv3 + dense head on tcgen05; AUTO uses it for large batches */
+    FLEXS_VARIANT_UMMA_LUT = 4, /* A == 4: conv1+conv2 as an L2-resident table over 9 residues,
+                                 * conv3 + dense head on tcgen05; AUTO uses it for large batches */
+    FLEXS_VARIANT_ENUM = 5     /* A^L <= 2^20 (any model kind): the model is evaluated once on all A^L
+                                 * sequences by the kernels above, a batch is then one gather per
+                                 * candidate; AUTO uses it for batches of at least A^L sequences      */
 };
 
 typedef struct flexs_model flexs_model_t;

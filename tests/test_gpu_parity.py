@@ -47,7 +47,7 @@ def _device_forward(model, idx):
 
 def _variants(model):
     vs = [_native.VARIANT_SIMPLE]
-    for v in (_native.VARIANT_TILED, _native.VARIANT_UMMA, _native.VARIANT_UMMA_LUT):
+    for v in (_native.VARIANT_TILED, _native.VARIANT_UMMA, _native.VARIANT_UMMA_LUT, _native.VARIANT_ENUM):
         try:
             model.set_variant(v)
             vs.append(v)
@@ -181,7 +181,7 @@ def test_cnn_full_size_properties():
         m.close()
 
 
-@pytest.mark.parametrize("L,n", [(20, 1000), (21, 259), (37, 1031), (100, 128 * 148 + 77), (120, 515), (170, 300)])
+@pytest.mark.parametrize("L,n", [(8, 1000), (9, 333), (14, 2000), (20, 1000), (21, 259), (37, 1031), (100, 128 * 148 + 77), (120, 515), (170, 300)])
 def test_cnn_table_kernel_lengths_and_ragged_groups(L, n):
     """cnn_k9.cu (conv1+conv2 as an L2-resident table over 9 residues): lengths whose conv positions do and do not
     fill the last 16-row tile, batches that end inside a group of 128 / an item of 8 sequences, unaligned pointers."""
@@ -239,6 +239,48 @@ def test_cnn_table_kernel_selection_rebuild_and_ensemble():
     ref = fo.ensemble_mean([fo.nan_to_num_f32(fo.cnn_forward(sub, ws, np.float64)) for ws in wss])
     assert rel_err(_device_forward(ens, sub), ref, _floor(ref)) < TOL
     ens.close()
+
+
+def test_whole_model_table_for_tiny_sequence_spaces():
+    """enum_table.cu: for A^L <= 2^20 the model is evaluated once on every sequence and a batch becomes a gather.  AUTO
+    switches to it for batches at least as large as the space, for CNNs, MLPs and ensembles alike; new weights
+    invalidate the table; a residue outside the alphabet cannot read outside it."""
+    L, A = 8, 4
+    rng = np.random.default_rng(12)
+    idx = rng.integers(0, A, size=(70_000, L), dtype=np.uint8)
+    sample = np.arange(0, len(idx), 131)
+    shp = fo.CNNShape(L, A, 32, 100, 5)
+    wss = [fo.trained_like_weights(shp.weight_shapes(), 40 + i) for i in range(2)]
+    m = _native.NativeModel("cnn", seq_len=L, alphabet_size=A, num_filters=32, hidden_size=100, kernel_size=5, n_members=2)
+    for i, ws in enumerate(wss):
+        m.set_weights(ws, i)
+    assert m.active_variant(1000) != _native.VARIANT_ENUM and m.active_variant(4 ** L) == _native.VARIANT_ENUM
+    direct = _device_forward(m, idx[:1000])
+    big = _device_forward(m, idx)                              # scores all 65 536 8-mers once, then gathers
+    assert m.active_variant(20) == _native.VARIANT_ENUM        # the table of these weights exists now
+    ref = fo.ensemble_mean([fo.nan_to_num_f32(fo.cnn_forward(idx[sample], ws, np.float64)) for ws in wss])
+    assert rel_err(big[sample], ref, _floor(ref)) < TOL
+    assert rel_err(big[:1000], direct, _floor(direct)) < TOL
+    np.testing.assert_array_equal(_device_forward(m, idx[:20]), big[:20])
+    bad = idx[:64].copy(); bad[:, 3] = 200
+    clamp = bad.copy(); clamp[:, 3] = A - 1
+    np.testing.assert_array_equal(_device_forward(m, bad), _device_forward(m, clamp))
+    m.set_weights(wss[0], 1)                                   # both members equal now; the old table must go
+    assert m.active_variant(20) != _native.VARIANT_ENUM
+    ref = fo.nan_to_num_f32(fo.cnn_forward(idx[sample], wss[0], np.float64))
+    assert rel_err(_device_forward(m, idx)[sample], ref, _floor(ref)) < TOL
+    m.close()
+    ms = fo.MLPShape(L, A, 100)
+    wm = fo.trained_like_weights(ms.weight_shapes(), 6)
+    mlp = _native.NativeModel("mlp", seq_len=L, alphabet_size=A, hidden_size=100)
+    mlp.set_weights(wm)
+    direct = _device_forward(mlp, idx[:500])
+    mlp.set_variant(_native.VARIANT_ENUM)
+    np.testing.assert_array_equal(_device_forward(mlp, idx[:500]), direct)  # same kernel filled the table
+    mlp.close()
+    with pytest.raises(ValueError):
+        big_space = _native.NativeModel("cnn", seq_len=14, alphabet_size=4, num_filters=32, hidden_size=100, kernel_size=5)
+        big_space.set_variant(_native.VARIANT_ENUM)
 
 
 @pytest.mark.parametrize("members", [2, 3])

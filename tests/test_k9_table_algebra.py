@@ -44,26 +44,46 @@ def table_rows(entries, ws):
     return out
 
 
+def pack_residues(seq):
+    """Producer warps of cnn_k9_kernel: residues as 2 bits each, 16 per 32-bit word, first residue in the top bits,
+    one zero word in front and zero padding behind."""
+    L = len(seq)
+    nw = (L + 15) // 16
+    words = [0]
+    for w in range(nw):
+        word = 0
+        for r in range(16):
+            i = 16 * w + r
+            word = (word << 2) | ((int(seq[i]) & 3) if i < L else 0)
+        words.append(word)
+    words.append(0)
+    return words
+
+
 def row_entry(seq, o, T):
-    """Producer warps of cnn_k9_kernel: table entry of conv2 position ``o`` of one sequence (or -1: zero row)."""
+    """Producer warps of cnn_k9_kernel: table entry of conv2 position ``o`` of one sequence (or -1: zero row), with the
+    kernel's arithmetic: input row c of tile q is position o = 16 q + c - 1, its 9-residue window starts 2 (c + 13) bits
+    into the three packed words q-1, q, q+1; truncated windows at the left end come out of the zero word in front,
+    those at the right end drop the bits past the end."""
     if o < 0 or o >= T:
         return -1
-    start, length, base = o - 2, 9, 0
-    if o == 0:
-        start, length, base = 0, 7, ENT_EL0
-    elif o == 1:
-        start, length, base = 0, 8, ENT_EL1
-    elif o == T - 2:
-        length, base = 8, ENT_ER1
-    elif o == T - 1:
-        length, base = 7, ENT_ER0
-    code = 0
-    for m in range(length):
-        code = code * 4 + (int(seq[start + m]) & 3)
-    return base + code
+    q, c = divmod(o + 1, 16)
+    if c >= 16:  # rows 16, 17 of a tile are rows 0, 1 of the next one
+        q, c = q + 1, c - 16
+    pw = pack_residues(seq)
+    w0, w1 = pw[q], pw[q + 1]
+    w2 = pw[q + 2] if q + 2 < len(pw) else 0
+    bits = (w0 << 64) | (w1 << 32) | w2
+    code = (bits >> (96 - 2 * (c + 13) - 18)) & 0x3FFFF
+    base, rsh = 0, 0
+    if o <= 1:
+        base = ENT_EL0 if o == 0 else ENT_EL1
+    if o >= T - 2:
+        base, rsh = (ENT_ER1, 2) if o == T - 2 else (ENT_ER0, 4)
+    return base + (code >> rsh)
 
 
-@pytest.mark.parametrize("L", [20, 37, 100])
+@pytest.mark.parametrize("L", [8, 9, 14, 20, 37, 100])
 def test_table_rows_equal_conv2_activations(L):
     shp = fo.CNNShape(L, A, F, 100, K)
     ws = fo.trained_like_weights(shp.weight_shapes(), 4)
