@@ -470,18 +470,45 @@ def main():
     fwd_ms = float(np.mean(screen.fwd_ms))
     fa = flop_alg(L_NS, A_NS, F_NS, H_NS, K_NS)
     achieved_tf = fa * args.batch / (fwd_ms / 1e3) / 1e12
+    kernel_name = _native.VARIANT_NAMES[screen.model.active_variant(args.batch)]
     roofline = {
         "bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
         "frac": achieved_tf / peaks["bf16_tflops"], "traffic": None, "peak_source": peak_src,
-        "kernel": _native.VARIANT_NAMES[screen.model.active_variant(args.batch)],
+        "kernel": kernel_name,
         "kernel_ms": fwd_ms, "kernel_share_of_step": fwd_ms * args.steps / ms,
         "flop_alg_per_seq": fa, "bytes_alg_per_seq": L_NS + 4,
         "hbm_gbs_alg": (L_NS + 4) * args.batch / (fwd_ms / 1e3) / 1e9,
         "hbm_frac": (L_NS + 4) * args.batch / (fwd_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
         "fp32_ffma_peak_tflops_nominal": 148 * 128 * 2 * 1.965e9 / 1e12,
         "note": "compute-bound path (1.55e4 flop/B): fraction is of the dense bf16 tensor peak; "
-                "algorithmic flops count each MAC once even though the tcgen05 kernel runs 3 fp16 hi/lo split products per MAC",
+                "algorithmic flops count each MAC once even though the tcgen05 kernels run 3 fp16 hi/lo split products per MAC",
     }
+    if kernel_name == "lut9_umma_tcgen05":
+        # One forward = ceil(batch / 1 060 864) launches of cnn_k9_kernel (conv1+conv2 as one 128-byte gather per
+        # position from an L2-resident table, conv3 on tcgen05) each followed by cnn_k9_dense_kernel; kernel_ms covers
+        # both (ncu launch list, profiles/r01_k9_launch_list.txt: 91.5 % / 8.5 %).  Tensor work actually issued per
+        # sequence: conv3 as 6 (M128 N64 K16) + 6 (M128 N32 K16) MMAs per 128-row tile of 8 sequences x 16 positions,
+        # the dense head as 2 + 7 pairs of (N224, N112) MMAs per 128 sequences.
+        T = L_NS - K_NS + 1
+        tiles_per_seq = ((T + 15) // 16) / 8
+        mac_exec = tiles_per_seq * 6 * (128 * 64 * 16 + 128 * 32 * 16) + 9 * (128 * 224 * 16 + 128 * 112 * 16) / 128
+        exec_tf = 2 * mac_exec * args.batch / (fwd_ms / 1e3) / 1e12
+        launches_per_fwd = -(-args.batch // (148 * 56 * 128))
+        seq_per_launch = args.batch / launches_per_fwd
+        roofline.update({
+            "kernel": "cnn_k9_kernel (+ cnn_k9_dense_kernel)",
+            "tensor_flop_executed_per_seq": 2 * mac_exec, "tensor_tflops_executed": exec_tf,
+            "tensor_frac_executed": exec_tf / peaks["bf16_tflops"],
+            # dram__bytes_read+write of one cnn_k9_kernel launch, `ncu --set full` (profiles/r01_k9_ncu_summary.txt:
+            # 321.6 MB for 1 048 576 sequences = 54.5 MB table first touch + 255 B per sequence: 100 B residues in,
+            # 128 B pooled features out, the rest spill of the feature tiles the dense kernel reads back)
+            "traffic": 54.5e6 + 254.7 * seq_per_launch, "traffic_unit": "bytes per cnn_k9_kernel launch",
+            "traffic_source": "ncu capture, scaled to this launch size",
+            "sequences_per_launch": seq_per_launch,
+            "note": "compute-bound path: `achieved` counts the algorithmic flops of the whole layer stack once per MAC "
+                    "(SURVEY.md 8d), although conv1+conv2 are served by a table lookup and conv3/dense run 3 fp16 hi/lo "
+                    "split products per MAC; tensor_tflops_executed is what the tensor pipe really ran",
+        })
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

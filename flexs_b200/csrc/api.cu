@@ -131,7 +131,7 @@ void flexs_model_destroy(flexs_model_t *m) {
     cudaFree(m->d_umma2_w);
     cudaFree(m->d_k9_tab);
     cudaFree(m->d_k9_ovf);
-    for (auto &w : m->k9_ws) cudaFree(w.ptr);
+    for (auto &w : m->k9_ws) { cudaFree(w.ptr); cudaFree(w.flag); }
     cudaFree(m->d_enum_tab);
     cudaFree(m->d_flag);
     cudaFree(m->d_adam_m);

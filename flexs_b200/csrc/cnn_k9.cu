@@ -584,7 +584,11 @@ int launch_cnn_k9(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out,
     const size_t ws_bytes = (size_t)std::min(n_groups, chunk_groups) * F * GS * sizeof(float);
     flexs_model::K9Workspace *ws = nullptr;
     for (auto &w : m->k9_ws) if (w.stream == s) ws = &w;
-    if (!ws) { m->k9_ws.push_back({s, nullptr, 0}); ws = &m->k9_ws.back(); }
+    if (!ws) {
+        m->k9_ws.push_back({s, nullptr, 0, nullptr});
+        ws = &m->k9_ws.back();
+        FX_CUDA(cudaMalloc(&ws->flag, sizeof(int)));
+    }
     if (ws->bytes < ws_bytes) {
         FX_CUDA(cudaStreamSynchronize(s));
         if (ws->ptr) FX_CUDA(cudaFree(ws->ptr));
@@ -596,12 +600,12 @@ int launch_cnn_k9(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out,
     p.dbg = std::getenv("FLEXS_UMMA_DBG") ? std::atoi(std::getenv("FLEXS_UMMA_DBG")) : 0;
     p.feat = reinterpret_cast<float *>(ws->ptr);
     p.tab_ovf = m->d_k9_ovf;
-    p.overflow_flag = m->d_flag;
+    p.overflow_flag = ws->flag;
     const size_t smem = carve(p).total + 1024;
     auto kernel = prof ? cnn_k9_kernel<true> : cnn_k9_kernel<false>;
     FX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FX_CUDA(cudaFuncSetAttribute(cnn_k9_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM));
-    FX_CUDA(cudaMemsetAsync(m->d_flag, 0, sizeof(int), s));
+    FX_CUDA(cudaMemsetAsync(ws->flag, 0, sizeof(int), s));
     for (int64_t g0 = 0; g0 < n_groups; g0 += chunk_groups) {
         const int64_t first = g0 * GS, cnt = std::min(n - first, chunk_groups * GS);
         p.idx = d_idx + first * m->L;
@@ -619,7 +623,7 @@ int launch_cnn_k9(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out,
             }
             kernel<<<grid, NT, smem, s>>>(p);
             FX_CUDA(cudaGetLastError());
-            DenseParams dp{p.feat, d_out + first, p.uw, m->d_flag, cnt, p.n_groups, mem, m->M};
+            DenseParams dp{p.feat, d_out + first, p.uw, ws->flag, cnt, p.n_groups, mem, m->M};
             cnn_k9_dense_kernel<<<grid, DNT, D_SMEM, s>>>(dp);
             FX_CUDA(cudaGetLastError());
             m->launches += 2;
@@ -640,7 +644,7 @@ int launch_cnn_k9(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out,
         }
     }
     // fp16 range guard: the gated FFMA kernel recomputes the batch iff the flag was raised
-    return launch_cnn_tiled_gated(m, d_idx, n, d_out, m->d_flag, s);
+    return launch_cnn_tiled_gated(m, d_idx, n, d_out, ws->flag, s);
 }
 
 }  // namespace fx

@@ -68,7 +68,7 @@ struct flexs_model {
     bool k9_ready = false;
     float *d_enum_tab = nullptr;     // enum_table.cu: scores of all A^L sequences (A^L <= 2^20)
     bool enum_ready = false;
-    struct K9Workspace { cudaStream_t stream; void *ptr; size_t bytes; };
+    struct K9Workspace { cudaStream_t stream; void *ptr; size_t bytes; int *flag; };  // flag: fp16-overflow, per stream
     std::vector<K9Workspace> k9_ws;  // pooled-feature tiles between the conv and dense kernels, one per stream in use
     int *d_flag = nullptr;           // fp16-overflow flag raised by the UMMA kernel
 
