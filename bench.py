@@ -457,6 +457,8 @@ def main():
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner out of stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=device)
     assert world == max(1, args.gpus) or world == 1, "launch N>1 through torch.distributed.run"
 
