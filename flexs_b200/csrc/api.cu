@@ -2,6 +2,7 @@
 // host-buffer scoring call.  No CPU compute path exists in this file or behind it.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -313,8 +314,15 @@ int flexs_model_score_host(flexs_model_t *m, const char *h_chars, int64_t n, con
     // equal chunks (a multiple of 128 sequences, the kernels' group size) instead of full slots plus a remainder:
     // every chunk takes the same kernel path, so scores do not depend on where a sequence falls in the batch
     const int64_t L = m->L;
-    const int64_t want = (n + m->host_chunk - 1) / m->host_chunk;
-    const int64_t chunk = std::min<int64_t>(m->host_chunk, ((n + want - 1) / want + 127) / 128 * 128);
+    // A chunk is a whole number of waves of the persistent kernels (sm_count groups of 128 sequences), close to
+    // FLEXS_HOST_CHUNK_MB of residue characters: small enough that the first copy in and the last compute (which nothing
+    // overlaps) are a small part of the call, large enough to amortise the per-chunk launches.
+    static const int64_t target_mb = std::getenv("FLEXS_HOST_CHUNK_MB") ? std::atoll(std::getenv("FLEXS_HOST_CHUNK_MB")) : 32;
+    const int64_t wave = (int64_t)m->sm_count * 128;
+    int64_t per = std::max<int64_t>(1, (target_mb << 20) / std::max<int64_t>(1, L * wave)) * wave;
+    per = std::min(per, m->host_chunk);
+    const int64_t want = (n + per - 1) / per;
+    const int64_t chunk = std::min<int64_t>(m->host_chunk, want <= 1 ? (n + 127) / 128 * 128 : per);
     // Buffers the caller already page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) are used
     // directly by the async copies; pageable ones go through the model's pinned staging slots.
     auto is_pinned = [](const void *ptr) {

@@ -118,8 +118,9 @@ bool cnn_k9_supported(const flexs_model *m);
 int launch_cnn_k9(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s);
 int prepare_cnn_umma2(flexs_model *m);
 // AUTO picks the table kernel from this batch size on (building the table costs about as much as scoring
-// 3e4 sequences with cnn_umma2), or for any batch once the table of the current weights exists
-constexpr int64_t K9_MIN_N = 65536, K9_MIN_N_READY = 1024;
+// 3e4 sequences with cnn_umma2), or, once the table of the current weights exists, from the size at which its
+// 128-sequence groups occupy enough SMs to beat cnn_umma2's finer-grained items
+constexpr int64_t K9_MIN_N = 65536, K9_MIN_N_READY = 8192;
 // whole-model table over all A^L sequences (enum_table.cu); enum_space() is 0 when A^L > 2^20
 int64_t enum_space(const flexs_model *m);
 int launch_enum(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s);

@@ -217,13 +217,13 @@ def test_cnn_table_kernel_selection_rebuild_and_ensemble():
     assert m.active_variant(100) == _native.VARIANT_UMMA and m.active_variant(70_000) == _native.VARIANT_UMMA_LUT
     small = _device_forward(m, idx[:100])                      # cnn_umma2
     big = _device_forward(m, idx)                              # builds the table, cnn_k9
-    assert m.active_variant(2000) == _native.VARIANT_UMMA_LUT  # the table of these weights exists now
+    assert m.active_variant(10_000) == _native.VARIANT_UMMA_LUT  # the table of these weights exists now
     sample = np.arange(0, len(idx), 499)
     ref = co.cnn_forward(idx[sample], [wss[0]])
     assert rel_err(big[sample], ref, _floor(ref)) < TOL
     assert rel_err(big[:100], small, _floor(small)) < TOL
     m.set_weights(wss[1])                                      # stale table must not be used
-    assert m.active_variant(2000) == _native.VARIANT_UMMA
+    assert m.active_variant(10_000) == _native.VARIANT_UMMA
     ref = co.cnn_forward(idx[sample], [wss[1]])
     assert rel_err(_device_forward(m, idx)[sample], ref, _floor(ref)) < TOL
     bad = idx[:300].copy(); bad[:, ::7] |= 0xF0               # garbage high bits: the kernel masks residues to 2 bits
