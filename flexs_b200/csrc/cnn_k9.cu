@@ -363,44 +363,42 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
             const int nitems = (s_grp + 7) >> 3;
             const uint32_t ntiles = (uint32_t)(nitems * nti);
             float *featT = feat_s;
-            for (int item = 0; item < nitems; ++item) {
-                const uint32_t k0 = kt + (uint32_t)(item * nti);
-                for (int q = (int)((k0 ^ (uint32_t)par) & 1u); q < nti; q += 2) {
-                    const uint32_t k = k0 + (uint32_t)q, acc = k & 7u;
-                    const long long w0 = now();
-                    fxd::mbar_wait(&tfull[acc], (k >> 3) & 1);
-                    const long long w1 = now();
-                    tc_fence_after();
-                    const bool valid = !(PROF && (p.dbg & 4)) && 16 * q + c < T;  // rows past the sequence: last tile only
+            // one tile: accumulator -> registers -> running maxima
+            auto visit = [&](uint32_t k, int q) {
+                const uint32_t acc = k & 7u;
+                const long long w0 = now();
+                fxd::mbar_wait(&tfull[acc], (k >> 3) & 1);
+                const long long w1 = now();
+                tc_fence_after();
+                const bool valid = !(PROF && (p.dbg & 4)) && 16 * q + c < T;  // rows past the sequence: last tile only
 #pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-                        uint32_t v[16], v2[16];
-                        tmem_ld16_nowait(tlane + acc * 64u + (uint32_t)(hf * 16), v);
-                        tmem_ld16_nowait(tlane + acc * 64u + 32u + (uint32_t)(hf * 16), v2);
-                        tmem_ld_wait();
-                        if (hf == 1) {
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&tempty[acc]);  // the accumulator is in registers: hand it back
-                        }
-                        if (valid) {
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t v[16], v2[16];
+                    tmem_ld16_nowait(tlane + acc * 64u + (uint32_t)(hf * 16), v);
+                    tmem_ld16_nowait(tlane + acc * 64u + 32u + (uint32_t)(hf * 16), v2);
+                    tmem_ld_wait();
+                    if (hf == 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[acc]);  // the accumulator is in registers: hand it back
+                    }
+                    if (valid) {
 #pragma unroll
-                            for (int j = 0; j < 16; j += 2) {
-                                float a0, a1;
-                                add_f32x2(a0, a1, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v2[j]),
-                                          __uint_as_float(v2[j + 1]));
-                                mx[hf * 16 + j] = fmaxf(mx[hf * 16 + j], a0);
-                                mx[hf * 16 + j + 1] = fmaxf(mx[hf * 16 + j + 1], a1);
-                            }
+                        for (int j = 0; j < 16; j += 2) {
+                            float a0, a1;
+                            add_f32x2(a0, a1, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v2[j]),
+                                      __uint_as_float(v2[j + 1]));
+                            mx[hf * 16 + j] = fmaxf(mx[hf * 16 + j], a0);
+                            mx[hf * 16 + j + 1] = fmaxf(mx[hf * 16 + j + 1], a1);
                         }
                     }
-                    if (PROF && tid == 8 * 32) { pt[4] += w1 - w0; pt[1] += now() - w1; }
                 }
-                // GlobalMaxPooling1D.  (1) The 4 lanes of stream b merge with a halving butterfly: after the xor-8 step a
-                // lane keeps filters 16 (lane bit 3) + 0..15, after the xor-16 step 8 of those.  (2) The 8 epilogue warps
-                // (4 position quarters x 2 tile parities) meet in a double-buffered staging area: plain stores, one
-                // 256-thread barrier, and warp w reduces filters 4 w .. 4 w + 3.  (3) Scale, bias, ReLU, one plain store
-                // per feature: no atomics anywhere.
+                if (PROF && tid == 8 * 32) { pt[4] += w1 - w0; pt[1] += now() - w1; }
+            };
+            // GlobalMaxPooling1D, step 1: the 4 lanes of stream b merge with a halving butterfly — after the xor-8 step a
+            // lane keeps filters 16 (lane bit 3) + 0..15, after the xor-16 step 8 of those (filters 8 fg .. 8 fg + 7) —
+            // and park them in this warp's 256-float slot of a staging buffer, [fg][b][8]
+            auto butterfly_to = [&](float *slot) {
                 float k16[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
@@ -415,25 +413,60 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
                 }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) mx[j] = -INFINITY;
-                float *stg = stage_s + (nflush & 1) * 8 * 256;
-                const int fg = (up8 ? 2 : 0) + (up16 ? 1 : 0);  // this lane holds filters 8 fg .. 8 fg + 7 of stream b
-                float4 *wr = reinterpret_cast<float4 *>(stg + ew * 256 + (fg * 8 + b) * 8);
+                const int fg = (up8 ? 2 : 0) + (up16 ? 1 : 0);
+                float4 *wr = reinterpret_cast<float4 *>(slot + (fg * 8 + b) * 8);
                 wr[0] = make_float4(k8[0], k8[1], k8[2], k8[3]);
                 wr[1] = make_float4(k8[4], k8[5], k8[6], k8[7]);
-                asm volatile("bar.sync 2, %0;" ::"n"(8 * 32) : "memory");
-                // lane (b, fi) of warp ew takes filter f = 4 ew + fi of stream b from all 8 warps' slots
-                const int f = 4 * ew + (lane >> 3), sl = item * 8 + b;
-                const float *rd = stg + ((f >> 3) * 8 + b) * 8 + (f & 7);
-                float t = rd[0];
+            };
+            if (nti == 1) {
+                // One tile per item (8 <= L <= 20): the item belongs to one tile parity, i.e. to the 4 warps of one set.
+                // Step 2: those 4 warps (4 positions each) meet in the set's staging buffer — plain stores, a 128-thread
+                // barrier, warp lq reduces filters 8 lq .. 8 lq + 7 — step 3: scale, bias, ReLU, one store per feature.
+                for (int item = 0; item < nitems; ++item) {
+                    const uint32_t k = kt + (uint32_t)item;
+                    if ((k & 1u) != (uint32_t)par) continue;
+                    visit(k, 0);
+                    float *stg = stage_s + (par * 2 + (int)(nflush & 1)) * 4 * 256;
+                    butterfly_to(stg + lq * 256);
+                    if (par == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
+                    else asm volatile("bar.sync 4, 128;" ::: "memory");
+                    const int pr = lane >> 3, f = 8 * lq + 2 * pr, sl = item * 8 + b;
+                    const float *rd = stg + (lq * 8 + b) * 8 + 2 * pr;
+                    float2 t = *reinterpret_cast<const float2 *>(rd);
 #pragma unroll
-                for (int w8 = 1; w8 < 8; ++w8) t = fmaxf(t, rd[w8 * 256]);
-                if (sl < s_grp) featT[f * SBP + sl] = fmaxf(fmaf(t, inv3, b3[f]), 0.f);
-                ++nflush;
+                    for (int w4 = 1; w4 < 4; ++w4) {
+                        const float2 o2 = *reinterpret_cast<const float2 *>(rd + w4 * 256);
+                        t.x = fmaxf(t.x, o2.x); t.y = fmaxf(t.y, o2.y);
+                    }
+                    if (sl < s_grp) {
+                        featT[f * SBP + sl] = fmaxf(fmaf(t.x, inv3, b3[f]), 0.f);
+                        featT[(f + 1) * SBP + sl] = fmaxf(fmaf(t.y, inv3, b3[f + 1]), 0.f);
+                    }
+                    ++nflush;
+                }
+            } else {
+                // Step 2: the 8 epilogue warps (4 position quarters x 2 tile parities) meet in a double-buffered staging
+                // area: plain stores, one 256-thread barrier, and warp w reduces filters 4 w .. 4 w + 3.  Step 3: scale,
+                // bias, ReLU, one plain store per feature: no atomics anywhere.
+                for (int item = 0; item < nitems; ++item) {
+                    const uint32_t k0 = kt + (uint32_t)(item * nti);
+                    for (int q = (int)((k0 ^ (uint32_t)par) & 1u); q < nti; q += 2) visit(k0 + (uint32_t)q, q);
+                    float *stg = stage_s + (nflush & 1) * 8 * 256;
+                    butterfly_to(stg + ew * 256);
+                    asm volatile("bar.sync 2, %0;" ::"n"(8 * 32) : "memory");
+                    // lane (b, fi) of warp ew takes filter f = 4 ew + fi of stream b from all 8 warps' slots
+                    const int f = 4 * ew + (lane >> 3), sl = item * 8 + b;
+                    const float *rd = stg + ((f >> 3) * 8 + b) * 8 + (f & 7);
+                    float t = rd[0];
+#pragma unroll
+                    for (int w8 = 1; w8 < 8; ++w8) t = fmaxf(t, rd[w8 * 256]);
+                    if (sl < s_grp) featT[f * SBP + sl] = fmaxf(fmaf(t, inv3, b3[f]), 0.f);
+                    ++nflush;
+                }
             }
             kt += ntiles;
             // the group's features are complete once all 8 epilogue warps are here: copy the [32][128] tile out
-            // (slots past the end of the batch keep stale values; the dense kernel never reports them).  The next
-            // write to the buffer follows the next item's barrier, which every warp reaches after its share of the copy.
+            // (slots past the end of the batch keep stale values; the dense kernel never reports them)
             asm volatile("bar.sync 2, %0;" ::"n"(8 * 32) : "memory");
             float4 *dst = reinterpret_cast<float4 *>(p.feat + (size_t)g * F * GS);
 #pragma unroll
@@ -441,6 +474,9 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
                 const int row = i >> 5, col = (i & 31) * 4;
                 dst[i] = *reinterpret_cast<const float4 *>(featT + row * SBP + col);
             }
+            // the next group's first features may be stored after a barrier of only one set (one-tile items): nobody
+            // may still be reading this group's
+            asm volatile("bar.sync 2, %0;" ::"n"(8 * 32) : "memory");
         }
     } else {
         // =========================== MMA issuers ===========================

@@ -13,7 +13,9 @@
  *     flexs_last_error() returns a thread-local message for the last failure.
  *   - "d_" pointers are device pointers on the model's device; "h_" pointers are host
  *     pointers.  `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
- *     Device entry points enqueue work on `stream` and return without synchronising.
+ *     Device entry points enqueue work on `stream` and return without synchronising — except for
+ *     the one-time preparation after a weight change or a larger batch than seen before (operand
+ *     re-layout, table build, workspace growth), which may allocate and synchronise `stream`.
  *   - Sequences are residue-index arrays uint8[n, seq_len], row-major: the value is
  *     alphabet.index(ch) (flexs/utils/sequence_utils.py:44-47).  The float one-hot of the
  *     reference is never materialised.

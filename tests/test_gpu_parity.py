@@ -241,6 +241,30 @@ def test_cnn_table_kernel_selection_rebuild_and_ensemble():
     ens.close()
 
 
+@pytest.mark.parametrize("L", [8, 14, 20, 21, 37, 100, 120])
+def test_cnn_table_kernel_random_batch_sizes_agree_with_umma2(L):
+    """Many launches of random sizes (ragged groups, odd tile counts carried from group to group inside a CTA, one- and
+    multi-tile items): the mbarrier protocol of cnn_k9 must neither hang nor drift from cnn_umma2 on the same inputs.
+    (tools/k9_stress.py is the longer form of this test.)"""
+    rng = np.random.default_rng(L)
+    m = _native.NativeModel("cnn", seq_len=L, alphabet_size=4, num_filters=32, hidden_size=100, kernel_size=5)
+    m.set_weights(fo.trained_like_weights(fo.CNNShape(L, 4, 32, 100, 5).weight_shapes(), L))
+    nmax = 120_000
+    idx = torch.randint(0, 4, (nmax, L), dtype=torch.uint8, device="cuda")
+    a = torch.empty(nmax, dtype=torch.float32, device="cuda")
+    b = torch.empty(nmax, dtype=torch.float32, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    for it in range(10):
+        n = int(rng.integers(1, nmax)) if it % 2 else int(rng.integers(1, 3000))
+        m.set_variant(_native.VARIANT_UMMA_LUT)
+        m.forward_dev(idx.data_ptr(), n, a.data_ptr(), s)
+        m.set_variant(_native.VARIANT_UMMA)
+        m.forward_dev(idx.data_ptr(), n, b.data_ptr(), s)
+        torch.cuda.synchronize()
+        assert float((a[:n] - b[:n]).abs().max() / b[:n].abs().max()) < TOL, (L, n)
+    m.close()
+
+
 def test_whole_model_table_for_tiny_sequence_spaces():
     """enum_table.cu: for A^L <= 2^20 the model is evaluated once on every sequence and a batch becomes a gather.  AUTO
     switches to it for batches at least as large as the space, for CNNs, MLPs and ensembles alike; new weights
