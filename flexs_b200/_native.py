@@ -41,6 +41,8 @@ _SIGNATURES = [
     ("flexs_model_score_host", c_int, [c_void_p, c_void_p, c_int64, c_char_p, c_void_p, POINTER(c_int64)]),
     ("flexs_topk_workspace_bytes", c_int64, [c_int64, c_int]),
     ("flexs_topk_dev", c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    ("flexs_dedup_workspace_bytes", c_int64, [c_int64]),
+    ("flexs_dedup_scores_dev", c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("flexs_mutate_dev", c_int, [c_void_p, c_int64, c_int, c_int, c_float, c_uint64, c_uint64, c_void_p, c_void_p]),
     ("flexs_argmax_decode_dev", c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
     ("flexs_model_fit_dev", c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_uint64, c_void_p, c_void_p]),
@@ -239,6 +241,19 @@ def topk_dev(d_scores: int, n: int, k: int, index_offset: int, d_index_map: int,
              d_work: int, stream: int = 0) -> None:
     check(lib().flexs_topk_dev(c_void_p(d_scores), n, k, index_offset, c_void_p(d_index_map), c_void_p(d_top_scores),
                                c_void_p(d_top_idx), c_void_p(d_work), c_void_p(stream)), "topk")
+
+
+def dedup_workspace_bytes(n: int) -> int:
+    b = int(lib().flexs_dedup_workspace_bytes(n))
+    if b < 0:
+        raise ValueError("n must be in [0, 2^31)")
+    return b
+
+
+def dedup_scores_dev(d_idx: int, n: int, seq_len: int, d_scores: int, d_scores_out: int, d_work: int, stream: int = 0) -> None:
+    """scores_out[i] = scores[i] if row i is the first occurrence of its sequence, else -inf (exact)."""
+    check(lib().flexs_dedup_scores_dev(c_void_p(d_idx), n, seq_len, c_void_p(d_scores), c_void_p(d_scores_out),
+                                       c_void_p(d_work), c_void_p(stream)), "dedup")
 
 
 def mutate_dev(d_parents: int, n: int, seq_len: int, alphabet_size: int, mu: float, seed: int, subsequence: int,

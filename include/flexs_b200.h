@@ -136,6 +136,18 @@ int flexs_topk_dev(const float *d_scores, int64_t n, int k, int64_t index_offset
                    const int64_t *d_index_map, float *d_top_scores, int64_t *d_top_idx,
                    void *d_work, void *stream);
 
+/* ---- K3b: de-duplication before the ranking ----------------------------------------------
+ * The reference ranks the keys of a dict (adalead.py:157, cmaes.py:112-115, dyna_ppo.py:310-314): a
+ * sequence proposed twice competes once.  d_scores_out[i] = d_scores[i] if row i of d_idx
+ * (uint8[n, seq_len]) is the LOWEST-indexed row with that content, else -inf (forward never produces
+ * -inf: nan_to_num clamps to +-FLT_MAX), so flexs_topk_dev on d_scores_out returns distinct
+ * sequences; winners whose score is -inf mean "fewer than k distinct candidates".  Exact (an
+ * open-addressing table keyed by the row bytes).  d_scores_out may alias d_scores.  n < 2^31.
+ * d_work: at least flexs_dedup_workspace_bytes(n) bytes.                                        */
+int64_t flexs_dedup_workspace_bytes(int64_t n);
+int flexs_dedup_scores_dev(const uint8_t *d_idx, int64_t n, int seq_len, const float *d_scores,
+                           float *d_scores_out, void *d_work, void *stream);
+
 /* ---- K5: candidate generation helpers -------------------------------------------------
  * flexs_mutate_dev replaces generate_random_mutant (sequence_utils.py:87-108) applied to
  * n parents at once: every residue is, with probability mu, replaced by a uniform draw

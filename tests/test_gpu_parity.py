@@ -605,6 +605,59 @@ def test_fp16_range_guard_falls_back_to_fp32_kernel():
         m.close()
 
 
+@pytest.mark.parametrize("L,A,n", [(8, 4, 300_000), (100, 4, 50_000), (3, 2, 1000), (237, 20, 4000), (1, 4, 77)])
+def test_dedup_scores_exact(L, A, n):
+    """flexs_dedup_scores_dev: the first occurrence of every distinct sequence keeps its score, every repeat gets
+    -inf — bit-exact against numpy's unique (the reference's dict keys, adalead.py:157)."""
+    rng = np.random.default_rng(L * 1000 + A)
+    idx = rng.integers(0, A, size=(n, L), dtype=np.uint8)
+    if L >= 100:                                   # long random sequences never repeat: plant repeats
+        src = rng.integers(0, n // 2, size=n // 3)
+        idx[n - len(src):] = idx[src]
+    scores = rng.normal(size=n).astype(np.float32)
+    _, first = np.unique(idx, axis=0, return_index=True)
+    want = np.full(n, -np.inf, dtype=np.float32)
+    want[first] = scores[first]
+    d_idx = torch.from_numpy(idx).cuda()
+    d_s = torch.from_numpy(scores).cuda()
+    d_o = torch.empty_like(d_s)
+    work = torch.empty(_native.dedup_workspace_bytes(n), dtype=torch.uint8, device="cuda")
+    for _ in range(2):                             # the workspace is reusable as is
+        _native.dedup_scores_dev(d_idx.data_ptr(), n, L, d_s.data_ptr(), d_o.data_ptr(), work.data_ptr(),
+                                 torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(d_o.cpu().numpy(), want)
+    _native.dedup_scores_dev(d_idx.data_ptr(), n, L, d_s.data_ptr(), d_s.data_ptr(), work.data_ptr(),
+                             torch.cuda.current_stream().cuda_stream)   # in place
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(d_s.cpu().numpy(), want)
+
+
+def test_virtual_screen_ranks_distinct_sequences():
+    """A screen whose candidates repeat (1M draws from the 65 536 8-mers in the reference's setting) must return k
+    DISTINCT winners, each through its first occurrence, like the reference's ranking of dict keys."""
+    import flexs_b200 as flexs
+    from flexs_b200.screen import VirtualScreen
+
+    L, n, B = 8, 200_000, 100
+    cnn = flexs.baselines.models.CNN(L, 32, 100, su.DNAA, seed=5)
+    idx = np.random.default_rng(3).integers(0, 4, size=(n, L), dtype=np.uint8)
+    scores = cnn.get_fitness(idx)
+    _, first = np.unique(idx, axis=0, return_index=True)
+    first = np.sort(first)
+    order = first[np.lexsort((first, -scores[first].astype(np.float64)))][: B - 1]
+    top_i, top_s = VirtualScreen(cnn, k=B - 1).screen(idx)
+    np.testing.assert_array_equal(top_i, order)
+    np.testing.assert_array_equal(top_s, scores[order])
+    assert len({bytes(r) for r in idx[top_i]}) == B - 1
+    # rows, not sequences: the best sequence's copies fill the list
+    rows_i, _ = VirtualScreen(cnn, k=B - 1, unique=False).screen(idx)
+    assert len({bytes(r) for r in idx[rows_i]}) < B - 1
+    # fewer distinct candidates than k: the list is short, not padded with repeats
+    few_i, few_s = VirtualScreen(cnn, k=B - 1).screen(idx[:40].repeat(5, axis=0))
+    assert len(few_i) == len(np.unique(idx[:40], axis=0)) and np.isfinite(few_s).all()
+
+
 def test_virtual_screen_single_rank_matches_numpy():
     """flexs_b200.screen.VirtualScreen (the sharded top-k of the path) on one rank: same winners, same order and
     scores as np.argsort over get_fitness; with >= 2 GPUs the NCCL form is covered by bench.py --gpus N."""

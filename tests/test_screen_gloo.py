@@ -37,6 +37,23 @@ def test_pack_unpack_roundtrip_bit_exact():
     assert torch.equal(s2.view(torch.int32), torch.cat(all_s).view(torch.int32))
 
 
+def test_pack_unpack_with_sequences_roundtrip():
+    """The unique screen ships the winners' residues in the same message (one collective): indices, score bits,
+    then k*L bytes padded to int64 words."""
+    k, world, L = 5, 3, 13   # 65 bytes: not a multiple of 8
+    rng = np.random.default_rng(1)
+    msgs, all_s, all_i, all_q = [], [], [], []
+    for r in range(world):
+        s = torch.from_numpy(rng.normal(size=k).astype(np.float32))
+        i = torch.from_numpy(rng.integers(-1, 1 << 40, size=k))
+        q = torch.from_numpy(rng.integers(0, 20, size=(k, L), dtype=np.uint8))
+        msgs.append(screen.pack_topk(s, i, q)); all_s.append(s); all_i.append(i); all_q.append(q)
+    assert msgs[0].numel() == 2 * k + 9
+    s2, i2, q2 = screen.unpack_topk(torch.cat(msgs), world, k, L)
+    assert torch.equal(i2, torch.cat(all_i)) and torch.equal(q2, torch.cat(all_q))
+    assert torch.equal(s2.view(torch.int32), torch.cat(all_s).view(torch.int32))
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))

@@ -1,0 +1,41 @@
+"""torchrun --nproc-per-node 2 tools/screen_2gpu_check.py — the sharded unique virtual screen against numpy.
+Candidates repeat inside and ACROSS the shards; every rank must return the same k distinct winners, each through its
+lowest global index, with the scores of a single-process ranking of the de-duplicated list."""
+import os
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import flexs_b200 as flexs
+from flexs_b200.screen import VirtualScreen
+from flexs_b200.utils import sequence_utils as su
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+dist.init_process_group("nccl")
+ok = True
+for L, n, B in ((8, 300_001, 100), (100, 40_000, 50)):
+    cnn = flexs.baselines.models.CNN(L, 32, 100, su.DNAA, seed=5, device=torch.cuda.current_device())
+    rng = np.random.default_rng(11)
+    idx = rng.integers(0, 4, size=(n, L), dtype=np.uint8)
+    if L == 100:                      # plant copies of first-half rows in the second half (the other shard)
+        src = rng.integers(0, n // 2, size=n // 4)
+        idx[n - len(src):] = idx[src]
+    top_i, top_s = VirtualScreen(cnn, k=B - 1).screen(idx)
+    cnn2 = flexs.baselines.models.CNN(L, 32, 100, su.DNAA, seed=5, device=torch.cuda.current_device())
+    scores = cnn2.get_fitness(idx)
+    _, first = np.unique(idx, axis=0, return_index=True)
+    first = np.sort(first)
+    order = first[np.lexsort((first, -scores[first].astype(np.float64)))][: B - 1]
+    same = np.array_equal(top_i, order) and np.array_equal(top_s, scores[order])
+    print(f"rank {rank}: L={L} n={n} k={B - 1}: {'OK' if same else 'MISMATCH'}", flush=True)
+    ok = ok and same
+flag = torch.tensor([0 if ok else 1], device="cuda")
+dist.all_reduce(flag)
+dist.destroy_process_group()
+sys.exit(int(flag.item() != 0))
