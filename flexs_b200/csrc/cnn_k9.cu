@@ -11,9 +11,10 @@
 // (cp.async, no registers).  What is left for the tensor pipe is conv3 (3 taps) and the dense head.
 //
 // Row mapping.  MMA row i = 8c + b of a 128-row tile is output position 16q + c of sequence ("stream") b of an item of
-// 8 sequences: a core matrix holds the same position of 8 sequences, a tap is +1 core matrix = +128 B (aligned), and
-// a thread of the epilogue sees ONE sequence for the whole item, so GlobalMaxPooling1D is a running fmaxf in registers
-// (two shuffles and four shared atomics per item instead of a REDUX round per tile and sequence).
+// 8 sequences: an 8-row group holds the same position of 8 sequences, a tap is +1 group = +1024 B (swizzle-aligned),
+// and a thread of the epilogue sees ONE sequence for the whole item, so GlobalMaxPooling1D is a running fmaxf in
+// registers (bias, scale and ReLU once per item; the warps merge an item through a staged reduction, no atomics)
+// instead of a REDUX round per tile and sequence.
 //
 // Roles (18 warps): 0-7 producers (warp w owns ring slot w: packed residues -> table index -> 128-byte gathers into a
 // SWIZZLE_128B operand slot), 8-15 conv3 epilogue (alternate tiles, running max in registers), 16-17 issue the MMAs of
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
     if (tid == 0) issue_idx_load(p, smem_raw + of.idx, mbar_idx, blockIdx.x);
 
     uint32_t kt = 0;  // tiles before the current group: tile k uses slot = accumulator = k & 7
-    uint32_t gi = 0;  // groups before the current one: packed-residue / feature buffer = gi & 1
+    uint32_t gi = 0;  // groups before the current one: packed-residue buffer and residue-barrier parity = gi & 1
     long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long t_begin = now();
 
