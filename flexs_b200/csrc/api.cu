@@ -311,8 +311,18 @@ int flexs_model_score_host(flexs_model_t *m, const char *h_chars, int64_t n, con
     FX_CUDA(cudaSetDevice(m->device));
     int rc = ensure_host_staging(m, n);
     if (rc != FLEXS_OK) return rc;
-    // equal chunks (a multiple of 128 sequences, the kernels' group size) instead of full slots plus a remainder:
-    // every chunk takes the same kernel path, so scores do not depend on where a sequence falls in the batch
+    // One kernel choice for the whole call: AUTO is resolved on the full batch and held for every chunk (a short last
+    // chunk would otherwise fall to the small-batch kernel and its scores would differ in the last bits), so scores
+    // do not depend on where a sequence falls in the batch.
+    struct VariantHold {
+        flexs_model *m;
+        int saved;
+        ~VariantHold() { m->variant = saved; }
+    } hold{m, m->variant};
+    if (m->variant == FLEXS_VARIANT_AUTO) {
+        const int v = flexs_model_active_variant(m, n);
+        if (v == FLEXS_VARIANT_ENUM || v == FLEXS_VARIANT_UMMA_LUT) m->variant = v;
+    }
     const int64_t L = m->L;
     // A chunk is a whole number of waves of the persistent kernels (sm_count groups of 128 sequences), close to
     // FLEXS_HOST_CHUNK_MB of residue characters: small enough that the first copy in and the last compute (which nothing

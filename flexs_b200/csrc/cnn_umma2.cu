@@ -472,103 +472,9 @@ __global__ void __launch_bounds__(NT, 1) cnn_umma2_kernel(const U2Params p) {
             __syncthreads();
             const long long tg1 = clock64();
             if (p.dense_umma) {
-                unsigned char *dx1 = a1 + DS_X1, *db1 = a1 + DS_B1, *dx2 = a1 + DS_X2, *db2 = a1 + DS_B2;
-                float *dpart = reinterpret_cast<float *>(a1 + DS_PART);
-                const float *gdv = reinterpret_cast<const float *>(uw + OFF_DV);
-                float *dv = reinterpret_cast<float *>(a1 + DS_DV);  // bias / output-weight vectors, staged in smem
-                const float inv_d1s = __ldg(gdv + 3 * DH), inv_d2 = __ldg(gdv + 3 * DH + 1), bd3v = __ldg(gdv + 3 * DH + 2);
-                for (int i = tid; i < 3 * DH; i += NT) dv[i] = __ldg(gdv + i);
-                // (1) stage the dense weight planes, turn the features into the A operand of layer 1
-                for (int i = tid; i < 4 * DBK / 16; i += NT)
-                    reinterpret_cast<uint4 *>(db1)[i] = __ldg(reinterpret_cast<const uint4 *>(uw + OFF_DB1) + i);
-                for (int i = tid; i < 14 * DBK / 16; i += NT)
-                    reinterpret_cast<uint4 *>(db2)[i] = __ldg(reinterpret_cast<const uint4 *>(uw + OFF_DB2) + i);
-                if (tid < 4 * DSLOTS) {
-                    const int slot = tid & (DSLOTS - 1), cchunk = tid >> 7;
-                    float x[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) x[q] = (slot < p.sbcap) ? featT[(cchunk * 8 + q) * p.sbp + slot] * ASCALE : 0.f;
-                    uint4 hi4, lo4;
-                    split8(x, hi4, lo4, xmax);
-                    *reinterpret_cast<uint4 *>(dx1 + (size_t)cchunk * DPLANE + slot * 16) = hi4;
-                    *reinterpret_cast<uint4 *>(dx1 + (size_t)(4 + cchunk) * DPLANE + slot * 16) = lo4;
-                }
-                fence_async_smem();
-                __syncthreads();
-                const int lq = wid & 3, half = wid >> 2, slot = 32 * lq + lane;
-                const uint32_t tl = tmem_base + ((uint32_t)(lq * 32) << 16);
-                // (2) layer 1 on the tensor cores, (3) bias + ReLU + split -> A operand of layer 2
-                if (wid == MMAW) {
-                    tc_fence_after();
-                    issue_dense_layer<2, 4>(fxd::smem_u32(dx1), fxd::smem_u32(db1), tmem_base);
-                    umma_commit_elect(dbar);
-                } else if (wid < 8) {
-                    fxd::mbar_wait(dbar, dph & 1);
-                    tc_fence_after();
-                    for (int c7 = 0; c7 < 7; ++c7) {
-                        const int cchunk = half * 7 + c7;
-                        uint32_t va[8], vb[8];
-                        tmem_ld8_nowait(tl + (uint32_t)(cchunk * 8), va);
-                        tmem_ld8_nowait(tl + (uint32_t)(DH + cchunk * 8), vb);
-                        const float4 b0 = *reinterpret_cast<const float4 *>(dv + cchunk * 8);
-                        const float4 b1 = *reinterpret_cast<const float4 *>(dv + cchunk * 8 + 4);
-                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                        tmem_ld_wait();
-                        float x[8];
-#pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            x[q] = fmaxf(fmaf(__uint_as_float(va[q]) + __uint_as_float(vb[q]), inv_d1s, bb[q]), 0.f);
-                        uint4 hi4, lo4;
-                        split8(x, hi4, lo4, xmax);
-                        *reinterpret_cast<uint4 *>(dx2 + (size_t)cchunk * DPLANE + slot * 16) = hi4;
-                        *reinterpret_cast<uint4 *>(dx2 + (size_t)(14 + cchunk) * DPLANE + slot * 16) = lo4;
-                    }
-                }
-                ++dph;
-                fence_async_smem();
-                tc_fence_before();
-                __syncthreads();
-                // (4) layer 2, (5) bias + ReLU + dot with the output weights
-                if (wid == MMAW) {
-                    tc_fence_after();
-                    issue_dense_layer<7, 14>(fxd::smem_u32(dx2), fxd::smem_u32(db2), tmem_base + 256u);
-                    umma_commit_elect(dbar);
-                } else if (wid < 8) {
-                    fxd::mbar_wait(dbar, dph & 1);
-                    tc_fence_after();
-                    float sum = 0.f;
-                    for (int c7 = 0; c7 < 7; ++c7) {
-                        const int cchunk = half * 7 + c7;
-                        uint32_t va[8], vb[8];
-                        tmem_ld8_nowait(tl + 256u + (uint32_t)(cchunk * 8), va);
-                        tmem_ld8_nowait(tl + 256u + (uint32_t)(DH + cchunk * 8), vb);
-                        const float4 b0 = *reinterpret_cast<const float4 *>(dv + DH + cchunk * 8);
-                        const float4 b1 = *reinterpret_cast<const float4 *>(dv + DH + cchunk * 8 + 4);
-                        const float4 w0 = *reinterpret_cast<const float4 *>(dv + 2 * DH + cchunk * 8);
-                        const float4 w1 = *reinterpret_cast<const float4 *>(dv + 2 * DH + cchunk * 8 + 4);
-                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                        const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float d2 = fmaxf(fmaf(__uint_as_float(va[q]) + __uint_as_float(vb[q]), inv_d2, bb[q]), 0.f);
-                            sum = fmaf(d2, ww[q], sum);
-                        }
-                    }
-                    dpart[half * DSLOTS + slot] = sum;
-                }
-                ++dph;
-                tc_fence_before();
-                __syncthreads();
-                // (6) Dense(1) bias, nan_to_num (keras_model.py:77), ensemble mean (ensemble.py:24)
-                for (int sl = tid; sl < g_slots; sl += NT) {
-                    const float y = fxd::nan_to_num(dpart[sl] + dpart[DSLOTS + sl] + bd3v);
-                    const long long seq = slot_seq[sl];
-                    float tot = (mem == 0) ? y : p.out[seq] + y;
-                    if (p.M > 1 && mem == p.M - 1) tot = tot / (float)p.M;
-                    p.out[seq] = tot;
-                }
-                __syncthreads();
+                // tensor-core dense head on the idle activation buffers (u2::dense_head_umma, shared with cnn_k9.cu)
+                dense_head_umma<NT, MMAW, true>(a1, featT, p.sbp, p.sbcap, g_slots, uw, tmem_base, dbar, dph, xmax, mem, p.M,
+                                                p.out, [slot_seq](int sl) { return slot_seq[sl]; });
             } else {
                 fxd::DenseArgs da{w + p.o.wd1, w + p.o.bd1, w + p.o.wd2, w + p.o.bd2, w + p.o.wd3, w + p.o.bd3,
                                   featT, reinterpret_cast<float *>(a1), slot_seq, p.out,

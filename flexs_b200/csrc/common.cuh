@@ -175,12 +175,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     // Slow path with a watchdog: no wait of these kernels lasts longer than a launch (milliseconds).  A protocol bug
-    // must surface as a launch failure the caller sees, not as a GPU that never comes back.
-    unsigned long long t0, t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    // must surface as a launch failure the caller sees, not as a GPU that never comes back.  The timer is read once
+    // per 64 failed attempts so the loop costs the working warps no more issue slots than a bare retry.
+    unsigned long long t0 = 0, t1;
+    unsigned int spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 4000000000ull) __trap();
+        if ((++spins & 63u) == 0) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t0 == 0) t0 = t1;
+            else if (t1 - t0 > 4000000000ull) __trap();
+        }
     }
 }
 // global -> shared bulk copy; dst/src 16-byte aligned, bytes a multiple of 16
