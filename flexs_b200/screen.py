@@ -168,8 +168,14 @@ class VirtualScreen:
         top_s, top_i, _ = self.local_topk(idx_local, index_offset)
         if not self.unique or self._world()[1] == 1:
             return self.merge(top_s, top_i)
-        rows = (top_i - index_offset).clamp(min=0)          # absent winners (-1) borrow row 0; their score is -inf
-        return self.merge(top_s, top_i, idx_local[rows].contiguous())
+        if idx_local.shape[0] == 0:                         # an empty shard (fewer candidates than ranks)
+            import torch
+
+            seqs = torch.zeros((self.k, idx_local.shape[1]), dtype=torch.uint8, device=idx_local.device)
+        else:
+            rows = (top_i - index_offset).clamp(min=0)      # absent winners (-1) borrow row 0; their score is -inf
+            seqs = idx_local[rows].contiguous()
+        return self.merge(top_s, top_i, seqs)
 
     def screen(self, sequences, alphabet: Optional[str] = None):
         """Host entry: every rank passes the SAME full candidate list (strings or ``uint8[N, L]`` indices);
