@@ -17,8 +17,8 @@
 // instead of a REDUX round per tile and sequence.
 //
 // Roles (18 warps): 0-7 producers (warp w owns ring slot w: packed residues -> table index -> 128-byte gathers into a
-// SWIZZLE_128B operand slot), 8-15 conv3 epilogue (alternate tiles, running max in registers), 16-17 issue the MMAs of
-// alternate tiles.  Eight operand slots and eight TMEM accumulators (64 columns each); the roles only meet through
+// SWIZZLE_128B operand slot), 8-15 conv3 epilogue (two sets of 4 warps on alternate items, running max in registers),
+// 16-17 issue the MMAs of alternate tiles.  Eight operand slots and eight TMEM accumulators (64 columns each); the roles only meet through
 // mbarriers, there is no CTA-wide barrier inside the kernel.  The pooled features of every 128 sequences leave as a
 // [32][128] fp32 tile (16 KB); cnn_k9_dense_kernel turns those tiles into scores with two tcgen05 GEMMs per tile,
 // its weights staged once per CTA.
@@ -95,7 +95,7 @@ __host__ __device__ inline Offs carve(const K9Params &p) {
     o.idx = take(p.idx_slot, 16);
     o.pw = take((size_t)2 * GS * p.nwp * 4, 16);
     o.feat = take((size_t)F * SBP * 4, 16);
-    o.stage = take((size_t)2 * 8 * 256 * 4, 16);  // epilogue merge buffers: [double buffer][8 warps][256 maxima]
+    o.stage = take((size_t)2 * 2 * 4 * 256 * 4, 16);  // epilogue merge buffers: [set][double buffer][4 warps][256 maxima]
     o.ring = take((size_t)RING * SLOT, 1024);
     o.total = off;
     return o;
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const Offs of = carve(p);
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + of.mbar);
-    uint64_t *mbar_idx = mbar, *full = mbar + 8, *empty = mbar + 16, *tfull = mbar + 24, *tempty = mbar + 32;
+    uint64_t *mbar_idx = mbar, *full = mbar + 8, *empty = mbar + 16, *tfull = mbar + 24, *tempty = mbar + 40;  // tfull: [2 sets][8]
     uint32_t *tmem_addr_s = reinterpret_cast<uint32_t *>(smem_raw + of.tm);
     float *b3 = reinterpret_cast<float *>(smem_raw + of.b3);
     unsigned char *uw3 = smem_raw + of.uw3;
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
         fxd::mbar_init(mbar_idx, 1);
         for (int i = 0; i < RING; ++i) {
             fxd::mbar_init(&full[i], 1); fxd::mbar_init(&empty[i], 1);
-            fxd::mbar_init(&tfull[i], 1); fxd::mbar_init(&tempty[i], 4);
+            fxd::mbar_init(&tfull[i], 1); fxd::mbar_init(&tfull[8 + i], 1); fxd::mbar_init(&tempty[i], 4);
         }
         fxd::fence_mbar_init();
     }
@@ -343,19 +343,24 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
         }
     } else if (wid < MMAW) {
         // =========================== conv3 epilogue: running max per sequence ===========================
-        // Warp (lq, par) owns TMEM lanes 32 lq .. 32 lq + 31 (positions 4 lq .. 4 lq + 3 of the 8 streams) of the tiles of
-        // parity par — i.e. of four of the eight accumulators, at every one of their uses, so no barrier phase is ever
-        // skipped — and all 32 filters.
+        // Two sets of 4 warps; set `par` owns the items of parity par with all their tiles, so an item is merged inside
+        // one set.  The eight accumulators are shared (tile k uses k & 7), which means a set does NOT see every use of an
+        // accumulator — and a parity wait cannot tell phase n from n + 2 — so each set has its own "accumulator full"
+        // barriers: the MMA warp commits a tile to the barrier of the set that owns it, and the set flips one private
+        // parity bit per accumulator.  Warp (lq, par) owns TMEM lanes 32 lq .. 32 lq + 31 (positions 4 lq .. 4 lq + 3 of
+        // the 8 streams) and all 32 filters.
         // max_t relu(a_t * inv3 + b) == relu(max_t(a_t) * inv3 + b) (inv3 > 0): per tile only one packed add of the two
         // accumulator halves and one fmaxf per filter; scale, bias and ReLU wait for the item's end.
-        const int lq = wid & 3, par = (wid >> 2) & 1, ew = wid - NPROD;
+        const int lq = wid & 3, par = (wid >> 2) & 1;
         // TMEM lane 32 lq + lane is MMA row 8 c + b: position c of stream b
         const int c = 4 * lq + (lane >> 3), b = lane & 7;
         const uint32_t tlane = tmem_base + ((uint32_t)(lq * 32) << 16);
         const bool up8 = (lane & 8) != 0, up16 = (lane & 16) != 0;
         const int et = tid - NPROD * 32;  // thread index among the 256 epilogue threads
-        float *stage_s = reinterpret_cast<float *>(smem_raw + of.stage);  // [2 buffers][8 warps][4 fg][8 b][8 f]
-        uint32_t nflush = 0;
+        float *stage_s = reinterpret_cast<float *>(smem_raw + of.stage) + par * 2 * 4 * 256;  // [2 buffers][4 warps][4 fg][8 b][8 f]
+        uint64_t *tfull_mine = tfull + 8 * par;
+        uint32_t nflush = 0;    // items of this set so far: staging buffer = nflush & 1
+        uint32_t phase_bits = 0;  // bit a: parity of the next phase of this set's barrier for accumulator a
         float mx[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) mx[j] = -INFINITY;
@@ -368,7 +373,8 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
             auto visit = [&](uint32_t k, int q) {
                 const uint32_t acc = k & 7u;
                 const long long w0 = now();
-                fxd::mbar_wait(&tfull[acc], (k >> 3) & 1);
+                fxd::mbar_wait(&tfull_mine[acc], (phase_bits >> acc) & 1u);
+                phase_bits ^= 1u << acc;
                 const long long w1 = now();
                 tc_fence_after();
                 const bool valid = !(PROF && (p.dbg & 4)) && 16 * q + c < T;  // rows past the sequence: last tile only
@@ -419,51 +425,29 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
                 wr[0] = make_float4(k8[0], k8[1], k8[2], k8[3]);
                 wr[1] = make_float4(k8[4], k8[5], k8[6], k8[7]);
             };
-            if (nti == 1) {
-                // One tile per item (8 <= L <= 20): the item belongs to one tile parity, i.e. to the 4 warps of one set.
-                // Step 2: those 4 warps (4 positions each) meet in the set's staging buffer — plain stores, a 128-thread
-                // barrier, warp lq reduces filters 8 lq .. 8 lq + 7 — step 3: scale, bias, ReLU, one store per feature.
-                for (int item = 0; item < nitems; ++item) {
-                    const uint32_t k = kt + (uint32_t)item;
-                    if ((k & 1u) != (uint32_t)par) continue;
-                    visit(k, 0);
-                    float *stg = stage_s + (par * 2 + (int)(nflush & 1)) * 4 * 256;
-                    butterfly_to(stg + lq * 256);
-                    if (par == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
-                    else asm volatile("bar.sync 4, 128;" ::: "memory");
-                    const int pr = lane >> 3, f = 8 * lq + 2 * pr, sl = item * 8 + b;
-                    const float *rd = stg + (lq * 8 + b) * 8 + 2 * pr;
-                    float2 t = *reinterpret_cast<const float2 *>(rd);
+            // Step 2: the 4 warps of the set (4 positions each) meet in the set's double-buffered staging area — plain
+            // stores, a 128-thread barrier, warp lq reduces filters 8 lq .. 8 lq + 7.  Step 3: scale, bias, ReLU, one plain
+            // store per feature: no atomics anywhere.
+            for (int item = par; item < nitems; item += 2) {
+                const uint32_t k0 = kt + (uint32_t)(item * nti);
+                for (int q = 0; q < nti; ++q) visit(k0 + (uint32_t)q, q);
+                float *stg = stage_s + (int)(nflush & 1) * 4 * 256;
+                butterfly_to(stg + lq * 256);
+                if (par == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
+                else asm volatile("bar.sync 4, 128;" ::: "memory");
+                const int pr = lane >> 3, f = 8 * lq + 2 * pr, sl = item * 8 + b;
+                const float *rd = stg + (lq * 8 + b) * 8 + 2 * pr;
+                float2 t = *reinterpret_cast<const float2 *>(rd);
 #pragma unroll
-                    for (int w4 = 1; w4 < 4; ++w4) {
-                        const float2 o2 = *reinterpret_cast<const float2 *>(rd + w4 * 256);
-                        t.x = fmaxf(t.x, o2.x); t.y = fmaxf(t.y, o2.y);
-                    }
-                    if (sl < s_grp) {
-                        featT[f * SBP + sl] = fmaxf(fmaf(t.x, inv3, b3[f]), 0.f);
-                        featT[(f + 1) * SBP + sl] = fmaxf(fmaf(t.y, inv3, b3[f + 1]), 0.f);
-                    }
-                    ++nflush;
+                for (int w4 = 1; w4 < 4; ++w4) {
+                    const float2 o2 = *reinterpret_cast<const float2 *>(rd + w4 * 256);
+                    t.x = fmaxf(t.x, o2.x); t.y = fmaxf(t.y, o2.y);
                 }
-            } else {
-                // Step 2: the 8 epilogue warps (4 position quarters x 2 tile parities) meet in a double-buffered staging
-                // area: plain stores, one 256-thread barrier, and warp w reduces filters 4 w .. 4 w + 3.  Step 3: scale,
-                // bias, ReLU, one plain store per feature: no atomics anywhere.
-                for (int item = 0; item < nitems; ++item) {
-                    const uint32_t k0 = kt + (uint32_t)(item * nti);
-                    for (int q = (int)((k0 ^ (uint32_t)par) & 1u); q < nti; q += 2) visit(k0 + (uint32_t)q, q);
-                    float *stg = stage_s + (nflush & 1) * 8 * 256;
-                    butterfly_to(stg + ew * 256);
-                    asm volatile("bar.sync 2, %0;" ::"n"(8 * 32) : "memory");
-                    // lane (b, fi) of warp ew takes filter f = 4 ew + fi of stream b from all 8 warps' slots
-                    const int f = 4 * ew + (lane >> 3), sl = item * 8 + b;
-                    const float *rd = stg + ((f >> 3) * 8 + b) * 8 + (f & 7);
-                    float t = rd[0];
-#pragma unroll
-                    for (int w8 = 1; w8 < 8; ++w8) t = fmaxf(t, rd[w8 * 256]);
-                    if (sl < s_grp) featT[f * SBP + sl] = fmaxf(fmaf(t, inv3, b3[f]), 0.f);
-                    ++nflush;
+                if (sl < s_grp) {
+                    featT[f * SBP + sl] = fmaxf(fmaf(t.x, inv3, b3[f]), 0.f);
+                    featT[(f + 1) * SBP + sl] = fmaxf(fmaf(t.y, inv3, b3[f + 1]), 0.f);
                 }
+                ++nflush;
             }
             kt += ntiles;
             // the group's features are complete once all 8 epilogue warps are here: copy the [32][128] tile out
@@ -475,7 +459,7 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
                 const int row = i >> 5, col = (i & 31) * 4;
                 dst[i] = *reinterpret_cast<const float4 *>(featT + row * SBP + col);
             }
-            // the next group's first features may be stored after a barrier of only one set (one-tile items): nobody
+            // the next group's first features are stored after a barrier of only one set: nobody
             // may still be reading this group's
             asm volatile("bar.sync 2, %0;" ::"n"(8 * 32) : "memory");
         }
@@ -497,7 +481,7 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
                 if (PROF && lane == 0 && wid == MMAW) { pt[5] += m1 - m0; pt[6] += now() - m1; }
                 tc_fence_after();
                 if (!(PROF && (p.dbg & 1))) issue_conv3_tile(ring_addr + s * SLOT, uw3_addr, tmem_base + s * 64u);
-                umma_commit_elect(&tfull[s]);
+                umma_commit_elect(&tfull[8u * ((tl / (uint32_t)nti) & 1u) + s]);  // the epilogue set that owns the tile's item
                 umma_commit_elect(&empty[s]);
             }
             kt += ntiles;
