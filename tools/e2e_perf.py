@@ -7,11 +7,11 @@ import numpy as np
 import torch
 
 from flexs_b200 import _native
-from oracle import flexs_oracle as fo
+from _weights import cnn_shapes, trained_like
 
 L, n = 100, 1 << 22
 m = _native.NativeModel("cnn", seq_len=L, alphabet_size=4, num_filters=32, hidden_size=100, kernel_size=5)
-m.set_weights(fo.trained_like_weights(fo.CNNShape(L, 4, 32, 100, 5).weight_shapes(), 5))
+m.set_weights(trained_like(cnn_shapes(L, 4), 5))
 idx = torch.randint(0, 4, (n, L), dtype=torch.uint8)
 chars = torch.tensor(list(b"TGCA"), dtype=torch.uint8)[idx.long()].contiguous().pin_memory()
 out = torch.empty(n, dtype=torch.float32).pin_memory()

@@ -11,12 +11,12 @@ import numpy as np
 import torch
 
 from flexs_b200 import _native
-from oracle import flexs_oracle as fo
+from _weights import cnn_shapes, trained_like
 
 L = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 n = 1 << (int(sys.argv[2]) if len(sys.argv) > 2 else 22)
 A = 4
-ws = fo.trained_like_weights(fo.CNNShape(L, A, 32, 100, 5).weight_shapes(), 5)
+ws = trained_like(cnn_shapes(L, A), 5)
 m = _native.NativeModel("cnn", seq_len=L, alphabet_size=A, num_filters=32, hidden_size=100, kernel_size=5)
 m.set_weights(ws)
 g = torch.Generator(device="cuda").manual_seed(1234)

@@ -7,12 +7,12 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import torch
 
 from flexs_b200 import _native
-from oracle import flexs_oracle as fo
+from _weights import cnn_shapes, trained_like
 
 for L, M, n in ((8, 1, 1 << 20), (14, 3, 1 << 20), (100, 1, 1 << 22)):
     m = _native.NativeModel("cnn", seq_len=L, alphabet_size=4, num_filters=32, hidden_size=100, kernel_size=5, n_members=M)
     for i in range(M):
-        m.set_weights(fo.trained_like_weights(fo.CNNShape(L, 4, 32, 100, 5).weight_shapes(), 5 + i), i)
+        m.set_weights(trained_like(cnn_shapes(L, 4), 5 + i), i)
     idx = torch.randint(0, 4, (n, L), dtype=torch.uint8, device="cuda")
     out = torch.empty(n, dtype=torch.float32, device="cuda")
     s = torch.cuda.current_stream().cuda_stream

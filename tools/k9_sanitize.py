@@ -1,4 +1,5 @@
-"""Small forward passes of cnn_k9 for compute-sanitizer (memcheck / racecheck / synccheck)."""
+"""Small forward passes of cnn_k9 for compute-sanitizer (memcheck / racecheck / synccheck), each compared with the
+first-generation tcgen05 kernel on the same inputs."""
 import sys
 from pathlib import Path
 
@@ -7,11 +8,10 @@ import numpy as np
 import torch
 
 from flexs_b200 import _native
-from oracle import c_oracle as co
-from oracle import flexs_oracle as fo
+from _weights import cnn_shapes, trained_like
 
 for L, n in ((100, 300), (14, 700), (21, 259)):
-    ws = fo.trained_like_weights(fo.CNNShape(L, 4, 32, 100, 5).weight_shapes(), L)
+    ws = trained_like(cnn_shapes(L, 4), L)
     m = _native.NativeModel("cnn", seq_len=L, alphabet_size=4, num_filters=32, hidden_size=100, kernel_size=5)
     m.set_weights(ws)
     m.set_variant(_native.VARIANT_UMMA_LUT)
@@ -20,6 +20,10 @@ for L, n in ((100, 300), (14, 700), (21, 259)):
     out = torch.empty(n, dtype=torch.float32, device="cuda")
     m.forward_dev(d.data_ptr(), n, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
-    ref = co.cnn_forward(idx, [ws])
-    print(L, n, "max err / scale", float(np.abs(out.cpu().numpy() - ref).max() / np.abs(ref).max()), flush=True)
+    got = out.cpu().numpy()
+    m.set_variant(_native.VARIANT_UMMA)
+    m.forward_dev(d.data_ptr(), n, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ref = out.cpu().numpy()
+    print(L, n, "max |k9 - umma2| / scale", float(np.abs(got - ref).max() / np.abs(ref).max()), flush=True)
     m.close()

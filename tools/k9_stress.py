@@ -8,14 +8,14 @@ import numpy as np
 import torch
 
 from flexs_b200 import _native
-from oracle import flexs_oracle as fo
+from _weights import cnn_shapes, trained_like
 
 rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 worst = 0.0
 for L in (8, 9, 14, 20, 21, 36, 37, 100, 116, 120, 170):
     m = _native.NativeModel("cnn", seq_len=L, alphabet_size=4, num_filters=32, hidden_size=100, kernel_size=5)
-    m.set_weights(fo.trained_like_weights(fo.CNNShape(L, 4, 32, 100, 5).weight_shapes(), L))
+    m.set_weights(trained_like(cnn_shapes(L, 4), L))
     nmax = 400_000 if L <= 40 else 150_000
     idx = torch.randint(0, 4, (nmax, L), dtype=torch.uint8, device="cuda")
     a = torch.empty(nmax, dtype=torch.float32, device="cuda")

@@ -6,11 +6,11 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import torch
 
 from flexs_b200 import _native
-from oracle import flexs_oracle as fo
+from _weights import cnn_shapes, trained_like
 
 for L, n in ((237, 1 << 17), (90, 1 << 18), (735, 1 << 15)):
     m = _native.NativeModel("cnn", seq_len=L, alphabet_size=20, num_filters=32, hidden_size=100, kernel_size=5)
-    m.set_weights(fo.trained_like_weights(fo.CNNShape(L, 20, 32, 100, 5).weight_shapes(), 5))
+    m.set_weights(trained_like(cnn_shapes(L, 20), 5))
     idx = torch.randint(0, 20, (n, L), dtype=torch.uint8, device="cuda")
     out = torch.empty(n, dtype=torch.float32, device="cuda")
     s = torch.cuda.current_stream().cuda_stream
