@@ -44,6 +44,7 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile every CUDA source for sm_100a and link the shared library."""
     if not force and not needs_build():
+        build_packstr()
         return LIB_PATH
     obj_dir = CSRC / "build"
     obj_dir.mkdir(exist_ok=True)
@@ -74,7 +75,31 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError("flexs_b200: link failed")
     if verbose:
         print("\n".join(log))
+    build_packstr(force)
     return LIB_PATH
+
+
+def packstr_path() -> Path:
+    import sysconfig
+
+    return PKG_DIR / ("_packstr" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+
+
+def build_packstr(force: bool = False) -> Path:
+    """Compile the CPython host helper (csrc/packstr.c, no CUDA) with the C compiler, in-tree."""
+    import sysconfig
+
+    out = packstr_path()
+    src = CSRC / "packstr.c"
+    if not force and out.exists() and out.stat().st_mtime >= src.stat().st_mtime:
+        return out
+    cc = os.environ.get("CC", "gcc")
+    cmd = [cc, "-O2", "-shared", "-fPIC", f"-I{sysconfig.get_paths()['include']}", str(src), "-o", str(out)]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout)
+        raise RuntimeError("flexs_b200: building _packstr failed")
+    return out
 
 
 if __name__ == "__main__":

@@ -28,6 +28,23 @@ def _lut(alphabet: str) -> np.ndarray:
     return table
 
 
+_PACKSTR = False  # not looked up yet
+
+
+def _packstr():
+    """``flexs_b200/_packstr`` (csrc/packstr.c, built next to the CUDA library): packs a list of str in one C pass.
+    ``None`` when it has not been built — the pure-Python route below is equivalent, only ~6x slower."""
+    global _PACKSTR
+    if _PACKSTR is False:
+        try:
+            from flexs_b200 import _packstr as mod
+
+            _PACKSTR = mod.pack
+        except ImportError:
+            _PACKSTR = None
+    return _PACKSTR
+
+
 def sequences_to_char_array(sequences: Union[Sequence[str], np.ndarray], seq_len: int = None) -> np.ndarray:
     """Pack sequences into a contiguous ``uint8[N, L]`` array of residue CHARACTER codes.
 
@@ -52,6 +69,13 @@ def sequences_to_char_array(sequences: Union[Sequence[str], np.ndarray], seq_len
     else:
         seqs = [str(s) for s in sequences] if not isinstance(sequences[0], str) else sequences
         width = len(seqs[0])
+        pack = _packstr()
+        if pack is not None and isinstance(seqs, (list, tuple)):
+            chars = np.empty((n, width), dtype=np.uint8)
+            pack(seqs, chars)  # one C pass over the str objects; raises the same ValueErrors as the route below
+            if seq_len is not None and width != seq_len:
+                raise ValueError(f"expected sequences of length {seq_len}, got {width}")
+            return chars
         joined = "".join(seqs)
         if len(joined) != n * width or max(map(len, seqs)) != width:
             raise ValueError("all sequences must have the same length")

@@ -238,3 +238,36 @@ def test_library_exports_every_declared_symbol(native_lib):
     assert native_lib.flexs_abi_version() == 1
     assert native_lib.flexs_topk_workspace_bytes(1000, 100) > 0
     assert native_lib.flexs_topk_workspace_bytes(1000, 5000) < 0
+
+
+def test_packstr_extension_matches_pure_python_route():
+    """csrc/packstr.c (CPython helper built next to the CUDA library): one C pass over a list of str gives the same
+    uint8[N, L] character array and the same ValueErrors as the "".join / encode route it short-cuts."""
+    from flexs_b200 import _build
+    from flexs_b200.utils import sequence_utils as su
+
+    _build.build_packstr()
+    su._PACKSTR = False                                   # look the module up again
+    assert su._packstr() is not None
+    rng = np.random.default_rng(0)
+    letters = np.array(list("ACDEFGHIKLMNPQRSTVWY\xe9"))  # includes a Latin-1 character above 127
+    seqs = ["".join(r) for r in letters[rng.integers(0, len(letters), size=(5000, 37))]]
+    fast = su.sequences_to_char_array(seqs)
+    su._PACKSTR = None                                    # force the pure-Python route
+    try:
+        slow = su.sequences_to_char_array(seqs)
+        for bad in (["ACG", "AC"], ["AC", "ACG"], ["AĀC", "ACG"]):
+            with pytest.raises(ValueError) as e_slow:
+                su.sequences_to_char_array(bad)
+            su._PACKSTR = False
+            with pytest.raises(ValueError) as e_fast:
+                su.sequences_to_char_array(bad)
+            su._PACKSTR = None
+            assert str(e_fast.value).split(":")[0] == str(e_slow.value).split(":")[0]
+    finally:
+        su._PACKSTR = False
+    assert fast.dtype == np.uint8 and fast.shape == (5000, 37) and np.array_equal(fast, slow)
+    assert su.sequences_to_char_array(tuple(seqs[:3])).tolist() == slow[:3].tolist()
+    assert su.sequences_to_char_array(seqs[:4], seq_len=37).shape == (4, 37)
+    with pytest.raises(ValueError):
+        su.sequences_to_char_array(seqs[:4], seq_len=36)
