@@ -132,9 +132,10 @@ void flexs_model_destroy(flexs_model_t *m) {
     cudaFree(m->d_umma2_w);
     cudaFree(m->d_k9_tab);
     cudaFree(m->d_k9_ovf);
-    for (auto &w : m->k9_ws) { cudaFree(w.ptr); cudaFree(w.flag); }
+    for (auto &w : m->stream_ws) { cudaFree(w.ptr); cudaFree(w.flag); }
+    cudaFree(m->d_a20_w);
+    cudaFree(m->d_mlp_w);
     cudaFree(m->d_enum_tab);
-    cudaFree(m->d_flag);
     cudaFree(m->d_adam_m);
     cudaFree(m->d_adam_v);
     cudaFree(m->train_ws);
@@ -173,6 +174,8 @@ int flexs_model_set_weights(flexs_model_t *m, int member, const float *const *h_
     m->umma2_ready = false;
     m->k9_ready = false;
     m->enum_ready = false;
+    m->a20_ready = false;
+    m->mlp_ready = false;
     return FLEXS_OK;
 }
 
@@ -241,6 +244,7 @@ int flexs_model_forward_dev(flexs_model_t *m, const uint8_t *d_idx, int64_t n, f
     FX_REQUIRE(n >= 0, "negative n");
     if (n == 0) return FLEXS_OK;
     FX_REQUIRE(d_idx && d_out, "null buffer");
+    FX_CUDA(cudaSetDevice(m->device));  // weights, tables and workspaces live on the model's device
     cudaStream_t s = (cudaStream_t)stream;
     if (flexs_model_active_variant(m, n) == FLEXS_VARIANT_ENUM) return launch_enum(m, d_idx, n, d_out, s);
     return forward_direct(m, d_idx, n, d_out, s);
@@ -249,6 +253,26 @@ int flexs_model_forward_dev(flexs_model_t *m, const uint8_t *d_idx, int64_t n, f
 }  // extern "C"
 
 namespace fx {
+
+int stream_workspace(flexs_model *m, cudaStream_t s, size_t bytes, flexs_model::StreamWs **out) {
+    flexs_model::StreamWs *ws = nullptr;
+    for (auto &w : m->stream_ws) if (w.stream == s) ws = &w;
+    if (!ws) {
+        m->stream_ws.push_back({s, nullptr, 0, nullptr});
+        ws = &m->stream_ws.back();
+        FX_CUDA(cudaMalloc(&ws->flag, sizeof(int)));
+    }
+    if (ws->bytes < bytes) {
+        FX_CUDA(cudaStreamSynchronize(s));
+        if (ws->ptr) FX_CUDA(cudaFree(ws->ptr));
+        ws->ptr = nullptr; ws->bytes = 0;
+        FX_CUDA(cudaMalloc(&ws->ptr, bytes));
+        FX_CUDA(cudaMemsetAsync(ws->ptr, 0, bytes, s));  // slots past the end of a batch are read (never reported)
+        ws->bytes = bytes;
+    }
+    *out = ws;
+    return FLEXS_OK;
+}
 
 int forward_direct(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s) {
     if (m->kind == FLEXS_KIND_MLP) return launch_mlp(m, d_idx, n, d_out, s);
@@ -301,9 +325,11 @@ static int ensure_host_staging(flexs_model *m, int64_t n) {
     return FLEXS_OK;
 }
 
-int flexs_model_score_host(flexs_model_t *m, const char *h_chars, int64_t n, const char *alphabet,
+// `alphabet` != NULL: h_in holds n * L residue characters (flexs_model_score_host); NULL: n packed rows of
+// ceil(L * bits / 8) bytes (flexs_model_score_host_packed).  Same pipeline, a different first kernel.
+static int score_host_impl(flexs_model_t *m, const char *h_chars, int64_t n, const char *alphabet,
                            float *h_out, int64_t *bad_pos) {
-    FX_REQUIRE(m && alphabet, "null argument");
+    FX_REQUIRE(m, "null argument");
     FX_REQUIRE(n >= 0, "negative n");
     if (bad_pos) *bad_pos = -1;
     if (n == 0) return FLEXS_OK;
@@ -324,6 +350,8 @@ int flexs_model_score_host(flexs_model_t *m, const char *h_chars, int64_t n, con
         if (v == FLEXS_VARIANT_ENUM || v == FLEXS_VARIANT_UMMA_LUT) m->variant = v;
     }
     const int64_t L = m->L;
+    const bool packed = alphabet == nullptr;
+    const int64_t row_bytes = packed ? (L * bits_per_residue(m->A) + 7) / 8 : L;  // bytes per sequence on the wire
     // A chunk is a whole number of waves of the persistent kernels (sm_count groups of 128 sequences), close to
     // FLEXS_HOST_CHUNK_MB of residue characters: small enough that the first copy in and the last compute (which nothing
     // overlaps) are a small part of the call, large enough to amortise the per-chunk launches.
@@ -350,21 +378,28 @@ int flexs_model_score_host(flexs_model_t *m, const char *h_chars, int64_t n, con
         if (inflight_start[slot] < 0) return FLEXS_OK;
         FX_CUDA(cudaEventSynchronize(m->slot_done[slot]));
         const int64_t *st = m->h_status + 2 * slot;
-        if (st[0] != 0) first_bad = std::min(first_bad, inflight_start[slot] * L + st[1]);
+        if (st[0] != 0) first_bad = std::min(first_bad, inflight_start[slot] * L + st[1]);  // flat residue position
         if (!out_pinned) std::memcpy(h_out + inflight_start[slot], m->h_pin_out[slot], inflight_cnt[slot] * sizeof(float));
         inflight_start[slot] = -1;
         return FLEXS_OK;
     };
+    // Whatever way this call ends, no copy may still be in flight on the caller's buffers (or on a slot the next call
+    // reuses) when it returns: an early error return synchronises every slot stream first.
+    struct DrainAll {
+        flexs_model *m;
+        ~DrainAll() { for (int i = 0; i < flexs_model::NSLOT; ++i) if (m->streams[i]) cudaStreamSynchronize(m->streams[i]); }
+    } drain_all{m};
     for (int64_t c = 0; c < nchunks; ++c) {
         const int slot = (int)(c % flexs_model::NSLOT);
         rc = drain(slot);
         if (rc != FLEXS_OK) return rc;
         const int64_t start = c * chunk, cnt = std::min(chunk, n - start);
         cudaStream_t s = m->streams[slot];
-        const void *src = h_chars + start * L;
-        if (!in_pinned) { std::memcpy(m->h_pin_chars[slot], src, cnt * L); src = m->h_pin_chars[slot]; }
-        FX_CUDA(cudaMemcpyAsync(m->d_chars[slot], src, cnt * L, cudaMemcpyHostToDevice, s));
-        rc = launch_encode(m->d_chars[slot], cnt * L, alphabet, m->A, m->d_idx[slot], m->d_status + 2 * slot, s);
+        const void *src = h_chars + start * row_bytes;
+        if (!in_pinned) { std::memcpy(m->h_pin_chars[slot], src, cnt * row_bytes); src = m->h_pin_chars[slot]; }
+        FX_CUDA(cudaMemcpyAsync(m->d_chars[slot], src, cnt * row_bytes, cudaMemcpyHostToDevice, s));
+        rc = packed ? launch_unpack(m->d_chars[slot], cnt, m->L, m->A, m->d_idx[slot], m->d_status + 2 * slot, s)
+                    : launch_encode(m->d_chars[slot], cnt * L, alphabet, m->A, m->d_idx[slot], m->d_status + 2 * slot, s);
         if (rc != FLEXS_OK) return rc;
         m->launches += 1;
         rc = flexs_model_forward_dev(m, m->d_idx[slot], cnt, m->d_out[slot], s);
@@ -381,10 +416,45 @@ int flexs_model_score_host(flexs_model_t *m, const char *h_chars, int64_t n, con
     }
     if (first_bad != std::numeric_limits<int64_t>::max()) {
         if (bad_pos) *bad_pos = first_bad;
-        set_error("character outside the alphabet at flat position " + std::to_string(first_bad));
+        set_error((packed ? "packed residue value outside the alphabet at flat position "
+                          : "character outside the alphabet at flat position ") + std::to_string(first_bad));
         return FLEXS_EALPHABET;
     }
     return FLEXS_OK;
+}
+
+int flexs_model_score_host(flexs_model_t *m, const char *h_chars, int64_t n, const char *alphabet,
+                           float *h_out, int64_t *bad_pos) {
+    FX_REQUIRE(alphabet, "null alphabet");
+    return score_host_impl(m, h_chars, n, alphabet, h_out, bad_pos);
+}
+
+int flexs_model_score_host_packed(flexs_model_t *m, const uint8_t *h_packed, int64_t n, float *h_out, int64_t *bad_pos) {
+    return score_host_impl(m, reinterpret_cast<const char *>(h_packed), n, nullptr, h_out, bad_pos);
+}
+
+int flexs_bits_per_residue(int alphabet_size) {
+    FX_REQUIRE(alphabet_size >= 2 && alphabet_size <= 255, "alphabet_size must be in [2,255]");
+    return bits_per_residue(alphabet_size);
+}
+
+int64_t flexs_packed_row_bytes(int seq_len, int alphabet_size) {
+    if (seq_len < 0 || alphabet_size < 2 || alphabet_size > 255) return FLEXS_EINVAL;
+    return ((int64_t)seq_len * bits_per_residue(alphabet_size) + 7) / 8;
+}
+
+int flexs_unpack_dev(const uint8_t *d_packed, int64_t n, int seq_len, int alphabet_size, uint8_t *d_idx,
+                     int64_t *d_status, void *stream) {
+    FX_REQUIRE(alphabet_size >= 2 && alphabet_size <= 255 && seq_len >= 1 && n >= 0, "bad sizes");
+    FX_REQUIRE(d_status != nullptr, "d_status is null");
+    FX_REQUIRE(n == 0 || (d_packed && d_idx), "null buffer");
+    return launch_unpack(d_packed, n, seq_len, alphabet_size, d_idx, d_status, (cudaStream_t)stream);
+}
+
+int flexs_pack_dev(const uint8_t *d_idx, int64_t n, int seq_len, int alphabet_size, uint8_t *d_packed, void *stream) {
+    FX_REQUIRE(alphabet_size >= 2 && alphabet_size <= 255 && seq_len >= 1 && n >= 0, "bad sizes");
+    FX_REQUIRE(n == 0 || (d_packed && d_idx), "null buffer");
+    return launch_pack(d_idx, n, seq_len, alphabet_size, d_packed, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,519 @@
+// K1f (tcgen05; A = 20, k = 5, k3 = 19, F = 32, H <= 112) — the kernel of the protein shapes (GFP 237/238, AAV 90/735):
+// BASELINE configs[3] and [4].  Successor of cnn_umma.cu (phase-serial, 16-byte-misaligned taps, conv1 on shared-memory
+// tables), rebuilt on the architecture of cnn_k9.cu.
+//
+// Row mapping.  A CTA works on an *item* of 8 sequences ("streams") in lockstep.  MMA row 8c + b of a 128-row tile is
+// position c (of 16) of stream b, so an 8-row group is the same position of the 8 streams, a convolution tap is
+// +1 group = +1024 bytes (aligned to the SWIZZLE_128B atom: no operand fetch straddles a line, the flaw of the
+// 16-byte row shift of cnn_umma.cu), and an epilogue thread sees ONE stream: GlobalMaxPooling1D (cnn.py:48) is a running
+// fmaxf in registers.
+//
+// Rolling activation rings.  The streams advance through the sequence in chunks of 16 positions.  h1 (conv1 output) and
+// h2 (conv2 output) live in two shared-memory rings of 1 KB groups ([8 streams][hi 32 ch | lo 32 ch] fp16, K-major
+// SWIZZLE_128B: the canonical tcgen05 A operand).  A conv tile reads a window of 16 + taps - 1 consecutive groups that
+// starts at a chunk boundary; the head of each ring is mirrored behind its end so every window is contiguous.  Nothing
+// is ever recomputed (no halo): "same" padding (cnn.py:33-47; TF rule left = (k-1)/2) is the zero groups before position
+// 0 and after position T-1, which the epilogues write as zeros.
+//      h1 group v  <->  position v - 11      conv2 tile q reads h1 groups [16q, 16q + 20)   ring: 2 chunks + 4 mirrored
+//      h2 group u  <->  position u - 9       conv3 tile q reads h2 groups [16q, 16q + 34)   ring: 3 chunks + 18 mirrored
+//
+// Roles (14 warps, no CTA-wide barrier inside the loop; everything meets through mbarriers):
+//   0-3   conv1: h1 = relu(T012[x0,x1,x2] + T34[x3,x4]) — two 128-byte gathers per position from L2-resident tables
+//         (bias folded in; 20^3 and 20^2 entries, 1 MB + 50 KB per member), split to fp16 hi/lo, stored swizzled
+//   12    issues the conv2 MMAs  (5 taps x 2 K-steps x {A_hi x [W_hi|W_lo] (N=64), A_lo x W_hi (N=32)})
+//   4-7   conv2 epilogue: TMEM -> bias, ReLU, split -> h2 ring
+//   13    issues the conv3 MMAs  (19 taps; the last two wait for the third chunk of the window)
+//   8-11  conv3 epilogue: TMEM -> running max per stream; per item a staged merge -> pooled features
+// The pooled features leave as [32][128] fp32 tiles; the dense head is cnn_k9_dense_kernel (launch_dense_tiles).
+// The rings keep rolling across items, so the tensor pipe only drains at the end of the launch.
+//
+// Precision: the fp16 hi/lo split of cnn_umma.cu (three products per MAC, FP32 accumulation in TMEM); activations above
+// 60000/8 raise the per-stream flag and the gated FP32 kernel recomputes the batch.
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "common.cuh"
+#include "operand_prep.h"
+#include "umma2_layout.cuh"
+
+namespace {
+
+using namespace u2;
+
+constexpr int KC3 = 19, NA = 20;
+constexpr int NT = 448;                     // 14 warps
+constexpr int W_E2 = 4, W_E3 = 8, W_I2 = 12, W_I3 = 13;
+constexpr int R1C = 2, R1M = K - 1, R1G = R1C * 16 + R1M;      // h1 ring: 36 groups
+constexpr int R2C = 3, R2M = KC3 - 1, R2G = R2C * 16 + R2M;    // h2 ring: 66 groups
+constexpr int GS = DSLOTS;                  // sequences per feature tile of the dense kernel
+
+// operand blob of one member: [u2-compatible prefix: only the dense-head parts are filled] | UW2 | UW3 | scales | T012 | T34
+constexpr int A20_OFF_UW2 = OFF_TBIG, A20_OFF_UW3 = A20_OFF_UW2 + K * UWTAP, A20_OFF_SCAL = A20_OFF_UW3 + KC3 * UWTAP;
+constexpr int A20_OFF_T012 = (A20_OFF_SCAL + 16 + 255) / 256 * 256;
+constexpr int A20_OFF_T34 = A20_OFF_T012 + NA * NA * NA * F * 4;
+constexpr int A20_MEMBER_BYTES = (A20_OFF_T34 + NA * NA * F * 4 + 255) / 256 * 256;
+
+// shared memory map (the rings need 1024-byte alignment: SWIZZLE_128B atoms)
+constexpr int S_BAR = 0, S_TM = 512, S_B2S = 640, S_B3 = 768;
+constexpr int S_W2 = 1024, S_W3 = S_W2 + K * UWTAP, S_R1 = S_W3 + KC3 * UWTAP, S_R2 = S_R1 + R1G * 1024;
+constexpr int S_STAGE = S_R2 + R2G * 1024, S_IDX = S_STAGE + 2 * 4 * 256 * 4;
+static_assert(S_R1 % 1024 == 0 && S_R2 % 1024 == 0, "rings must be aligned to the swizzle atom");
+
+// mbarriers
+constexpr int B_IDX = 0, B_H1F = 2, B_H1E = 4, B_A2F = 6, B_A2E = 8, B_H2F = 10, B_H2E = 13, B_A3F = 16, B_A3E = 18, B_N = 20;
+
+struct A20Params {
+    const uint8_t *idx;        // [n][L] residues
+    float *feat;               // [tiles][32][128] pooled features (workspace)
+    const float *weights;      // this member's fp32 block (b2, b3)
+    const unsigned char *uw;   // this member's operand blob
+    int *overflow_flag;
+    int64_t n, n_items;
+    fx::CnnOffsets o;
+    int L, T, nt3, nc2, nlive2, nc1, idx_slot;
+};
+
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// A operand (both rings): K-major SWIZZLE_128B, 8-row groups of 1024 B (SBO); a K step of 16 channels is +32 B, the lo
+// half +64 B, a tap +1024 B.  hi word: SBO = 1024 B, version 1, layout type 2.
+constexpr uint32_t A_DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+
+// taps [J0, J1) of one 128-row tile: per tap 2 K steps x {A_hi x [W_hi|W_lo], A_lo x W_hi}.  All 32 lanes call it.
+template <int J0, int J1>
+__device__ __forceinline__ void issue_taps(uint32_t a_win_addr, uint32_t w_addr, uint32_t d_tmem) {
+    const uint32_t a0 = desc_lo(a_win_addr, 16), b0 = desc_lo(w_addr, UWKC);
+#pragma unroll
+    for (int j = J0; j < J1; ++j) {
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) {
+            const uint32_t a_hi = a0 + (((uint32_t)j * 1024u + (uint32_t)kp * 32u) >> 4);
+            const uint32_t a_lo = a_hi + (64u >> 4);
+            const uint32_t bd = b0 + (((uint32_t)j * UWTAP + (uint32_t)(2 * kp) * UWKC) >> 4);
+            umma_f16_elect(d_tmem, a_hi, A_DESC_HI, bd, DESC_HI, IDESC_N64, (j | kp) ? 1u : 0u);
+            umma_f16_elect(d_tmem, a_lo, A_DESC_HI, bd, DESC_HI, IDESC_N32, 1u);
+        }
+    }
+}
+
+__device__ __forceinline__ void issue_idx_load(const A20Params &p, uint8_t *dst, uint64_t *bar, int64_t item) {
+    const int64_t first = item * 8;
+    const int64_t cnt = min((int64_t)8, p.n - first);
+    const uintptr_t g0 = reinterpret_cast<uintptr_t>(p.idx) + (uintptr_t)(first * p.L);
+    const uintptr_t a0 = g0 & ~(uintptr_t)15;
+    const uintptr_t a1 = (g0 + (uintptr_t)(cnt * p.L) + 15) & ~(uintptr_t)15;
+    const uint32_t bytes = (uint32_t)(a1 - a0);
+    fxd::mbar_arrive_expect_tx(bar, bytes);
+    fxd::bulk_g2s(dst, reinterpret_cast<const void *>(a0), bytes, bar);
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4 &v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + S_BAR);
+    uint32_t *tmem_addr_s = reinterpret_cast<uint32_t *>(smem_raw + S_TM);
+    float *b2s = reinterpret_cast<float *>(smem_raw + S_B2S);
+    float *b3 = reinterpret_cast<float *>(smem_raw + S_B3);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int L = p.L, T = p.T;
+
+    if (tid == 0) {
+        fxd::mbar_init(&bar[B_IDX], 1); fxd::mbar_init(&bar[B_IDX + 1], 1);
+        for (int i = 0; i < 2; ++i) {
+            fxd::mbar_init(&bar[B_H1F + i], 4); fxd::mbar_init(&bar[B_H1E + i], 1);
+            fxd::mbar_init(&bar[B_A2F + i], 1); fxd::mbar_init(&bar[B_A2E + i], 4);
+            fxd::mbar_init(&bar[B_A3F + i], 1); fxd::mbar_init(&bar[B_A3E + i], 4);
+        }
+        for (int i = 0; i < 3; ++i) { fxd::mbar_init(&bar[B_H2F + i], 4); fxd::mbar_init(&bar[B_H2E + i], 1); }
+        fxd::fence_mbar_init();
+    }
+    if (wid == 0) tmem_alloc(tmem_addr_s, 256);  // conv2 accumulators at columns 0 / 64, conv3 at 128 / 192
+    const float *scal = reinterpret_cast<const float *>(p.uw + A20_OFF_SCAL);
+    const float inv2s = __ldg(scal), inv3 = __ldg(scal + 1);
+    for (int i = tid; i < F; i += NT) {
+        b2s[i] = __ldg(p.weights + p.o.b2 + i) * ASCALE;
+        b3[i] = __ldg(p.weights + p.o.b3 + i);
+    }
+    for (int i = tid; i < (K + KC3) * UWTAP / 16; i += NT)
+        reinterpret_cast<uint4 *>(smem_raw + S_W2)[i] = __ldg(reinterpret_cast<const uint4 *>(p.uw + A20_OFF_UW2) + i);
+    for (int i = tid; i < (R1G + R2G) * 1024 / 16; i += NT)
+        reinterpret_cast<uint4 *>(smem_raw + S_R1)[i] = make_uint4(0, 0, 0, 0);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_addr_s;
+    const uint32_t r1_addr = fxd::smem_u32(smem_raw + S_R1), r2_addr = fxd::smem_u32(smem_raw + S_R2);
+    const uint32_t w2_addr = fxd::smem_u32(smem_raw + S_W2), w3_addr = fxd::smem_u32(smem_raw + S_W3);
+    const int64_t stride = gridDim.x;
+    float xmax = 0.f;  // largest activation written as fp16 (range guard)
+
+    if (wid < W_E2) {
+        // =========================== conv1 producers ===========================
+        // lane = 4 b + cc moves 8 channels (cc) of stream b: the 4 lanes of a stream read one whole 128-byte table row,
+        // the warp writes the 32 16-byte chunks of one group to 8 different bank groups, 4 rows each (4 wavefronts).
+        const int b = lane >> 2, cc = lane & 3;
+        const float *t012 = reinterpret_cast<const float *>(p.uw + A20_OFF_T012) + cc * 8;
+        const float *t34 = reinterpret_cast<const float *>(p.uw + A20_OFF_T34) + cc * 8;
+        const uint32_t row_off = (uint32_t)(b * 128), hi_off = (uint32_t)((cc ^ b) << 4), lo_off = (uint32_t)(((4 + cc) ^ b) << 4);
+        if (tid == 0 && (int64_t)blockIdx.x < p.n_items) issue_idx_load(p, smem_raw + S_IDX, &bar[B_IDX], blockIdx.x);
+        uint32_t g1 = 0, itc = 0;
+        for (int64_t item = blockIdx.x; item < p.n_items; item += stride, ++itc) {
+            // every producer is done with the previous item: its residue buffer (the next item's) is free
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (tid == 0 && item + stride < p.n_items)
+                issue_idx_load(p, smem_raw + S_IDX + ((itc + 1) & 1) * p.idx_slot, &bar[B_IDX + ((itc + 1) & 1)], item + stride);
+            fxd::mbar_wait(&bar[B_IDX + (itc & 1)], (itc >> 1) & 1);
+            const int nvalid = (int)min((int64_t)8, p.n - item * 8);
+            const uint8_t *sidx = smem_raw + S_IDX + (itc & 1) * p.idx_slot +
+                                  ((reinterpret_cast<uintptr_t>(p.idx) + (uintptr_t)(item * 8 * L)) & 15) + (b < nvalid ? b : 0) * L;
+            for (int qc = 0; qc < p.nc1; ++qc, ++g1) {
+                const uint32_t slot = g1 & 1u;
+                if (g1 >= 2) fxd::mbar_wait(&bar[B_H1E + slot], ((g1 >> 1) - 1) & 1);
+                float4 ta[4][2], tb[4][2];
+                bool ok[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int t = 16 * qc + wid + 4 * i - 11;
+                    ok[i] = b < nvalid && t >= 0 && t < T;
+                    if (ok[i]) {
+                        const uint8_t *ip = sidx + t;
+                        const uint32_t x0 = min((uint32_t)ip[0], 19u), x1 = min((uint32_t)ip[1], 19u), x2 = min((uint32_t)ip[2], 19u);
+                        const uint32_t x3 = min((uint32_t)ip[3], 19u), x4 = min((uint32_t)ip[4], 19u);
+                        const float4 *pa = reinterpret_cast<const float4 *>(t012 + (size_t)((x0 * NA + x1) * NA + x2) * F);
+                        const float4 *pb = reinterpret_cast<const float4 *>(t34 + (size_t)(x3 * NA + x4) * F);
+                        ta[i][0] = __ldg(pa); ta[i][1] = __ldg(pa + 1);
+                        tb[i][0] = __ldg(pb); tb[i][1] = __ldg(pb + 1);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint4 hi4 = make_uint4(0, 0, 0, 0), lo4 = make_uint4(0, 0, 0, 0);
+                    if (ok[i]) {
+                        const float x[8] = {fmaxf(ta[i][0].x + tb[i][0].x, 0.f), fmaxf(ta[i][0].y + tb[i][0].y, 0.f),
+                                            fmaxf(ta[i][0].z + tb[i][0].z, 0.f), fmaxf(ta[i][0].w + tb[i][0].w, 0.f),
+                                            fmaxf(ta[i][1].x + tb[i][1].x, 0.f), fmaxf(ta[i][1].y + tb[i][1].y, 0.f),
+                                            fmaxf(ta[i][1].z + tb[i][1].z, 0.f), fmaxf(ta[i][1].w + tb[i][1].w, 0.f)};
+                        split8(x, hi4, lo4, xmax);
+                    }
+                    const uint32_t gr = slot * 16u + (uint32_t)(wid + 4 * i);
+                    const uint32_t row = r1_addr + gr * 1024u + row_off;
+                    st_shared_v4(row + hi_off, hi4);
+                    st_shared_v4(row + lo_off, lo4);
+                    if (gr < (uint32_t)R1M) {  // head of the ring, mirrored behind its end
+                        st_shared_v4(row + R1C * 16 * 1024 + hi_off, hi4);
+                        st_shared_v4(row + R1C * 16 * 1024 + lo_off, lo4);
+                    }
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar[B_H1F + slot]);
+            }
+        }
+    } else if (wid < W_E3) {
+        // =========================== conv2 epilogue: accumulator -> h2 ring ===========================
+        // warp lq owns TMEM lanes 32 lq .. 32 lq + 31 = positions 4 lq .. 4 lq + 3 of the chunk, all 8 streams
+        const int lq = wid & 3, c = 4 * lq + (lane >> 3), b = lane & 7;
+        const uint32_t tlane = tmem_base + ((uint32_t)(lq * 32) << 16);
+        uint32_t g2 = 0, a2 = 0;
+        for (int64_t item = blockIdx.x; item < p.n_items; item += stride) {
+            const int nvalid = (int)min((int64_t)8, p.n - item * 8);
+            for (int qc = 0; qc < p.nc2; ++qc, ++g2) {
+                const uint32_t slot = g2 % 3u;
+                uint4 hi4[4], lo4[4];
+                if (qc < p.nlive2) {
+                    const uint32_t a = a2 & 1u;
+                    fxd::mbar_wait(&bar[B_A2F + a], (a2 >> 1) & 1);
+                    tc_fence_after();
+                    const int pos = 16 * qc + c - 9;
+                    const bool valid = b < nvalid && pos >= 0 && pos < T;
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        uint32_t v[16], v2[16];
+                        tmem_ld16_nowait(tlane + a * 64u + (uint32_t)(hf * 16), v);
+                        tmem_ld16_nowait(tlane + a * 64u + 32u + (uint32_t)(hf * 16), v2);
+                        tmem_ld_wait();
+                        if (hf == 1) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&bar[B_A2E + a]);  // the accumulator is in registers
+                        }
+#pragma unroll
+                        for (int h8 = 0; h8 < 2; ++h8) {
+                            float x[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int col = h8 * 8 + i;
+                                const float acc = __uint_as_float(v[col]) + __uint_as_float(v2[col]);
+                                x[i] = valid ? fmaxf(fmaf(acc, inv2s, b2s[hf * 16 + col]), 0.f) : 0.f;
+                            }
+                            split8(x, hi4[hf * 2 + h8], lo4[hf * 2 + h8], xmax);
+                        }
+                    }
+                    ++a2;
+                } else {
+                    // a chunk past the end of the sequence: the right-hand "same" padding of conv3
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { hi4[j] = make_uint4(0, 0, 0, 0); lo4[j] = make_uint4(0, 0, 0, 0); }
+                }
+                if (g2 >= 3) fxd::mbar_wait(&bar[B_H2E + slot], ((g2 / 3u) - 1) & 1);  // the conv3 tiles reading this slot retired
+                const uint32_t gr = slot * 16u + (uint32_t)c;
+                const uint32_t row = r2_addr + gr * 1024u + (uint32_t)(b * 128);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    st_shared_v4(row + (uint32_t)((j ^ b) << 4), hi4[j]);
+                    st_shared_v4(row + (uint32_t)(((4 + j) ^ b) << 4), lo4[j]);
+                }
+                if (gr < (uint32_t)R2M) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        st_shared_v4(row + R2C * 16 * 1024 + (uint32_t)((j ^ b) << 4), hi4[j]);
+                        st_shared_v4(row + R2C * 16 * 1024 + (uint32_t)(((4 + j) ^ b) << 4), lo4[j]);
+                    }
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar[B_H2F + slot]);
+            }
+        }
+    } else if (wid < W_I2) {
+        // =========================== conv3 epilogue: running max per stream ===========================
+        // max_t relu(a_t * inv3 + b) == relu(max_t(a_t) * inv3 + b) (inv3 > 0): per tile one add of the two accumulator
+        // halves and one fmaxf per filter; scale, bias and ReLU wait for the item's end.
+        const int lq = wid & 3, c = 4 * lq + (lane >> 3), b = lane & 7;
+        const uint32_t tlane = tmem_base + ((uint32_t)(lq * 32) << 16) + 128u;
+        const bool up8 = (lane & 8) != 0, up16 = (lane & 16) != 0;
+        float *stage_s = reinterpret_cast<float *>(smem_raw + S_STAGE);  // [2 buffers][4 warps][4 fg][8 b][8 f]
+        uint32_t t3 = 0, nflush = 0;
+        float mx[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mx[j] = -INFINITY;
+        for (int64_t item = blockIdx.x; item < p.n_items; item += stride) {
+            const int nvalid = (int)min((int64_t)8, p.n - item * 8);
+            for (int q = 0; q < p.nt3; ++q, ++t3) {
+                const uint32_t a = t3 & 1u;
+                fxd::mbar_wait(&bar[B_A3F + a], (t3 >> 1) & 1);
+                tc_fence_after();
+                const bool valid = 16 * q + c < T;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t v[16], v2[16];
+                    tmem_ld16_nowait(tlane + a * 64u + (uint32_t)(hf * 16), v);
+                    tmem_ld16_nowait(tlane + a * 64u + 32u + (uint32_t)(hf * 16), v2);
+                    tmem_ld_wait();
+                    if (hf == 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bar[B_A3E + a]);
+                    }
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            mx[hf * 16 + j] = fmaxf(mx[hf * 16 + j], __uint_as_float(v[j]) + __uint_as_float(v2[j]));
+                    }
+                }
+            }
+            // GlobalMaxPooling1D: the 4 lanes of stream b merge with a halving butterfly (after the xor-8 step a lane keeps
+            // filters 16 (lane bit 3) + 0..15, after the xor-16 step 8 of those), park them in this warp's 256-float slot
+            // [fg][b][8]; the 4 warps meet in the double-buffered staging area; warp lq then reduces filters 8 lq .. 8 lq + 7.
+            float *stg = stage_s + (int)(nflush & 1) * 4 * 256;
+            {
+                float k16[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float send = up8 ? mx[j] : mx[j + 16], keep = up8 ? mx[j + 16] : mx[j];
+                    k16[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+                }
+                float k8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float send = up16 ? k16[j] : k16[j + 8], keep = up16 ? k16[j + 8] : k16[j];
+                    k8[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) mx[j] = -INFINITY;
+                const int fg = (up8 ? 2 : 0) + (up16 ? 1 : 0);
+                float4 *wr = reinterpret_cast<float4 *>(stg + lq * 256 + (fg * 8 + b) * 8);
+                wr[0] = make_float4(k8[0], k8[1], k8[2], k8[3]);
+                wr[1] = make_float4(k8[4], k8[5], k8[6], k8[7]);
+            }
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            const int pr = lane >> 3, f = 8 * lq + 2 * pr;
+            const float *rd = stg + (lq * 8 + b) * 8 + 2 * pr;
+            float2 t = *reinterpret_cast<const float2 *>(rd);
+#pragma unroll
+            for (int w4 = 1; w4 < 4; ++w4) {
+                const float2 o2 = *reinterpret_cast<const float2 *>(rd + w4 * 256);
+                t.x = fmaxf(t.x, o2.x); t.y = fmaxf(t.y, o2.y);
+            }
+            if (b < nvalid) {
+                const int64_t seq = item * 8 + b;
+                float *dst = p.feat + (size_t)(seq >> 7) * (F * GS) + (size_t)(seq & (GS - 1));
+                dst[(size_t)f * GS] = fmaxf(fmaf(t.x, inv3, b3[f]), 0.f);
+                dst[(size_t)(f + 1) * GS] = fmaxf(fmaf(t.y, inv3, b3[f + 1]), 0.f);
+            }
+            ++nflush;
+        }
+    } else if (wid == W_I2) {
+        // =========================== conv2 MMA issue ===========================
+        uint32_t g1 = 0, a2 = 0;
+        for (int64_t item = blockIdx.x; item < p.n_items; item += stride) {
+            for (int qc = 0; qc < p.nlive2; ++qc, ++g1, ++a2) {
+                const uint32_t s0 = g1 & 1u, a = a2 & 1u;
+                fxd::mbar_wait(&bar[B_H1F + s0], (g1 >> 1) & 1);
+                fxd::mbar_wait(&bar[B_H1F + (s0 ^ 1u)], ((g1 + 1) >> 1) & 1);  // the window ends 4 groups into the next chunk
+                if (a2 >= 2) fxd::mbar_wait(&bar[B_A2E + a], ((a2 >> 1) - 1) & 1);
+                tc_fence_after();
+                issue_taps<0, K>(r1_addr + s0 * 16u * 1024u, w2_addr, tmem_base + a * 64u);
+                umma_commit_elect(&bar[B_A2F + a]);
+                umma_commit_elect(&bar[B_H1E + s0]);
+            }
+            // the item's last h1 chunk is only ever the 4-group tail of the last window: release it as well
+            umma_commit_elect(&bar[B_H1E + (g1 & 1u)]);
+            ++g1;
+        }
+    } else {
+        // =========================== conv3 MMA issue ===========================
+        uint32_t g2 = 0, t3 = 0;
+        for (int64_t item = blockIdx.x; item < p.n_items; item += stride) {
+            for (int q = 0; q < p.nt3; ++q, ++t3) {
+                const uint32_t G = g2 + (uint32_t)q, s0 = G % 3u, a = t3 & 1u;
+                fxd::mbar_wait(&bar[B_H2F + s0], (G / 3u) & 1);
+                fxd::mbar_wait(&bar[B_H2F + (G + 1) % 3u], ((G + 1) / 3u) & 1);
+                if (t3 >= 2) fxd::mbar_wait(&bar[B_A3E + a], ((t3 >> 1) - 1) & 1);
+                tc_fence_after();
+                const uint32_t win = r2_addr + s0 * 16u * 1024u, d = tmem_base + 128u + a * 64u;
+                issue_taps<0, KC3 - 2>(win, w3_addr, d);
+                // taps 17 and 18 reach into the third chunk of the window (its first two groups)
+                fxd::mbar_wait(&bar[B_H2F + (G + 2) % 3u], ((G + 2) / 3u) & 1);
+                tc_fence_after();
+                issue_taps<KC3 - 2, KC3>(win, w3_addr, d);
+                umma_commit_elect(&bar[B_A3F + a]);
+                umma_commit_elect(&bar[B_H2E + s0]);
+            }
+            // the two trailing chunks of the item were never the first chunk of a window: release them here
+            umma_commit_elect(&bar[B_H2E + (g2 + (uint32_t)p.nt3) % 3u]);
+            umma_commit_elect(&bar[B_H2E + (g2 + (uint32_t)p.nt3 + 1) % 3u]);
+            g2 += (uint32_t)p.nc2;
+        }
+    }
+    if (xmax > 60000.f) atomicExch(p.overflow_flag, 1);
+    tc_fence_before();
+    __syncthreads();
+    if (wid == 0) tmem_dealloc(tmem_base, 256);
+}
+
+static bool plan(const flexs_model *m, A20Params &p) {
+    p.o = fx::cnn_offsets(m);
+    p.L = m->L;
+    p.T = m->L - m->K + 1;
+    p.nt3 = (p.T + 15) / 16;            // conv3 tiles per item
+    p.nc2 = p.nt3 + 2;                  // h2 chunks per item: the last window ends 2 groups into chunk nt3 + 1
+    p.nlive2 = (p.T + 8) / 16 + 1;      // h2 chunks with a position inside the sequence (the others are zero padding)
+    p.nc1 = p.nlive2 + 1;               // h1 chunks per item: a conv2 window ends 4 groups into the next chunk
+    p.idx_slot = (int)align_up((size_t)8 * m->L + 32, 16);
+    return (int64_t)S_IDX + 2 * p.idx_slot + 1024 <= m->max_smem_optin;
+}
+
+static int prepare(flexs_model *m) {
+    if (m->a20_ready) return FLEXS_OK;
+    const fx::CnnOffsets o = fx::cnn_offsets(m);
+    std::vector<float> host((size_t)m->member_floats * m->M);
+    FX_CUDA(cudaSetDevice(m->device));
+    FX_CUDA(cudaMemcpy(host.data(), m->d_weights, host.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    std::vector<unsigned char> blob((size_t)A20_MEMBER_BYTES * m->M, 0);
+    m->umma_weights_ok = true;
+    for (int mem = 0; mem < m->M; ++mem) {
+        const float *w = host.data() + (size_t)mem * m->member_floats;
+        unsigned char *dst = blob.data() + (size_t)mem * A20_MEMBER_BYTES;
+        const float inv2 = prep::fill_conv_planes(w + o.w2, K, dst + A20_OFF_UW2, &m->umma_weights_ok);
+        const float inv3 = prep::fill_conv_planes(w + o.w3, KC3, dst + A20_OFF_UW3, &m->umma_weights_ok);
+        float *scal = reinterpret_cast<float *>(dst + A20_OFF_SCAL);
+        scal[0] = inv2 * ASCALE;  // the conv2 epilogue emits activations pre-scaled by ASCALE
+        scal[1] = inv3;
+        prep::fill_dense_head(w, o, m->H, dst, &m->umma_weights_ok);
+        // conv1 (cnn.py:25-32) as two gathers: T012[x0,x1,x2] = b1 + W1[0,x0] + W1[1,x1] + W1[2,x2], T34[x3,x4] =
+        // W1[3,x3] + W1[4,x4], both pre-scaled by ASCALE (a power of two: exact)
+        const float *w1 = w + o.w1, *b1 = w + o.b1;  // w1 (k, A, F)
+        float *t012 = reinterpret_cast<float *>(dst + A20_OFF_T012), *t34 = reinterpret_cast<float *>(dst + A20_OFF_T34);
+        for (int x0 = 0; x0 < NA; ++x0)
+            for (int x1 = 0; x1 < NA; ++x1)
+                for (int x2 = 0; x2 < NA; ++x2) {
+                    float *e = t012 + (size_t)((x0 * NA + x1) * NA + x2) * F;
+                    for (int f = 0; f < F; ++f) {
+                        const float v = ((w1[(0 * NA + x0) * F + f] + w1[(1 * NA + x1) * F + f]) + w1[(2 * NA + x2) * F + f]) + b1[f];
+                        if (!std::isfinite(v)) m->umma_weights_ok = false;
+                        e[f] = v * ASCALE;
+                    }
+                }
+        for (int x3 = 0; x3 < NA; ++x3)
+            for (int x4 = 0; x4 < NA; ++x4)
+                for (int f = 0; f < F; ++f) {
+                    const float v = w1[(3 * NA + x3) * F + f] + w1[(4 * NA + x4) * F + f];
+                    if (!std::isfinite(v)) m->umma_weights_ok = false;
+                    t34[(size_t)(x3 * NA + x4) * F + f] = v * ASCALE;
+                }
+    }
+    if (!m->d_a20_w) FX_CUDA(cudaMalloc(&m->d_a20_w, blob.size()));
+    FX_CUDA(cudaMemcpy(m->d_a20_w, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    m->a20_ready = true;
+    return FLEXS_OK;
+}
+
+}  // namespace
+
+namespace fx {
+
+bool cnn_a20_supported(const flexs_model *m) {
+    if (m->kind != FLEXS_KIND_CNN || m->F != 32 || m->K != 5 || m->A != NA || m->H > DH) return false;
+    if (!cnn_tiled_supported(m)) return false;  // the fp16-overflow fall-back path
+    A20Params p;
+    return plan(m, p);
+}
+
+int launch_cnn_a20(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s) {
+    A20Params p;
+    FX_REQUIRE(cnn_a20_supported(m) && plan(m, p), "shape not supported by the A = 20 tcgen05 kernel");
+    int rc = prepare(m);
+    if (rc != FLEXS_OK) return rc;
+    if (!m->umma_weights_ok) return launch_cnn_tiled(m, d_idx, n, d_out, s);  // non-finite weights: fp32 path
+    // feature workspace of this stream: one [32][128] fp32 tile per 128 sequences of a chunk (<= 136 MB)
+    const int64_t chunk_tiles = (int64_t)m->sm_count * 56;
+    const int64_t n_tiles = (n + GS - 1) / GS;
+    flexs_model::StreamWs *ws = nullptr;
+    rc = stream_workspace(m, s, (size_t)std::min(n_tiles, chunk_tiles) * F * GS * sizeof(float), &ws);
+    if (rc != FLEXS_OK) return rc;
+    p.feat = reinterpret_cast<float *>(ws->ptr);
+    p.overflow_flag = ws->flag;
+    const size_t smem = (size_t)S_IDX + 2 * p.idx_slot + 1024;
+    FX_CUDA(cudaFuncSetAttribute(cnn_a20_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FX_CUDA(cudaMemsetAsync(ws->flag, 0, sizeof(int), s));
+    for (int64_t t0 = 0; t0 < n_tiles; t0 += chunk_tiles) {
+        const int64_t first = t0 * GS, cnt = std::min(n - first, chunk_tiles * GS);
+        p.idx = d_idx + first * m->L;
+        p.n = cnt;
+        p.n_items = (cnt + 7) / 8;
+        const int grid = (int)std::min<int64_t>(p.n_items, m->sm_count);
+        for (int mem = 0; mem < m->M; ++mem) {
+            p.weights = m->d_weights + (int64_t)mem * m->member_floats;
+            p.uw = reinterpret_cast<const unsigned char *>(m->d_a20_w) + (size_t)mem * A20_MEMBER_BYTES;
+            cnn_a20_kernel<<<grid, NT, smem, s>>>(p);
+            FX_CUDA(cudaGetLastError());
+            m->launches += 1;
+            rc = launch_dense_tiles(m, p.feat, d_out + first, p.uw, ws->flag, cnt, mem, s);
+            if (rc != FLEXS_OK) return rc;
+        }
+    }
+    // fp16 range guard: the gated FFMA kernel recomputes the batch iff the flag was raised
+    return launch_cnn_tiled_gated(m, d_idx, n, d_out, ws->flag, s);
+}
+
+}  // namespace fx

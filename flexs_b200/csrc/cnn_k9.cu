@@ -592,6 +592,19 @@ bool cnn_k9_supported(const flexs_model *m) {
     return plan(m, p);
 }
 
+int launch_dense_tiles(flexs_model *m, const float *feat, float *out, const unsigned char *uw, int *flag, int64_t n,
+                       int mem, cudaStream_t s) {
+    const int64_t n_groups = (n + GS - 1) / GS;
+    FX_REQUIRE(m->H <= DH && D_SMEM <= m->max_smem_optin, "dense-head kernel needs H <= 112");
+    FX_CUDA(cudaFuncSetAttribute(cnn_k9_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM));
+    DenseParams dp{feat, out, uw, flag, n, n_groups, mem, m->M};
+    const int grid = (int)std::min<int64_t>(n_groups, m->sm_count);
+    cnn_k9_dense_kernel<<<grid, DNT, D_SMEM, s>>>(dp);
+    FX_CUDA(cudaGetLastError());
+    m->launches += 1;
+    return FLEXS_OK;
+}
+
 int launch_cnn_k9(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s) {
     K9Params p;
     FX_REQUIRE(cnn_k9_supported(m) && plan(m, p), "shape not supported by the table + tcgen05 kernel");
@@ -603,20 +616,9 @@ int launch_cnn_k9(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out,
     const int64_t chunk_groups = (int64_t)m->sm_count * 56;
     const int64_t n_groups = (n + GS - 1) / GS;
     const size_t ws_bytes = (size_t)std::min(n_groups, chunk_groups) * F * GS * sizeof(float);
-    flexs_model::K9Workspace *ws = nullptr;
-    for (auto &w : m->k9_ws) if (w.stream == s) ws = &w;
-    if (!ws) {
-        m->k9_ws.push_back({s, nullptr, 0, nullptr});
-        ws = &m->k9_ws.back();
-        FX_CUDA(cudaMalloc(&ws->flag, sizeof(int)));
-    }
-    if (ws->bytes < ws_bytes) {
-        FX_CUDA(cudaStreamSynchronize(s));
-        if (ws->ptr) FX_CUDA(cudaFree(ws->ptr));
-        ws->ptr = nullptr; ws->bytes = 0;
-        FX_CUDA(cudaMalloc(&ws->ptr, ws_bytes));
-        ws->bytes = ws_bytes;
-    }
+    flexs_model::StreamWs *ws = nullptr;
+    rc = stream_workspace(m, s, ws_bytes, &ws);
+    if (rc != FLEXS_OK) return rc;
     static const bool prof = std::getenv("FLEXS_UMMA_PROF") && std::getenv("FLEXS_UMMA_PROF")[0] == '1';
     p.dbg = std::getenv("FLEXS_UMMA_DBG") ? std::atoi(std::getenv("FLEXS_UMMA_DBG")) : 0;
     p.feat = reinterpret_cast<float *>(ws->ptr);

@@ -546,7 +546,6 @@ int prepare_cnn_umma(flexs_model *m) {
     }
     FX_CUDA(cudaSetDevice(m->device));
     if (!m->d_umma_w) FX_CUDA(cudaMalloc(&m->d_umma_w, blob.size()));
-    if (!m->d_flag) FX_CUDA(cudaMalloc(&m->d_flag, sizeof(int)));
     FX_CUDA(cudaMemcpy(m->d_umma_w, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     m->umma_ready = true;
     return FLEXS_OK;
@@ -556,6 +555,7 @@ int launch_cnn_umma(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_ou
     // A = 4 shapes run the pipelined kernel of cnn_umma2.cu; this file's kernel serves k3 = 19
     static const bool force_v1 = std::getenv("FLEXS_UMMA_V1") && std::getenv("FLEXS_UMMA_V1")[0] == '1';
     if (!force_v1 && cnn_umma2_supported(m)) return launch_cnn_umma2(m, d_idx, n, d_out, s);
+    if (!force_v1 && cnn_a20_supported(m)) return launch_cnn_a20(m, d_idx, n, d_out, s);  // k3 = 19: cnn_a20.cu
     UmmaParams p;
     FX_REQUIRE(cnn_umma_supported(m) && plan(m, p), "shape not supported by the UMMA kernel");
     int rc = prepare_cnn_umma(m);
@@ -563,7 +563,10 @@ int launch_cnn_umma(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_ou
     if (!m->umma_weights_ok) return launch_cnn_tiled(m, d_idx, n, d_out, s);  // non-finite weights: fp32 path
     p.idx = d_idx; p.out = d_out; p.weights = m->d_weights; p.n = n;
     p.uw = reinterpret_cast<const unsigned char *>(m->d_umma_w);
-    p.overflow_flag = m->d_flag;
+    flexs_model::StreamWs *ws = nullptr;  // the fp16-overflow flag is per stream: chunks of score_host run concurrently
+    rc = stream_workspace(m, s, 0, &ws);
+    if (rc != FLEXS_OK) return rc;
+    p.overflow_flag = ws->flag;
     p.n_items = (n + p.S - 1) / p.S;
     static const bool swap = std::getenv("FLEXS_UMMA_SWAP") && std::getenv("FLEXS_UMMA_SWAP")[0] == '1';
     p.swap_lbo_sbo = swap ? 1 : 0;
@@ -575,7 +578,7 @@ int launch_cnn_umma(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_ou
         FX_CUDA(cudaMalloc(&p.prof, (size_t)grid * 8 * sizeof(long long)));
         FX_CUDA(cudaMemset(p.prof, 0, (size_t)grid * 8 * sizeof(long long)));
     }
-    FX_CUDA(cudaMemsetAsync(m->d_flag, 0, sizeof(int), s));
+    FX_CUDA(cudaMemsetAsync(ws->flag, 0, sizeof(int), s));
     FX_CUDA(cudaFuncSetAttribute(cnn_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cnn_umma_kernel<<<grid, NT, smem, s>>>(p);
     FX_CUDA(cudaGetLastError());
@@ -593,7 +596,7 @@ int launch_cnn_umma(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_ou
                 (long long)n, grid, a[6], a[0] / ch, a[1] / ch, a[2] / ch, a[3] / ch, a[4] / ch, a[5] / ch);
     }
     // fp16 range guard: the gated FFMA kernel recomputes the batch iff the flag was raised
-    return launch_cnn_tiled_gated(m, d_idx, n, d_out, m->d_flag, s);
+    return launch_cnn_tiled_gated(m, d_idx, n, d_out, ws->flag, s);
 }
 
 }  // namespace fx

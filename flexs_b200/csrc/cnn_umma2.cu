@@ -29,6 +29,7 @@
 
 #include "common.cuh"
 #include "dense_head.cuh"
+#include "operand_prep.h"
 #include "umma2_layout.cuh"
 
 namespace {
@@ -527,32 +528,8 @@ static int prepare(flexs_model *m, const U2Params &p) {
         const float *w = host.data() + (size_t)mem * m->member_floats;
         unsigned char *dst = blob.data() + (size_t)mem * UW_MEMBER_BYTES;
         float inv[2];
-        for (int layer = 0; layer < 2; ++layer) {
-            const int taps = layer == 0 ? K : K3;
-            const float *src = w + (layer == 0 ? p.o.w2 : p.o.w3);  // (taps, in g, out f)
-            float mx = 0.f;
-            for (int i = 0; i < taps * F * F; ++i) {
-                if (!std::isfinite(src[i])) m->umma_weights_ok = false;
-                mx = std::max(mx, std::fabs(src[i]));
-            }
-            int e = 0;
-            if (mx > 0.f && std::isfinite(mx)) e = 14 - (int)std::floor(std::log2(mx));  // scaled max in [2^14, 2^15)
-            e = std::max(-24, std::min(e, 40));
-            const float scale = std::ldexp(1.f, e);
-            inv[layer] = std::ldexp(1.f, -e) / ASCALE;
-            __half *planes = reinterpret_cast<__half *>(dst + (layer == 0 ? 0 : OFF_UW3));
-            for (int j = 0; j < taps; ++j)
-                for (int g = 0; g < F; ++g)
-                    for (int f = 0; f < F; ++f) {
-                        const float v = src[((size_t)j * F + g) * F + f] * scale;
-                        const __half hi = __float2half_rn(v);
-                        const __half lo = __float2half_rn(v - __half2float(hi));
-                        // [tap][chunk g/8][n: 0-31 hi, 32-63 lo][g%8]
-                        const size_t base = (size_t)j * (UWTAP / 2) + (size_t)(g >> 3) * (UWKC / 2) + (g & 7);
-                        planes[base + (size_t)f * 8] = hi;
-                        planes[base + (size_t)(32 + f) * 8] = lo;
-                    }
-        }
+        inv[0] = prep::fill_conv_planes(w + p.o.w2, K, dst, &m->umma_weights_ok);
+        inv[1] = prep::fill_conv_planes(w + p.o.w3, K3, dst + OFF_UW3, &m->umma_weights_ok);
         // conv1 gather tables for A = 4: T012[a0,a1,a2] (with bias) and T34[a3,a4], scaled by ASCALE
         const float *w1 = w + p.o.w1, *b1 = w + p.o.b1;  // w1 (k, A, F)
         float *t012 = reinterpret_cast<float *>(dst + OFF_T012), *t34 = reinterpret_cast<float *>(dst + OFF_T34);
@@ -587,46 +564,10 @@ static int prepare(flexs_model *m, const U2Params &p) {
         tail[1] = inv[1];
         // dense head operands (used when H <= 112): Wd1 (F,H) and Wd2 (H,H) as [k chunk][n hi|lo][8 k] planes
         const int H = p.d.H;
-        if (H <= DH) {
-            float dinv[2];
-            for (int layer = 0; layer < 2; ++layer) {
-                const int kin = layer == 0 ? F : H;
-                const float *src = w + (layer == 0 ? p.o.wd1 : p.o.wd2);  // (in, out)
-                float mx = 0.f;
-                for (int i = 0; i < kin * H; ++i) {
-                    if (!std::isfinite(src[i])) m->umma_weights_ok = false;
-                    mx = std::max(mx, std::fabs(src[i]));
-                }
-                int e = 0;
-                if (mx > 0.f && std::isfinite(mx)) e = 14 - (int)std::floor(std::log2(mx));
-                e = std::max(-24, std::min(e, 40));
-                const float scale = std::ldexp(1.f, e);
-                dinv[layer] = std::ldexp(1.f, -e) / ASCALE;
-                __half *planes = reinterpret_cast<__half *>(dst + (layer == 0 ? OFF_DB1 : OFF_DB2));
-                for (int k = 0; k < kin; ++k)
-                    for (int o = 0; o < H; ++o) {
-                        const float v = src[(size_t)k * H + o] * scale;
-                        const __half hi = __float2half_rn(v);
-                        const __half lo = __float2half_rn(v - __half2float(hi));
-                        const size_t base = (size_t)(k >> 3) * (DBK / 2) + (k & 7);
-                        planes[base + (size_t)o * 8] = hi;
-                        planes[base + (size_t)(DH + o) * 8] = lo;
-                    }
-            }
-            float *dv = reinterpret_cast<float *>(dst + OFF_DV);
-            for (int o = 0; o < H; ++o) {
-                dv[o] = w[p.o.bd1 + o] * ASCALE;
-                dv[DH + o] = w[p.o.bd2 + o];
-                dv[2 * DH + o] = w[p.o.wd3 + o];
-            }
-            dv[3 * DH] = dinv[0] * ASCALE;  // layer-1 epilogue emits activations pre-scaled by ASCALE
-            dv[3 * DH + 1] = dinv[1];
-            dv[3 * DH + 2] = w[p.o.bd3];
-        }
+        if (H <= DH) prep::fill_dense_head(w, p.o, H, dst, &m->umma_weights_ok);
     }
     FX_CUDA(cudaSetDevice(m->device));
     if (!m->d_umma2_w) FX_CUDA(cudaMalloc(&m->d_umma2_w, blob.size()));
-    if (!m->d_flag) FX_CUDA(cudaMalloc(&m->d_flag, sizeof(int)));
     FX_CUDA(cudaMemcpy(m->d_umma2_w, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     m->umma2_ready = true;
     return FLEXS_OK;
@@ -657,7 +598,10 @@ int launch_cnn_umma2(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_o
     if (!m->umma_weights_ok) return launch_cnn_tiled(m, d_idx, n, d_out, s);  // non-finite weights: fp32 path
     p.idx = d_idx; p.out = d_out; p.weights = m->d_weights; p.n = n;
     p.uw = reinterpret_cast<const unsigned char *>(m->d_umma2_w);
-    p.overflow_flag = m->d_flag;
+    flexs_model::StreamWs *ws = nullptr;  // the fp16-overflow flag is per stream: chunks of score_host run concurrently
+    rc = stream_workspace(m, s, 0, &ws);
+    if (rc != FLEXS_OK) return rc;
+    p.overflow_flag = ws->flag;
     p.n_items = (n + p.S - 1) / p.S;
     const size_t smem = carve(p).total + 1024;
     const int grid = (int)std::min<int64_t>(p.n_items, m->sm_count);
@@ -668,7 +612,7 @@ int launch_cnn_umma2(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_o
         FX_CUDA(cudaMalloc(&p.prof, (size_t)grid * 16 * sizeof(long long)));
         FX_CUDA(cudaMemset(p.prof, 0, (size_t)grid * 16 * sizeof(long long)));
     }
-    FX_CUDA(cudaMemsetAsync(m->d_flag, 0, sizeof(int), s));
+    FX_CUDA(cudaMemsetAsync(ws->flag, 0, sizeof(int), s));
     FX_CUDA(cudaFuncSetAttribute(cnn_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cnn_umma2_kernel<<<grid, NT, smem, s>>>(p);
     FX_CUDA(cudaGetLastError());
@@ -688,7 +632,7 @@ int launch_cnn_umma2(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_o
                 a[11] / ch, a[12] / ch, a[14] / ch, a[15] / ch, a[1] / ch);
     }
     // fp16 range guard: the gated FFMA kernel recomputes the batch iff the flag was raised
-    return launch_cnn_tiled_gated(m, d_idx, n, d_out, m->d_flag, s);
+    return launch_cnn_tiled_gated(m, d_idx, n, d_out, ws->flag, s);
 }
 
 }  // namespace fx

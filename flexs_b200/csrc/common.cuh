@@ -68,9 +68,15 @@ struct flexs_model {
     bool k9_ready = false;
     float *d_enum_tab = nullptr;     // enum_table.cu: scores of all A^L sequences (A^L <= 2^20)
     bool enum_ready = false;
-    struct K9Workspace { cudaStream_t stream; void *ptr; size_t bytes; int *flag; };  // flag: fp16-overflow, per stream
-    std::vector<K9Workspace> k9_ws;  // pooled-feature tiles between the conv and dense kernels, one per stream in use
-    int *d_flag = nullptr;           // fp16-overflow flag raised by the UMMA kernel
+    // Per-stream scratch of the tcgen05 kernels: the fp16-overflow flag (raised by a kernel, read by the gated FP32
+    // re-computation enqueued behind it on the same stream) and the pooled-feature tiles that travel from a conv kernel
+    // to the dense-head kernel.  One per stream in use, so concurrent chunks of score_host never share a flag.
+    struct StreamWs { cudaStream_t stream; void *ptr; size_t bytes; int *flag; };
+    std::vector<StreamWs> stream_ws;
+    void *d_a20_w = nullptr;         // cnn_a20.cu: operand blob (dense planes, conv planes, conv1 gather tables), all members
+    bool a20_ready = false;
+    void *d_mlp_w = nullptr;         // mlp_umma.cu: operand blob, all members
+    bool mlp_ready = false;
 
     // Adam state for K4 (same layout as d_weights) and the 1-based step counter per member
     float *d_adam_m = nullptr, *d_adam_v = nullptr;
@@ -101,6 +107,9 @@ MlpOffsets mlp_offsets(const flexs_model *m);
 // kernels' host launchers (each returns a FLEXS_* code and bumps m->launches)
 int launch_encode(const uint8_t *d_chars, int64_t n_bytes, const char *alphabet, int a,
                   uint8_t *d_idx, int64_t *d_status, cudaStream_t s);
+int bits_per_residue(int alphabet_size);
+int launch_unpack(const uint8_t *d_packed, int64_t n, int L, int a, uint8_t *d_idx, int64_t *d_status, cudaStream_t s);
+int launch_pack(const uint8_t *d_idx, int64_t n, int L, int a, uint8_t *d_packed, cudaStream_t s);
 int launch_cnn_simple(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s);
 int launch_cnn_tiled(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s);
 // same kernel, but every CTA returns immediately unless *d_gate != 0 (fp16-overflow fall-back)
@@ -127,6 +136,15 @@ int launch_enum(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, c
 // the fused kernels, without the whole-model table in front of them
 int forward_direct(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s);
 int launch_mlp(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s);
+// k3 = 19 (A = 20) shapes: stream-interleaved rows, rolling activation rings, conv2 + conv3 on tcgen05 (cnn_a20.cu)
+bool cnn_a20_supported(const flexs_model *m);
+int launch_cnn_a20(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s);
+// per-stream scratch (created on first use; grown to `bytes` of feature space, zero-filled when (re)allocated)
+int stream_workspace(flexs_model *m, cudaStream_t s, size_t bytes, flexs_model::StreamWs **out);
+// dense head over [32][128] pooled-feature tiles (cnn_k9.cu): Dense(H,relu) x2 -> Dense(1) -> nan_to_num -> ensemble mean;
+// `uw` is a member blob with the u2 dense offsets (OFF_DB1 / OFF_DB2 / OFF_DV) filled in
+int launch_dense_tiles(flexs_model *m, const float *feat, float *out, const unsigned char *uw, int *flag, int64_t n,
+                       int mem, cudaStream_t s);
 
 }  // namespace fx
 

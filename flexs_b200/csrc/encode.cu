@@ -75,9 +75,97 @@ __global__ void __launch_bounds__(256) encode_kernel(const uint8_t *__restrict__
     }
 }
 
+// ---- packed residues: the wire format of the host boundary -------------------------------------------------------
+// A sequence travels over PCIe as a little-endian bit stream of ceil(log2 A) bits per residue (2 bits for DNA/RNA, 5 for
+// proteins), rows padded to whole bytes: 25 bytes instead of 100 for a 100-mer.  unpack_kernel turns the rows back into
+// one byte per residue for the forward kernels (HBM-bound byte work: reads bits/8, writes 1 byte per residue; values
+// >= A — impossible for a row packed from the alphabet — are reported through `status` like bad characters are).
+__global__ void __launch_bounds__(256) unpack_kernel(const uint8_t *__restrict__ packed, int64_t n, int L, int A, int bits,
+                                                     int row_bytes, uint8_t *__restrict__ idx, int64_t *__restrict__ status) {
+    const int64_t total = n * (int64_t)L;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 16;
+    const uint32_t mask = (1u << bits) - 1u;
+    int64_t bad_count = 0, bad_first = 0x7fffffffffffffffll;
+    const bool vec = (reinterpret_cast<uintptr_t>(idx) & 15) == 0;
+    for (int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16; p0 < total; p0 += stride) {
+        int64_t row = p0 / L;
+        int i = (int)(p0 - row * L);
+        const uint8_t *src = packed + row * row_bytes;
+        const int cnt = (int)min((int64_t)16, total - p0);
+        uint32_t o[4] = {0, 0, 0, 0};
+        for (int k = 0; k < cnt; ++k) {
+            const int bit = i * bits, byte = bit >> 3, sh = bit & 7;
+            uint32_t w = src[byte];
+            if (sh + bits > 8) w |= (uint32_t)src[byte + 1] << 8;
+            uint32_t code = (w >> sh) & mask;
+            if (code >= (uint32_t)A) {
+                bad_count++;
+                bad_first = min(bad_first, p0 + k);
+                code = 0;
+            }
+            o[k >> 2] |= code << (8 * (k & 3));
+            if (++i == L) { i = 0; src += row_bytes; }
+        }
+        if (vec && cnt == 16) *reinterpret_cast<uint4 *>(idx + p0) = make_uint4(o[0], o[1], o[2], o[3]);
+        else for (int k = 0; k < cnt; ++k) idx[p0 + k] = (uint8_t)(o[k >> 2] >> (8 * (k & 3)));
+    }
+    if (bad_count) {
+        atomicAdd(reinterpret_cast<unsigned long long *>(status), (unsigned long long)bad_count);
+        atomicMin(reinterpret_cast<long long *>(status + 1), (long long)bad_first);
+    }
+}
+
+// residue indices -> packed rows (device-generated candidates on their way to the host); one thread per output byte
+__global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ idx, int64_t n, int L, int bits, int row_bytes,
+                                                   uint8_t *__restrict__ packed) {
+    const int64_t total = n * (int64_t)row_bytes;
+    const uint32_t mask = (1u << bits) - 1u;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = q / row_bytes;
+        const int byte = (int)(q - row * row_bytes);
+        const uint8_t *src = idx + row * L;
+        const int first = (byte * 8) / bits, last = min(L - 1, (byte * 8 + 7) / bits);
+        uint32_t out = 0;
+        for (int i = first; i <= last; ++i) {
+            const int rel = i * bits - byte * 8;  // position of residue i's bit 0 relative to this byte
+            const uint32_t v = (uint32_t)src[i] & mask;
+            out |= rel >= 0 ? (v << rel) : (v >> (-rel));
+        }
+        packed[q] = (uint8_t)out;
+    }
+}
+
 }  // namespace
 
 namespace fx {
+
+int bits_per_residue(int a) {
+    int bits = 1;
+    while ((1 << bits) < a) ++bits;
+    return bits;
+}
+
+static int grid_for(int64_t work_items) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return (int)std::max<int64_t>(1, std::min<int64_t>((work_items + 255) / 256, (int64_t)sms * 8));
+}
+
+int launch_unpack(const uint8_t *d_packed, int64_t n, int L, int a, uint8_t *d_idx, int64_t *d_status, cudaStream_t s) {
+    const int bits = bits_per_residue(a), row_bytes = (L * bits + 7) / 8;
+    encode_init_kernel<<<1, 1, 0, s>>>(d_status);
+    if (n > 0) unpack_kernel<<<grid_for((n * L + 15) / 16), 256, 0, s>>>(d_packed, n, L, a, bits, row_bytes, d_idx, d_status);
+    FX_CUDA(cudaGetLastError());
+    return FLEXS_OK;
+}
+
+int launch_pack(const uint8_t *d_idx, int64_t n, int L, int a, uint8_t *d_packed, cudaStream_t s) {
+    const int bits = bits_per_residue(a), row_bytes = (L * bits + 7) / 8;
+    if (n > 0) pack_kernel<<<grid_for(n * row_bytes), 256, 0, s>>>(d_idx, n, L, bits, row_bytes, d_packed);
+    FX_CUDA(cudaGetLastError());
+    return FLEXS_OK;
+}
 
 int launch_encode(const uint8_t *d_chars, int64_t n_bytes, const char *alphabet, int a,
                   uint8_t *d_idx, int64_t *d_status, cudaStream_t s) {

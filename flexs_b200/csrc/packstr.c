@@ -10,9 +10,19 @@
  *   sequences: list or tuple of str, all of one length (ValueError otherwise: "all sequences must have the same length"),
  *              only code points <= 255 (ValueError otherwise, worded like str.index's failure as the Python path is)
  *   out:       writable C-contiguous buffer of exactly len(sequences) * width bytes
+ *
+ * pack_bits(sequences, alphabet, out, threads) -> width
+ *   the same walk, but each character is mapped through the alphabet (first occurrence wins, like str.index) and
+ *   stored as ceil(log2 A) bits, rows padded to whole bytes: the wire format of flexs_model_score_host_packed
+ *   (include/flexs_b200.h).  The per-row work runs on `threads` POSIX threads with the GIL released (the strings are
+ *   kept alive by references taken first).  A character outside the alphabet raises ValueError naming the sequence
+ *   and position, as str.index does in the reference (sequence_utils.py:46).
  */
 #define PY_SSIZE_T_CLEAN
 #include <Python.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 static PyObject *pack(PyObject *self, PyObject *args) {
@@ -54,7 +64,122 @@ done:
     return result;
 }
 
+typedef struct {
+    const unsigned char **rows;
+    Py_ssize_t begin, end, width, row_bytes;
+    int bits;
+    const unsigned char *lut;
+    unsigned char *dst;
+    Py_ssize_t bad_row, bad_col;  /* first character outside the alphabet in this range, or -1 */
+} pack_job;
+
+static void *pack_rows(void *arg) {
+    pack_job *j = (pack_job *)arg;
+    j->bad_row = -1; j->bad_col = -1;
+    for (Py_ssize_t r = j->begin; r < j->end; ++r) {
+        const unsigned char *src = j->rows[r];
+        unsigned char *out = j->dst + r * j->row_bytes;
+        uint64_t acc = 0;
+        int have = 0;
+        for (Py_ssize_t i = 0; i < j->width; ++i) {
+            unsigned code = j->lut[src[i]];
+            if (code == 0xFF) {
+                if (j->bad_row < 0) { j->bad_row = r; j->bad_col = i; }
+                code = 0;
+            }
+            acc |= (uint64_t)code << have;
+            have += j->bits;
+            while (have >= 8) { *out++ = (unsigned char)acc; acc >>= 8; have -= 8; }
+        }
+        if (have > 0) *out++ = (unsigned char)acc;
+    }
+    return NULL;
+}
+
+static PyObject *pack_bits(PyObject *self, PyObject *args) {
+    PyObject *seqs;
+    Py_buffer out, alpha;
+    int threads = 1;
+    (void)self;
+    if (!PyArg_ParseTuple(args, "Oy*w*|i", &seqs, &alpha, &out, &threads)) return NULL;
+    PyObject *fast = PySequence_Fast(seqs, "sequences must be a list or tuple of str");
+    if (!fast) { PyBuffer_Release(&out); PyBuffer_Release(&alpha); return NULL; }
+    const Py_ssize_t n = PySequence_Fast_GET_SIZE(fast);
+    PyObject **items = PySequence_Fast_ITEMS(fast);
+    PyObject *result = NULL;
+    const unsigned char **rows = NULL;
+    Py_ssize_t held = 0, width = -1;
+    unsigned char lut[256];
+    memset(lut, 0xFF, sizeof lut);
+    if (alpha.len < 2 || alpha.len > 255) { PyErr_SetString(PyExc_ValueError, "alphabet must have 2..255 characters"); goto done; }
+    for (Py_ssize_t i = alpha.len - 1; i >= 0; --i) lut[((const unsigned char *)alpha.buf)[i]] = (unsigned char)i;
+    int bits = 1;
+    while ((1 << bits) < alpha.len) ++bits;
+    rows = (const unsigned char **)malloc((size_t)(n > 0 ? n : 1) * sizeof *rows);
+    if (!rows) { PyErr_NoMemory(); goto done; }
+    for (Py_ssize_t i = 0; i < n; ++i) {
+        PyObject *s = items[i];
+        if (!PyUnicode_Check(s)) { PyErr_SetString(PyExc_TypeError, "sequences must be str"); goto done; }
+        const Py_ssize_t len = PyUnicode_GET_LENGTH(s);
+        if (width < 0) width = len;
+        else if (len != width) { PyErr_SetString(PyExc_ValueError, "all sequences must have the same length"); goto done; }
+        if (PyUnicode_KIND(s) != PyUnicode_1BYTE_KIND) {
+            PyErr_SetString(PyExc_ValueError, "substring not found: non latin-1 character in sequence");
+            goto done;
+        }
+        Py_INCREF(s);  /* the rows are read with the GIL released */
+        rows[i] = PyUnicode_1BYTE_DATA(s);
+        held = i + 1;
+    }
+    if (width < 0) width = 0;
+    const Py_ssize_t row_bytes = (width * bits + 7) / 8;
+    if (!PyBuffer_IsContiguous(&out, 'C') || out.len != n * row_bytes) {
+        PyErr_SetString(PyExc_ValueError, "out must be a C-contiguous buffer of len(sequences) * ceil(width * bits / 8) bytes");
+        goto done;
+    }
+    if (threads < 1) threads = 1;
+    if (threads > 64) threads = 64;
+    if (n * width < (Py_ssize_t)1 << 18) threads = 1;  /* thread start-up costs more than the packing */
+    pack_job jobs[64];
+    pthread_t tids[64];
+    Py_ssize_t bad_row = -1, bad_col = -1;
+    Py_BEGIN_ALLOW_THREADS
+    for (int t = 0; t < threads; ++t) {
+        jobs[t].rows = rows; jobs[t].width = width; jobs[t].row_bytes = row_bytes; jobs[t].bits = bits;
+        jobs[t].lut = lut; jobs[t].dst = (unsigned char *)out.buf;
+        jobs[t].begin = n * t / threads; jobs[t].end = n * (t + 1) / threads;
+        if (t == threads - 1 || pthread_create(&tids[t], NULL, pack_rows, &jobs[t]) != 0) {
+            /* the last range (or one whose thread could not start) runs here */
+            pack_rows(&jobs[t]);
+            tids[t] = 0;
+        }
+    }
+    for (int t = 0; t < threads; ++t)
+        if (tids[t]) pthread_join(tids[t], NULL);
+    Py_END_ALLOW_THREADS
+    for (int t = 0; t < threads; ++t)
+        if (jobs[t].bad_row >= 0 && (bad_row < 0 || jobs[t].bad_row < bad_row)) { bad_row = jobs[t].bad_row; bad_col = jobs[t].bad_col; }
+    if (bad_row >= 0) {
+        PyObject *ch = PyUnicode_FromOrdinal(rows[bad_row][bad_col]);
+        PyErr_Format(PyExc_ValueError, "substring not found: character %R of sequence %zd (position %zd) is not in the alphabet",
+                     ch ? ch : Py_None, bad_row, bad_col);
+        Py_XDECREF(ch);
+        goto done;
+    }
+    result = PyLong_FromSsize_t(width);
+done:
+    for (Py_ssize_t i = 0; i < held; ++i) Py_DECREF(items[i]);
+    free((void *)rows);
+    Py_DECREF(fast);
+    PyBuffer_Release(&out);
+    PyBuffer_Release(&alpha);
+    return result;
+}
+
 static PyMethodDef methods[] = {
+    {"pack_bits", pack_bits, METH_VARARGS,
+     "pack_bits(sequences, alphabet, out, threads=1) -> width: map equal-length str objects through the alphabet and store "
+     "ceil(log2 A) bits per residue"},
     {"pack", pack, METH_VARARGS, "pack(sequences, out) -> width: copy equal-length Latin-1 str objects into a uint8 buffer"},
     {NULL, NULL, 0, NULL}};
 

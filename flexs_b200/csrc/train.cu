@@ -542,6 +542,7 @@ int flexs_model_train_step_dev(flexs_model_t *m, int member, const uint8_t *d_id
     FX_REQUIRE(member >= 0 && member < m->M, "member out of range");
     FX_REQUIRE(n >= 1 && n <= 65536, "batch of 1..65536 sequences");
     FX_REQUIRE(d_dropout_mask == nullptr || m->kind == FLEXS_KIND_CNN, "only the CNN has a Dropout layer (cnn.py:51)");
+    FX_CUDA(cudaSetDevice(m->device));
     cudaStream_t s = (cudaStream_t)stream;
     int rc = ensure_training_state(m, (int)n);
     if (rc != FLEXS_OK) return rc;
@@ -560,6 +561,7 @@ int flexs_model_fit_dev(flexs_model_t *m, const uint8_t *d_idx, const float *d_l
     FX_REQUIRE(m && d_idx && d_labels, "null argument");
     FX_REQUIRE(n >= 1 && n < (1ll << 31), "bad n");
     FX_REQUIRE(batch_size >= 1 && epochs >= 0, "bad batch_size / epochs");
+    FX_CUDA(cudaSetDevice(m->device));
     cudaStream_t s = (cudaStream_t)stream;
     const int B = (int)std::min<int64_t>(batch_size, n);
     int rc = ensure_training_state(m, B);

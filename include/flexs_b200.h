@@ -120,6 +120,25 @@ int flexs_model_forward_dev(flexs_model_t *m, const uint8_t *d_idx, int64_t n, f
 int flexs_model_score_host(flexs_model_t *m, const char *h_chars, int64_t n,
                            const char *alphabet, float *h_out, int64_t *bad_pos);
 
+/* ---- packed residues: the wire format of the host boundary --------------------------------
+ * The float one-hot the reference ships to TensorFlow (keras_model.py:70-75: 4*L*A bytes per
+ * sequence) is replaced on the wire by ceil(log2 A) bits per residue: residue i of a row occupies
+ * bits [i*b, (i+1)*b) of the row's little-endian bit stream (bit k = bit k%8 of byte k/8), rows
+ * padded to whole bytes — 25 bytes for a DNA 100-mer, 149 for a GFP 237-mer.
+ * flexs_model_score_host_packed is flexs_model_score_host for rows already in that format (the
+ * host packers: flexs_b200/csrc/packstr.c pack_bits for str lists, sequence_utils.pack_indices for
+ * arrays); a value >= alphabet_size in a row is reported as FLEXS_EALPHABET with *bad_pos = its
+ * flat residue position.  flexs_unpack_dev / flexs_pack_dev convert on the device; d_status as in
+ * flexs_encode_dev.                                                                           */
+int flexs_bits_per_residue(int alphabet_size);
+int64_t flexs_packed_row_bytes(int seq_len, int alphabet_size);
+int flexs_unpack_dev(const uint8_t *d_packed, int64_t n, int seq_len, int alphabet_size,
+                     uint8_t *d_idx, int64_t *d_status, void *stream);
+int flexs_pack_dev(const uint8_t *d_idx, int64_t n, int seq_len, int alphabet_size,
+                   uint8_t *d_packed, void *stream);
+int flexs_model_score_host_packed(flexs_model_t *m, const uint8_t *h_packed, int64_t n,
+                                  float *h_out, int64_t *bad_pos);
+
 /* ---- K3: selection -------------------------------------------------------------------
  * Replaces the final ranking of propose_sequences: np.argsort(preds)[: -B : -1]
  * (adalead.py:171-175, cbas_dbas.py:197-201, cmaes.py:117-122) and

@@ -43,3 +43,29 @@ def rel_err(got, ref, floor):
     got = np.asarray(got, dtype=np.float64)
     ref = np.asarray(ref, dtype=np.float64)
     return float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), floor))) if ref.size else 0.0
+
+
+def elem_rel_err(got, ref, frac=1e-2):
+    """Per-element relative error max_i |got_i - ref_i| / |ref_i| over the elements with |ref_i| >= frac * max|ref|
+    (north_star's "within 1e-4 relative", element by element; scores closer to zero than 1 % of the batch's scale
+    are covered by :func:`rel_err`'s scale-normalised bound).  Returns (error, number of elements compared)."""
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    if not ref.size:
+        return 0.0, 0
+    scale = np.abs(ref).max()
+    if scale == 0.0:  # an all-zero batch (e.g. every ReLU closed): only exact zeros agree
+        return (0.0 if not np.any(got) else float("inf")), int(ref.size)
+    keep = np.abs(ref) >= frac * scale
+    return float(np.max(np.abs(got - ref)[keep] / np.abs(ref)[keep])), int(keep.sum())
+
+
+def parity_report(tag, **fields):
+    """Append one line to gpurun_out/parity_report.jsonl (copied to profiles/ after a GPU run)."""
+    out = REPO / "gpurun_out"
+    try:
+        out.mkdir(exist_ok=True)
+        with open(out / "parity_report.jsonl", "a") as fh:
+            fh.write(json.dumps({"case": tag, **fields}) + "\n")
+    except OSError:
+        pass
