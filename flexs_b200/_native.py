@@ -39,6 +39,11 @@ _SIGNATURES = [
     ("flexs_encode_dev", c_int, [c_void_p, c_int64, c_char_p, c_int, c_void_p, c_void_p, c_void_p]),
     ("flexs_model_forward_dev", c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     ("flexs_model_score_host", c_int, [c_void_p, c_void_p, c_int64, c_char_p, c_void_p, POINTER(c_int64)]),
+    ("flexs_bits_per_residue", c_int, [c_int]),
+    ("flexs_packed_row_bytes", c_int64, [c_int, c_int]),
+    ("flexs_unpack_dev", c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    ("flexs_pack_dev", c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    ("flexs_model_score_host_packed", c_int, [c_void_p, c_void_p, c_int64, c_void_p, POINTER(c_int64)]),
     ("flexs_topk_workspace_bytes", c_int64, [c_int64, c_int]),
     ("flexs_topk_dev", c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("flexs_dedup_workspace_bytes", c_int64, [c_int64]),
@@ -197,6 +202,25 @@ class NativeModel:
         check(rc, "score_host")
         return out
 
+    def score_host_packed(self, packed: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """``packed``: contiguous ``uint8[n, ceil(L * bits / 8)]`` rows in the wire format of include/flexs_b200.h
+        (``sequence_utils.pack_sequences``) in host memory -> ``float32[n]``."""
+        row_bytes = packed_row_bytes(self.seq_len, self.alphabet_size)
+        if packed.dtype != np.uint8 or not packed.flags.c_contiguous or packed.ndim != 2 or packed.shape[1] != row_bytes:
+            raise ValueError(f"packed must be a C-contiguous uint8 [n, {row_bytes}] array")
+        n = packed.shape[0]
+        if out is None:
+            out = np.empty(n, dtype=np.float32)
+        bad = c_int64(-1)
+        rc = lib().flexs_model_score_host_packed(self._h, packed.ctypes.data_as(c_void_p), n,
+                                                 out.ctypes.data_as(c_void_p), ctypes.byref(bad))
+        if rc == EALPHABET:
+            pos = bad.value
+            raise ValueError(f"substring not found: residue {pos % self.seq_len} of sequence {pos // self.seq_len} "
+                             f"is not a valid index into the alphabet")
+        check(rc, "score_host_packed")
+        return out
+
     # -- training --------------------------------------------------------------------------
     def fit_dev(self, d_idx: int, d_labels: int, n: int, batch_size: int, epochs: int, seed: int,
                 stream: int = 0) -> np.ndarray:
@@ -228,6 +252,27 @@ class NativeModel:
 def encode_dev(d_chars: int, n_bytes: int, alphabet: str, d_idx: int, d_status: int, stream: int = 0) -> None:
     check(lib().flexs_encode_dev(c_void_p(d_chars), n_bytes, alphabet.encode("latin-1"), len(alphabet),
                                  c_void_p(d_idx), c_void_p(d_status), c_void_p(stream)), "encode")
+
+
+def bits_per_residue(alphabet_size: int) -> int:
+    bits = 1
+    while (1 << bits) < alphabet_size:
+        bits += 1
+    return bits
+
+
+def packed_row_bytes(seq_len: int, alphabet_size: int) -> int:
+    """Bytes of one sequence in the packed wire format (pure arithmetic, mirrors flexs_packed_row_bytes)."""
+    return (seq_len * bits_per_residue(alphabet_size) + 7) // 8
+
+
+def unpack_dev(d_packed: int, n: int, seq_len: int, alphabet_size: int, d_idx: int, d_status: int, stream: int = 0) -> None:
+    check(lib().flexs_unpack_dev(c_void_p(d_packed), n, seq_len, alphabet_size, c_void_p(d_idx), c_void_p(d_status),
+                                 c_void_p(stream)), "unpack")
+
+
+def pack_dev(d_idx: int, n: int, seq_len: int, alphabet_size: int, d_packed: int, stream: int = 0) -> None:
+    check(lib().flexs_pack_dev(c_void_p(d_idx), n, seq_len, alphabet_size, c_void_p(d_packed), c_void_p(stream)), "pack")
 
 
 def topk_workspace_bytes(n: int, k: int) -> int:

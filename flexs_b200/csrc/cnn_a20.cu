@@ -87,7 +87,11 @@ constexpr uint32_t A_DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
 // taps [J0, J1) of one 128-row tile: per tap 2 K steps x {A_hi x [W_hi|W_lo], A_lo x W_hi}.  All 32 lanes call it.
 template <int J0, int J1>
 __device__ __forceinline__ void issue_taps(uint32_t a_win_addr, uint32_t w_addr, uint32_t d_tmem) {
-    const uint32_t a0 = desc_lo(a_win_addr, 16), b0 = desc_lo(w_addr, UWKC);
+    // redux.sync lands in a uniform register: the descriptor arithmetic below then stays on the uniform datapath
+    // (base + immediate) instead of six R2UR moves per MMA
+    const uint32_t a0 = __reduce_or_sync(0xffffffffu, desc_lo(a_win_addr, 16));
+    const uint32_t b0 = __reduce_or_sync(0xffffffffu, desc_lo(w_addr, UWKC));
+    d_tmem = __reduce_or_sync(0xffffffffu, d_tmem);
 #pragma unroll
     for (int j = J0; j < J1; ++j) {
 #pragma unroll
@@ -122,7 +126,10 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
     uint32_t *tmem_addr_s = reinterpret_cast<uint32_t *>(smem_raw + S_TM);
     float *b2s = reinterpret_cast<float *>(smem_raw + S_B2S);
     float *b3 = reinterpret_cast<float *>(smem_raw + S_B3);
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // broadcast from lane 0: tells the compiler the role branches below are warp-uniform, which keeps the issuing warps'
+    // descriptor arithmetic on the uniform datapath
+    const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int L = p.L, T = p.T;
 
     if (tid == 0) {
@@ -177,7 +184,6 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
                                   ((reinterpret_cast<uintptr_t>(p.idx) + (uintptr_t)(item * 8 * L)) & 15) + (b < nvalid ? b : 0) * L;
             for (int qc = 0; qc < p.nc1; ++qc, ++g1) {
                 const uint32_t slot = g1 & 1u;
-                if (g1 >= 2) fxd::mbar_wait(&bar[B_H1E + slot], ((g1 >> 1) - 1) & 1);
                 float4 ta[4][2], tb[4][2];
                 bool ok[4];
 #pragma unroll
@@ -194,6 +200,9 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
                         tb[i][0] = __ldg(pb); tb[i][1] = __ldg(pb + 1);
                     }
                 }
+                // the gathers are in flight before the ring slot is waited for: their L2 latency is off the
+                // conv2 -> conv1 -> conv2 dependency chain of the two-chunk ring
+                if (g1 >= 2) fxd::mbar_wait(&bar[B_H1E + slot], ((g1 >> 1) - 1) & 1);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     uint4 hi4 = make_uint4(0, 0, 0, 0), lo4 = make_uint4(0, 0, 0, 0);
@@ -368,9 +377,9 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
         for (int64_t item = blockIdx.x; item < p.n_items; item += stride) {
             for (int qc = 0; qc < p.nlive2; ++qc, ++g1, ++a2) {
                 const uint32_t s0 = g1 & 1u, a = a2 & 1u;
-                fxd::mbar_wait(&bar[B_H1F + s0], (g1 >> 1) & 1);
-                fxd::mbar_wait(&bar[B_H1F + (s0 ^ 1u)], ((g1 + 1) >> 1) & 1);  // the window ends 4 groups into the next chunk
-                if (a2 >= 2) fxd::mbar_wait(&bar[B_A2E + a], ((a2 >> 1) - 1) & 1);
+                fxd::mbar_wait_warp(&bar[B_H1F + s0], (g1 >> 1) & 1);
+                fxd::mbar_wait_warp(&bar[B_H1F + (s0 ^ 1u)], ((g1 + 1) >> 1) & 1);  // the window ends 4 groups into the next chunk
+                if (a2 >= 2) fxd::mbar_wait_warp(&bar[B_A2E + a], ((a2 >> 1) - 1) & 1);
                 tc_fence_after();
                 issue_taps<0, K>(r1_addr + s0 * 16u * 1024u, w2_addr, tmem_base + a * 64u);
                 umma_commit_elect(&bar[B_A2F + a]);
@@ -386,14 +395,14 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
         for (int64_t item = blockIdx.x; item < p.n_items; item += stride) {
             for (int q = 0; q < p.nt3; ++q, ++t3) {
                 const uint32_t G = g2 + (uint32_t)q, s0 = G % 3u, a = t3 & 1u;
-                fxd::mbar_wait(&bar[B_H2F + s0], (G / 3u) & 1);
-                fxd::mbar_wait(&bar[B_H2F + (G + 1) % 3u], ((G + 1) / 3u) & 1);
-                if (t3 >= 2) fxd::mbar_wait(&bar[B_A3E + a], ((t3 >> 1) - 1) & 1);
+                fxd::mbar_wait_warp(&bar[B_H2F + s0], (G / 3u) & 1);
+                fxd::mbar_wait_warp(&bar[B_H2F + (G + 1) % 3u], ((G + 1) / 3u) & 1);
+                if (t3 >= 2) fxd::mbar_wait_warp(&bar[B_A3E + a], ((t3 >> 1) - 1) & 1);
                 tc_fence_after();
                 const uint32_t win = r2_addr + s0 * 16u * 1024u, d = tmem_base + 128u + a * 64u;
                 issue_taps<0, KC3 - 2>(win, w3_addr, d);
                 // taps 17 and 18 reach into the third chunk of the window (its first two groups)
-                fxd::mbar_wait(&bar[B_H2F + (G + 2) % 3u], ((G + 2) / 3u) & 1);
+                fxd::mbar_wait_warp(&bar[B_H2F + (G + 2) % 3u], ((G + 2) / 3u) & 1);
                 tc_fence_after();
                 issue_taps<KC3 - 2, KC3>(win, w3_addr, d);
                 umma_commit_elect(&bar[B_A3F + a]);

@@ -219,7 +219,10 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
     float *feat_s = reinterpret_cast<float *>(smem_raw + of.feat);
     unsigned char *ring = smem_raw + of.ring;
 
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // broadcast from lane 0: tells the compiler the role branches are warp-uniform, which keeps the MMA issuers'
+    // descriptor arithmetic on the uniform datapath (UTCHMMA every ~4 uniform instructions instead of ~16 with R2UR moves)
+    const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int L = p.L, T = p.T, nti = p.nti;
 
     if (tid == 0) {
@@ -475,9 +478,9 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
             for (uint32_t tl = (me - kt) & (NMMA - 1); tl < ntiles; tl += NMMA) {
                 const uint32_t k = kt + tl, s = k & 7u, use = k >> 3;
                 const long long m0 = now();
-                fxd::mbar_wait(&full[s], use & 1);
+                fxd::mbar_wait_warp(&full[s], use & 1);
                 const long long m1 = now();
-                if (use > 0) fxd::mbar_wait(&tempty[s], (use - 1) & 1);  // accumulator drained by the epilogue
+                if (use > 0) fxd::mbar_wait_warp(&tempty[s], (use - 1) & 1);  // accumulator drained by the epilogue
                 if (PROF && lane == 0 && wid == MMAW) { pt[5] += m1 - m0; pt[6] += now() - m1; }
                 tc_fence_after();
                 if (!(PROF && (p.dbg & 1))) issue_conv3_tile(ring_addr + s * SLOT, uw3_addr, tmem_base + s * 64u);
@@ -512,7 +515,7 @@ __global__ void __launch_bounds__(DNT, 1) cnn_k9_dense_kernel(const DenseParams 
     uint32_t *tmem_addr_s = reinterpret_cast<uint32_t *>(smem_raw + D_OFF_TM);
     float *ft = reinterpret_cast<float *>(smem_raw + D_OFF_FT);
     unsigned char *scratch = smem_raw + D_OFF_SCR;
-    const int tid = threadIdx.x, wid = tid >> 5;
+    const int tid = threadIdx.x, wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
     if (tid == 0) {
         fxd::mbar_init(&mbar[0], 1); fxd::mbar_init(&mbar[1], 1); fxd::mbar_init(&mbar[2], 1);
         fxd::fence_mbar_init();

@@ -205,6 +205,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         }
     }
 }
+// The same wait for a warp that must stay CONVERGED afterwards (the MMA-issuing warps): the loop exits on a vote, a
+// warp-uniform condition, so the compiler keeps the code behind it on the uniform datapath (descriptor arithmetic in
+// uniform registers, no per-MMA R2UR moves under an election predicate).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity) {
+    if (__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) return;
+    unsigned long long t0 = 0, t1;
+    unsigned int spins = 0;
+    while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+        if ((++spins & 63u) == 0) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t0 == 0) t0 = t1;
+            else if (t1 - t0 > 4000000000ull) __trap();
+        }
+    }
+}
 // global -> shared bulk copy; dst/src 16-byte aligned, bytes a multiple of 16
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
                                          uint64_t *bar) {

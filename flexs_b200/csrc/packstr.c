@@ -65,33 +65,45 @@ done:
 }
 
 typedef struct {
-    const unsigned char **rows;
+    PyObject **items;
     Py_ssize_t begin, end, width, row_bytes;
     int bits;
     const unsigned char *lut;
     unsigned char *dst;
-    Py_ssize_t bad_row, bad_col;  /* first character outside the alphabet in this range, or -1 */
+    int err;                      /* 0 ok, 1 not a str, 2 ragged, 3 not latin-1, 4 character outside the alphabet */
+    Py_ssize_t bad_row, bad_col;  /* first offending sequence (and position, for err 4) in this range */
 } pack_job;
 
+/* Runs WITHOUT the GIL: only reads immutable fields of str objects that the caller's list keeps alive. */
 static void *pack_rows(void *arg) {
     pack_job *j = (pack_job *)arg;
-    j->bad_row = -1; j->bad_col = -1;
+    j->err = 0; j->bad_row = -1; j->bad_col = -1;
     for (Py_ssize_t r = j->begin; r < j->end; ++r) {
-        const unsigned char *src = j->rows[r];
+        PyObject *s = j->items[r];
+        if (r + 8 < j->end) __builtin_prefetch(j->items[r + 8]);
+        int err = 0;
+        if (!PyUnicode_Check(s)) err = 1;
+        else if (PyUnicode_GET_LENGTH(s) != j->width) err = 2;
+        else if (PyUnicode_KIND(s) != PyUnicode_1BYTE_KIND) err = 3;
+        if (err) {
+            if (!j->err) { j->err = err; j->bad_row = r; }
+            continue;
+        }
+        const unsigned char *src = PyUnicode_1BYTE_DATA(s);
         unsigned char *out = j->dst + r * j->row_bytes;
         uint64_t acc = 0;
         int have = 0;
         for (Py_ssize_t i = 0; i < j->width; ++i) {
             unsigned code = j->lut[src[i]];
             if (code == 0xFF) {
-                if (j->bad_row < 0) { j->bad_row = r; j->bad_col = i; }
+                if (!j->err) { j->err = 4; j->bad_row = r; j->bad_col = i; }
                 code = 0;
             }
             acc |= (uint64_t)code << have;
             have += j->bits;
-            while (have >= 8) { *out++ = (unsigned char)acc; acc >>= 8; have -= 8; }
+            if (have >= 32) { memcpy(out, &acc, 4); out += 4; acc >>= 32; have -= 32; }
         }
-        if (have > 0) *out++ = (unsigned char)acc;
+        while (have > 0) { *out++ = (unsigned char)acc; acc >>= 8; have -= 8; }
     }
     return NULL;
 }
@@ -107,31 +119,17 @@ static PyObject *pack_bits(PyObject *self, PyObject *args) {
     const Py_ssize_t n = PySequence_Fast_GET_SIZE(fast);
     PyObject **items = PySequence_Fast_ITEMS(fast);
     PyObject *result = NULL;
-    const unsigned char **rows = NULL;
-    Py_ssize_t held = 0, width = -1;
     unsigned char lut[256];
     memset(lut, 0xFF, sizeof lut);
     if (alpha.len < 2 || alpha.len > 255) { PyErr_SetString(PyExc_ValueError, "alphabet must have 2..255 characters"); goto done; }
     for (Py_ssize_t i = alpha.len - 1; i >= 0; --i) lut[((const unsigned char *)alpha.buf)[i]] = (unsigned char)i;
     int bits = 1;
     while ((1 << bits) < alpha.len) ++bits;
-    rows = (const unsigned char **)malloc((size_t)(n > 0 ? n : 1) * sizeof *rows);
-    if (!rows) { PyErr_NoMemory(); goto done; }
-    for (Py_ssize_t i = 0; i < n; ++i) {
-        PyObject *s = items[i];
-        if (!PyUnicode_Check(s)) { PyErr_SetString(PyExc_TypeError, "sequences must be str"); goto done; }
-        const Py_ssize_t len = PyUnicode_GET_LENGTH(s);
-        if (width < 0) width = len;
-        else if (len != width) { PyErr_SetString(PyExc_ValueError, "all sequences must have the same length"); goto done; }
-        if (PyUnicode_KIND(s) != PyUnicode_1BYTE_KIND) {
-            PyErr_SetString(PyExc_ValueError, "substring not found: non latin-1 character in sequence");
-            goto done;
-        }
-        Py_INCREF(s);  /* the rows are read with the GIL released */
-        rows[i] = PyUnicode_1BYTE_DATA(s);
-        held = i + 1;
+    Py_ssize_t width = 0;
+    if (n > 0) {
+        if (!PyUnicode_Check(items[0])) { PyErr_SetString(PyExc_TypeError, "sequences must be str"); goto done; }
+        width = PyUnicode_GET_LENGTH(items[0]);
     }
-    if (width < 0) width = 0;
     const Py_ssize_t row_bytes = (width * bits + 7) / 8;
     if (!PyBuffer_IsContiguous(&out, 'C') || out.len != n * row_bytes) {
         PyErr_SetString(PyExc_ValueError, "out must be a C-contiguous buffer of len(sequences) * ceil(width * bits / 8) bytes");
@@ -142,34 +140,37 @@ static PyObject *pack_bits(PyObject *self, PyObject *args) {
     if (n * width < (Py_ssize_t)1 << 18) threads = 1;  /* thread start-up costs more than the packing */
     pack_job jobs[64];
     pthread_t tids[64];
-    Py_ssize_t bad_row = -1, bad_col = -1;
+    int started[64];
+    /* The str objects are reached through the caller's list, which must not be mutated while this call runs (the usual
+     * contract of an extension that releases the GIL over borrowed data); touching a million heap objects is a million
+     * cache misses, so that walk is what the threads parallelise. */
     Py_BEGIN_ALLOW_THREADS
     for (int t = 0; t < threads; ++t) {
-        jobs[t].rows = rows; jobs[t].width = width; jobs[t].row_bytes = row_bytes; jobs[t].bits = bits;
+        jobs[t].items = items; jobs[t].width = width; jobs[t].row_bytes = row_bytes; jobs[t].bits = bits;
         jobs[t].lut = lut; jobs[t].dst = (unsigned char *)out.buf;
         jobs[t].begin = n * t / threads; jobs[t].end = n * (t + 1) / threads;
-        if (t == threads - 1 || pthread_create(&tids[t], NULL, pack_rows, &jobs[t]) != 0) {
-            /* the last range (or one whose thread could not start) runs here */
-            pack_rows(&jobs[t]);
-            tids[t] = 0;
-        }
+        started[t] = (t < threads - 1) && pthread_create(&tids[t], NULL, pack_rows, &jobs[t]) == 0;
+        if (!started[t]) pack_rows(&jobs[t]);  /* the last range (or one whose thread could not start) runs here */
     }
     for (int t = 0; t < threads; ++t)
-        if (tids[t]) pthread_join(tids[t], NULL);
+        if (started[t]) pthread_join(tids[t], NULL);
     Py_END_ALLOW_THREADS
-    for (int t = 0; t < threads; ++t)
-        if (jobs[t].bad_row >= 0 && (bad_row < 0 || jobs[t].bad_row < bad_row)) { bad_row = jobs[t].bad_row; bad_col = jobs[t].bad_col; }
-    if (bad_row >= 0) {
-        PyObject *ch = PyUnicode_FromOrdinal(rows[bad_row][bad_col]);
-        PyErr_Format(PyExc_ValueError, "substring not found: character %R of sequence %zd (position %zd) is not in the alphabet",
-                     ch ? ch : Py_None, bad_row, bad_col);
-        Py_XDECREF(ch);
-        goto done;
+    for (int t = 0; t < threads; ++t) {
+        if (!jobs[t].err) continue;
+        const Py_ssize_t r = jobs[t].bad_row, c = jobs[t].bad_col;
+        if (jobs[t].err == 1) PyErr_SetString(PyExc_TypeError, "sequences must be str");
+        else if (jobs[t].err == 2) PyErr_SetString(PyExc_ValueError, "all sequences must have the same length");
+        else if (jobs[t].err == 3) PyErr_SetString(PyExc_ValueError, "substring not found: non latin-1 character in sequence");
+        else {
+            PyObject *ch = PyUnicode_FromOrdinal(PyUnicode_1BYTE_DATA(items[r])[c]);
+            PyErr_Format(PyExc_ValueError, "substring not found: character %R of sequence %zd (position %zd) is not in the alphabet",
+                         ch ? ch : Py_None, r, c);
+            Py_XDECREF(ch);
+        }
+        goto done;  /* ranges are ordered: the first range with an error holds the first offending sequence */
     }
     result = PyLong_FromSsize_t(width);
 done:
-    for (Py_ssize_t i = 0; i < held; ++i) Py_DECREF(items[i]);
-    free((void *)rows);
     Py_DECREF(fast);
     PyBuffer_Release(&out);
     PyBuffer_Release(&alpha);

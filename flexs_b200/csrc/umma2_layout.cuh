@@ -157,7 +157,8 @@ __device__ __forceinline__ void dense_head_umma(unsigned char *scratch, const fl
                                                 int g_slots, const unsigned char *uw, uint32_t tmem_base,
                                                 uint64_t *dbar, uint32_t &dph, float &xmax, int mem, int M,
                                                 float *out, SeqOf seq_of) {
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler: MMA issue on the uniform datapath
     unsigned char *dx1 = scratch + DS_X1, *db1 = scratch + DS_B1, *dx2 = scratch + DS_X2, *db2 = scratch + DS_B2;
     float *dpart = reinterpret_cast<float *>(scratch + DS_PART);
     const float *gdv = reinterpret_cast<const float *>(uw + OFF_DV);

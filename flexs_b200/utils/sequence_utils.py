@@ -31,7 +31,7 @@ def _lut(alphabet: str) -> np.ndarray:
 _PACKSTR = False  # not looked up yet
 
 
-def _packstr():
+def _packstr(name: str = "pack"):
     """``flexs_b200/_packstr`` (csrc/packstr.c, built next to the CUDA library): packs a list of str in one C pass.
     ``None`` when it has not been built — the pure-Python route below is equivalent, only ~6x slower."""
     global _PACKSTR
@@ -39,10 +39,69 @@ def _packstr():
         try:
             from flexs_b200 import _packstr as mod
 
-            _PACKSTR = mod.pack
+            _PACKSTR = mod
         except ImportError:
             _PACKSTR = None
-    return _PACKSTR
+    return getattr(_PACKSTR, name, None) if _PACKSTR is not None else None
+
+
+def bits_per_residue(alphabet_size: int) -> int:
+    bits = 1
+    while (1 << bits) < alphabet_size:
+        bits += 1
+    return bits
+
+
+def pack_indices(idx: np.ndarray, alphabet_size: int) -> np.ndarray:
+    """``uint8[N, L]`` residue indices -> the packed wire format of include/flexs_b200.h: ``ceil(log2 A)`` bits per
+    residue, residue i in bits ``[i*b, (i+1)*b)`` of the row's little-endian bit stream, rows padded to whole bytes
+    (``uint8[N, ceil(L*b/8)]``).  Vectorised numpy; the reference never builds anything like it (it ships a float32
+    one-hot of 4*L*A bytes per sequence to TensorFlow, keras_model.py:70-75)."""
+    idx = np.ascontiguousarray(idx, dtype=np.uint8)
+    n, length = idx.shape
+    bits = bits_per_residue(alphabet_size)
+    if idx.size and int(idx.max()) >= alphabet_size:
+        raise ValueError("residue index outside the alphabet")
+    planes = ((idx[:, :, None] >> np.arange(bits, dtype=np.uint8)) & 1).reshape(n, length * bits)
+    return np.packbits(planes, axis=1, bitorder="little")
+
+
+def unpack_indices(packed: np.ndarray, seq_len: int, alphabet_size: int) -> np.ndarray:
+    """Inverse of :func:`pack_indices`."""
+    bits = bits_per_residue(alphabet_size)
+    packed = np.ascontiguousarray(packed, dtype=np.uint8)
+    planes = np.unpackbits(packed, axis=1, bitorder="little")[:, : seq_len * bits].reshape(len(packed), seq_len, bits)
+    return (planes.astype(np.uint16) << np.arange(bits, dtype=np.uint16)).sum(axis=2).astype(np.uint8)
+
+
+def host_threads() -> int:
+    """Threads the C packer may use: the cores this process may run on (torchrun pins OMP_NUM_THREADS=1 per rank, which
+    says nothing about the cores available to a short host-side pass), capped at 16."""
+    import os
+
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(16, n))
+
+
+def pack_sequences(sequences: Union[Sequence[str], np.ndarray], alphabet: str) -> np.ndarray:
+    """Strings (or a ``uint8[N, L]`` index array) -> packed wire format.  A list/tuple of ``str`` goes through ONE
+    multi-threaded C pass over the string objects (csrc/packstr.c ``pack_bits``: alphabet lookup + bit packing, GIL
+    released); everything else through numpy.  ``ValueError`` for a character outside the alphabet, like ``str.index``
+    in the reference (sequence_utils.py:46)."""
+    if isinstance(sequences, np.ndarray) and sequences.dtype == np.uint8:
+        return pack_indices(sequences, len(alphabet))
+    n = len(sequences)
+    bits = bits_per_residue(len(alphabet))
+    pack_bits = _packstr("pack_bits")
+    if pack_bits is not None and n and isinstance(sequences, (list, tuple)) and isinstance(sequences[0], str):
+        width = len(sequences[0])
+        out = np.empty((n, (width * bits + 7) // 8), dtype=np.uint8)
+        pack_bits(sequences, alphabet.encode("latin-1"), out, host_threads())
+        return out
+    return pack_indices(encode_sequences(sequences, alphabet), len(alphabet))
 
 
 def sequences_to_char_array(sequences: Union[Sequence[str], np.ndarray], seq_len: int = None) -> np.ndarray:
@@ -69,7 +128,7 @@ def sequences_to_char_array(sequences: Union[Sequence[str], np.ndarray], seq_len
     else:
         seqs = [str(s) for s in sequences] if not isinstance(sequences[0], str) else sequences
         width = len(seqs[0])
-        pack = _packstr()
+        pack = _packstr("pack")
         if pack is not None and isinstance(seqs, (list, tuple)):
             chars = np.empty((n, width), dtype=np.uint8)
             pack(seqs, chars)  # one C pass over the str objects; raises the same ValueErrors as the route below
