@@ -46,6 +46,11 @@ _SIGNATURES = [
     ("flexs_model_score_host_packed", c_int, [c_void_p, c_void_p, c_int64, c_void_p, POINTER(c_int64)]),
     ("flexs_topk_workspace_bytes", c_int64, [c_int64, c_int]),
     ("flexs_topk_dev", c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    ("flexs_topk_select_workspace_bytes", c_int64, []),
+    ("flexs_topk_select_dev", c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p]),
+    ("flexs_screen_message_bytes", c_int64, [c_int, c_int]),
+    ("flexs_screen_merge_dev", c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("flexs_dedup_workspace_bytes", c_int64, [c_int64]),
     ("flexs_dedup_scores_dev", c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("flexs_mutate_dev", c_int, [c_void_p, c_int64, c_int, c_int, c_float, c_uint64, c_uint64, c_void_p, c_void_p]),
@@ -286,6 +291,28 @@ def topk_dev(d_scores: int, n: int, k: int, index_offset: int, d_index_map: int,
              d_work: int, stream: int = 0) -> None:
     check(lib().flexs_topk_dev(c_void_p(d_scores), n, k, index_offset, c_void_p(d_index_map), c_void_p(d_top_scores),
                                c_void_p(d_top_idx), c_void_p(d_work), c_void_p(stream)), "topk")
+
+
+def topk_select_workspace_bytes() -> int:
+    return int(lib().flexs_topk_select_workspace_bytes())
+
+
+def topk_select_dev(d_scores: int, n: int, k: int, index_offset: int, d_rows: int, row_len: int, unique: bool,
+                    d_top_scores: int, d_top_idx: int, d_top_rows: int, d_status: int, d_work: int, stream: int = 0) -> None:
+    """Single-launch exact top-k (optionally over distinct rows, with the winners' rows); see include/flexs_b200.h."""
+    check(lib().flexs_topk_select_dev(c_void_p(d_scores), n, k, index_offset, c_void_p(d_rows), row_len, 1 if unique else 0,
+                                      c_void_p(d_top_scores), c_void_p(d_top_idx), c_void_p(d_top_rows), c_void_p(d_status),
+                                      c_void_p(d_work), c_void_p(stream)), "topk_select")
+
+
+def screen_message_bytes(k: int, seq_len: int) -> int:
+    return int(lib().flexs_screen_message_bytes(k, seq_len))
+
+
+def screen_merge_dev(d_gathered: int, world: int, k: int, seq_len: int, d_top_scores: int, d_top_idx: int,
+                     d_top_rows: int, stream: int = 0) -> None:
+    check(lib().flexs_screen_merge_dev(c_void_p(d_gathered), world, k, seq_len, c_void_p(d_top_scores), c_void_p(d_top_idx),
+                                       c_void_p(d_top_rows), c_void_p(stream)), "screen_merge")
 
 
 def dedup_workspace_bytes(n: int) -> int:

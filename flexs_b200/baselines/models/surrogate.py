@@ -31,6 +31,9 @@ class B200Surrogate(Model):
 
     #: subclasses set: "cnn" | "mlp"
     kind: str = ""
+    #: lists of at least this many strings travel bit-packed (below it the byte route has one kernel launch less and
+    #: PCIe volume is irrelevant)
+    PACK_MIN_N: int = 4096
 
     def __init__(self, native_kwargs: dict, alphabet: str, name: str, batch_size: int = 256, epochs: int = 20,
                  device: int = 0, seed: Optional[int] = None):
@@ -100,6 +103,12 @@ class B200Surrogate(Model):
             # pre-encoded residue INDICES: the identity alphabet maps index -> index on the device
             chars = np.ascontiguousarray(sequences)
             alphabet = bytes(range(len(self.alphabet)))
+        elif isinstance(sequences, (list, tuple)) and isinstance(sequences[0], str) and n >= self.PACK_MIN_N:
+            # A list of str crosses PCIe bit-packed (2 bits per DNA residue, 5 per amino acid): one multi-threaded C
+            # pass maps the characters through the alphabet and packs them (csrc/packstr.c), the GPU unpacks.
+            if len(sequences[0]) != self.seq_len:
+                raise ValueError(f"{self.name} was built for sequences of length {self.seq_len}, got {len(sequences[0])}")
+            return self.native.score_host_packed(s_utils.pack_sequences(sequences, self.alphabet))
         else:
             chars = s_utils.sequences_to_char_array(sequences)
         if chars.shape[1] != self.seq_len:
@@ -112,6 +121,9 @@ class B200Surrogate(Model):
 
         if idx.dtype != torch.uint8 or idx.dim() != 2 or idx.shape[1] != self.seq_len:
             raise ValueError(f"expected a uint8 [N, {self.seq_len}] CUDA tensor of residue indices")
+        if idx.device.index != self.device:
+            raise ValueError(f"{self.name} lives on cuda:{self.device} but the candidates are on {idx.device} "
+                             f"(build one model per rank with device=LOCAL_RANK)")
         idx = idx.contiguous()
         out = torch.empty(idx.shape[0], dtype=torch.float32, device=idx.device)
         with torch.cuda.device(idx.device):

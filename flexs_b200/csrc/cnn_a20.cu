@@ -76,6 +76,7 @@ struct A20Params {
     int64_t n, n_items;
     fx::CnnOffsets o;
     int L, T, nt3, nc2, nlive2, nc1, idx_slot;
+    long long *prof;  // FLEXS_UMMA_PROF=1: per-CTA wait counters of each role
 };
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -120,7 +121,11 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4 &v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+template <bool PROF>
 __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
+    auto now = [] { return PROF ? clock64() : 0ll; };  // phase timers exist only in the FLEXS_UMMA_PROF=1 instantiation
+    long long pt[4] = {0, 0, 0, 0};
+    const long long t_begin = now();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + S_BAR);
     uint32_t *tmem_addr_s = reinterpret_cast<uint32_t *>(smem_raw + S_TM);
@@ -202,7 +207,9 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
                 }
                 // the gathers are in flight before the ring slot is waited for: their L2 latency is off the
                 // conv2 -> conv1 -> conv2 dependency chain of the two-chunk ring
+                const long long w0 = now();
                 if (g1 >= 2) fxd::mbar_wait(&bar[B_H1E + slot], ((g1 >> 1) - 1) & 1);
+                pt[0] += now() - w0;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     uint4 hi4 = make_uint4(0, 0, 0, 0), lo4 = make_uint4(0, 0, 0, 0);
@@ -240,7 +247,9 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
                 uint4 hi4[4], lo4[4];
                 if (qc < p.nlive2) {
                     const uint32_t a = a2 & 1u;
+                    const long long w0 = now();
                     fxd::mbar_wait(&bar[B_A2F + a], (a2 >> 1) & 1);
+                    pt[0] += now() - w0;
                     tc_fence_after();
                     const int pos = 16 * qc + c - 9;
                     const bool valid = b < nvalid && pos >= 0 && pos < T;
@@ -273,7 +282,9 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) { hi4[j] = make_uint4(0, 0, 0, 0); lo4[j] = make_uint4(0, 0, 0, 0); }
                 }
+                const long long w1 = now();
                 if (g2 >= 3) fxd::mbar_wait(&bar[B_H2E + slot], ((g2 / 3u) - 1) & 1);  // the conv3 tiles reading this slot retired
+                pt[1] += now() - w1;
                 const uint32_t gr = slot * 16u + (uint32_t)c;
                 const uint32_t row = r2_addr + gr * 1024u + (uint32_t)(b * 128);
 #pragma unroll
@@ -309,7 +320,9 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
             const int nvalid = (int)min((int64_t)8, p.n - item * 8);
             for (int q = 0; q < p.nt3; ++q, ++t3) {
                 const uint32_t a = t3 & 1u;
+                const long long w0 = now();
                 fxd::mbar_wait(&bar[B_A3F + a], (t3 >> 1) & 1);
+                pt[0] += now() - w0;
                 tc_fence_after();
                 const bool valid = 16 * q + c < T;
 #pragma unroll
@@ -377,13 +390,18 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
         for (int64_t item = blockIdx.x; item < p.n_items; item += stride) {
             for (int qc = 0; qc < p.nlive2; ++qc, ++g1, ++a2) {
                 const uint32_t s0 = g1 & 1u, a = a2 & 1u;
+                const long long w0 = now();
                 fxd::mbar_wait_warp(&bar[B_H1F + s0], (g1 >> 1) & 1);
                 fxd::mbar_wait_warp(&bar[B_H1F + (s0 ^ 1u)], ((g1 + 1) >> 1) & 1);  // the window ends 4 groups into the next chunk
+                const long long w1 = now();
                 if (a2 >= 2) fxd::mbar_wait_warp(&bar[B_A2E + a], ((a2 >> 1) - 1) & 1);
+                const long long w2 = now();
+                pt[0] += w1 - w0; pt[1] += w2 - w1;
                 tc_fence_after();
                 issue_taps<0, K>(r1_addr + s0 * 16u * 1024u, w2_addr, tmem_base + a * 64u);
                 umma_commit_elect(&bar[B_A2F + a]);
                 umma_commit_elect(&bar[B_H1E + s0]);
+                pt[2] += now() - w2;
             }
             // the item's last h1 chunk is only ever the 4-group tail of the last window: release it as well
             umma_commit_elect(&bar[B_H1E + (g1 & 1u)]);
@@ -395,18 +413,24 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
         for (int64_t item = blockIdx.x; item < p.n_items; item += stride) {
             for (int q = 0; q < p.nt3; ++q, ++t3) {
                 const uint32_t G = g2 + (uint32_t)q, s0 = G % 3u, a = t3 & 1u;
+                const long long w0 = now();
                 fxd::mbar_wait_warp(&bar[B_H2F + s0], (G / 3u) & 1);
                 fxd::mbar_wait_warp(&bar[B_H2F + (G + 1) % 3u], ((G + 1) / 3u) & 1);
+                const long long w1 = now();
                 if (t3 >= 2) fxd::mbar_wait_warp(&bar[B_A3E + a], ((t3 >> 1) - 1) & 1);
+                const long long w2 = now();
                 tc_fence_after();
                 const uint32_t win = r2_addr + s0 * 16u * 1024u, d = tmem_base + 128u + a * 64u;
                 issue_taps<0, KC3 - 2>(win, w3_addr, d);
                 // taps 17 and 18 reach into the third chunk of the window (its first two groups)
+                const long long w3 = now();
                 fxd::mbar_wait_warp(&bar[B_H2F + (G + 2) % 3u], ((G + 2) / 3u) & 1);
+                const long long w4 = now();
                 tc_fence_after();
                 issue_taps<KC3 - 2, KC3>(win, w3_addr, d);
                 umma_commit_elect(&bar[B_A3F + a]);
                 umma_commit_elect(&bar[B_H2E + s0]);
+                pt[0] += w1 - w0; pt[1] += w2 - w1; pt[2] += w4 - w3; pt[3] += (w3 - w2) + (now() - w4);
             }
             // the two trailing chunks of the item were never the first chunk of a window: release them here
             umma_commit_elect(&bar[B_H2E + (g2 + (uint32_t)p.nt3) % 3u]);
@@ -415,6 +439,12 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
         }
     }
     if (xmax > 60000.f) atomicExch(p.overflow_flag, 1);
+    if (PROF && p.prof != nullptr && lane == 0 && (wid == 0 || wid == W_E2 || wid == W_E3 || wid == W_I2 || wid == W_I3)) {
+        const int role = wid == 0 ? 0 : wid == W_E2 ? 1 : wid == W_E3 ? 2 : wid == W_I2 ? 3 : 4;
+        long long *dst = p.prof + (size_t)blockIdx.x * 24 + role * 4;
+        for (int i = 0; i < 4; ++i) dst[i] = pt[i];
+        if (role == 0) p.prof[(size_t)blockIdx.x * 24 + 20] = now() - t_begin;
+    }
     tc_fence_before();
     __syncthreads();
     if (wid == 0) tmem_dealloc(tmem_base, 256);
@@ -503,7 +533,9 @@ int launch_cnn_a20(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out
     p.feat = reinterpret_cast<float *>(ws->ptr);
     p.overflow_flag = ws->flag;
     const size_t smem = (size_t)S_IDX + 2 * p.idx_slot + 1024;
-    FX_CUDA(cudaFuncSetAttribute(cnn_a20_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static const bool prof = std::getenv("FLEXS_UMMA_PROF") && std::getenv("FLEXS_UMMA_PROF")[0] == '1';
+    auto kernel = prof ? cnn_a20_kernel<true> : cnn_a20_kernel<false>;
+    FX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FX_CUDA(cudaMemsetAsync(ws->flag, 0, sizeof(int), s));
     for (int64_t t0 = 0; t0 < n_tiles; t0 += chunk_tiles) {
         const int64_t first = t0 * GS, cnt = std::min(n - first, chunk_tiles * GS);
@@ -514,9 +546,29 @@ int launch_cnn_a20(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out
         for (int mem = 0; mem < m->M; ++mem) {
             p.weights = m->d_weights + (int64_t)mem * m->member_floats;
             p.uw = reinterpret_cast<const unsigned char *>(m->d_a20_w) + (size_t)mem * A20_MEMBER_BYTES;
-            cnn_a20_kernel<<<grid, NT, smem, s>>>(p);
+            p.prof = nullptr;
+            if (prof) {
+                FX_CUDA(cudaMalloc(&p.prof, (size_t)grid * 24 * sizeof(long long)));
+                FX_CUDA(cudaMemset(p.prof, 0, (size_t)grid * 24 * sizeof(long long)));
+            }
+            kernel<<<grid, NT, smem, s>>>(p);
             FX_CUDA(cudaGetLastError());
             m->launches += 1;
+            if (prof) {
+                FX_CUDA(cudaStreamSynchronize(s));
+                std::vector<long long> h((size_t)grid * 24);
+                FX_CUDA(cudaMemcpy(h.data(), p.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+                cudaFree(p.prof);
+                double a[24] = {0};
+                for (int b = 0; b < grid; ++b) for (int i = 0; i < 24; ++i) a[i] += (double)h[(size_t)b * 24 + i] / grid;
+                const double it = (double)p.n_items / grid;  // items per CTA
+                fprintf(stderr, "[a20 prof] n=%lld grid=%d items/CTA=%.1f | cycles per item %.0f (conv3 tiles %d, conv2 tiles %d) | "
+                                "conv1 warp 0: wait ring %.0f | conv2 epilogue: wait MMA %.0f, wait ring %.0f | conv3 epilogue: wait MMA %.0f | "
+                                "conv2 issue: wait h1 %.0f, wait accumulator %.0f, issue %.0f | conv3 issue: wait h2 %.0f, wait accumulator %.0f, "
+                                "wait 3rd chunk %.0f, issue %.0f\n",
+                        (long long)cnt, grid, it, a[20] / it, p.nt3, p.nlive2, a[0] / it, a[4] / it, a[5] / it, a[8] / it, a[12] / it,
+                        a[13] / it, a[14] / it, a[16] / it, a[17] / it, a[18] / it, a[19] / it);
+            }
             rc = launch_dense_tiles(m, p.feat, d_out + first, p.uw, ws->flag, cnt, mem, s);
             if (rc != FLEXS_OK) return rc;
         }

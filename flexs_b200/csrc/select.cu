@@ -1,0 +1,437 @@
+// K3c: single-launch exact top-k, optionally over DISTINCT rows, and the one-kernel merge of the all-gathered
+// per-shard lists of a multi-GPU screen.
+//
+// Replaces the final ranking of propose_sequences — np.argsort(preds)[: -B : -1] over the keys of a dict
+// (adalead.py:157,171-175; cbas_dbas.py:197-201; cmaes.py:112-122) and np.argsort(preds)[::-1][:B] (dyna_ppo.py:310-319)
+// — for batches where the 11-launch radix select of topk.cu plus the hash de-duplication of dedup.cu dominate a step
+// (a 1M-candidate screen of 8-mers: 0.11 ms of selection behind 0.013 ms of scoring).
+//
+// topk_select_kernel (cooperative launch, one CTA per SM): radix select on the 64-bit key
+// (order-preserving score bits << 32 | ~position) with 12-bit digits; a level histograms the keys that match the prefix
+// found so far, a grid barrier, every CTA locates the bin of the wanted rank; the descent stops as soon as "everything
+// above the bin + the bin" fits the candidate buffer (8192 keys) — one level for any score distribution that is not a
+// wall of ties — and the surviving keys are collected.  CTA 0 sorts them (bitonic, shared memory) and writes the winners.
+//
+// Distinct rows ("unique"): the reference ranks dict keys, a sequence proposed twice competes once.  Hashing all n rows
+// (dedup.cu) reads the whole batch two to three times; here the select asks for the best max(k, 4096) rows and
+// de-duplicates only those, in rank order: equal rows have equal scores (the surrogate is deterministic), so the first
+// k distinct rows of the ranked candidates ARE the k best distinct rows of the batch whenever the candidates hold k
+// distinct rows.  When they do not (a batch that is almost all repeats) status[0] = 1 and the caller falls back to
+// dedup.cu + topk.cu; nothing is ever approximated.
+//
+// screen_merge_kernel (one CTA): the gathered messages of all ranks ([k] int64 index | [k] float score | [k][L] rows
+// each) -> sort, drop sequences that reached the top-k of two shards (the copy with the lower global index survives),
+// first k.  Replaces ~25 small launches (unpack, dedup, radix select) behind the collective.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int NT = 512;
+constexpr int CAP = 8192;          // candidate keys the final sort takes
+constexpr int KSLACK = 4096;       // rank asked for in unique mode (room for repeats among the best rows)
+constexpr int NBIN = 4096, DIGIT = 12, NLEVEL = 6;
+
+struct SelWork {
+    unsigned int hist[NLEVEL][NBIN];
+    unsigned int count;
+    unsigned int pad[3];
+};
+
+__device__ __forceinline__ unsigned int ord32(float f) {
+    if (f == 0.f) f = 0.f;  // -0.0 and +0.0 compare equal in numpy
+    unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float unord32(unsigned int k) {
+    unsigned int u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ unsigned long long make_key(float s, unsigned int pos) {
+    return ((unsigned long long)ord32(s) << 32) | (unsigned long long)(0xffffffffu - pos);
+}
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {  // splitmix64 finaliser
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+    x ^= x >> 27; x *= 0x94d049bb133111ebull;
+    x ^= x >> 31;
+    return x;
+}
+__device__ __forceinline__ unsigned long long hash_row(const uint8_t *__restrict__ row, int L) {
+    unsigned long long h = 0x9e3779b97f4a7c15ull ^ (unsigned long long)L;
+    int i = 0;
+    for (; i + 8 <= L; i += 8) {
+        unsigned long long w = 0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) w |= (unsigned long long)row[i + b] << (8 * b);
+        h = mix64(h ^ w);
+    }
+    unsigned long long w = 0;
+    for (int b = 0; i + b < L; ++b) w |= (unsigned long long)row[i + b] << (8 * b);
+    return mix64(h ^ w ^ 0xabcdef);
+}
+__device__ __forceinline__ bool rows_equal(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b, int L) {
+    for (int i = 0; i < L; ++i)
+        if (a[i] != b[i]) return false;
+    return true;
+}
+
+// in-place bitonic sort of `len` (a power of two) 64-bit keys in shared memory; all NT threads call it
+template <bool DESC>
+__device__ void bitonic_sort(unsigned long long *keys, int len) {
+    for (int size = 2; size <= len; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < len / 2; i += NT) {
+                const int lo = 2 * i - (i & (stride - 1));
+                const int hi = lo + stride;
+                const bool up = ((lo & size) == 0);
+                const unsigned long long a = keys[lo], b = keys[hi];
+                if (((a < b) == up) == DESC) { keys[lo] = b; keys[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ int pow2_at_least(int v) {
+    int p = 2;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// Final stage, one CTA.  keys[0 .. m) hold the candidates (any order), keys has room for pow2(m) entries, hs for as many.
+// RowOf(j) -> pointer to the row of the candidate whose key's low word decodes to position j (nullptr semantics: L == 0
+// means "rank rows, not distinct rows").  IdxOf(j) -> the index to report.  Writes k winners (score desc, position asc),
+// their rows when top_rows != nullptr, and returns through *short_of whether fewer than k distinct candidates exist.
+template <class RowOf, class IdxOf>
+__device__ void finalize(unsigned long long *keys, unsigned long long *hs, unsigned short *rank_of, int m, int k, int L,
+                         RowOf row_of, IdxOf idx_of, float *top_scores, long long *top_idx, uint8_t *top_rows,
+                         int *n_found) {
+    __shared__ int s_found, s_scan[NT];
+    const int t = threadIdx.x;
+    const int len = pow2_at_least(max(m, 2));
+    for (int i = m + t; i < len; i += NT) keys[i] = 0ull;
+    __syncthreads();
+    bitonic_sort<true>(keys, len);
+    // keys[0..m) sorted descending: rank order.  keep[i] (bit 63 of hs reused as scratch is avoided: separate pass)
+    int found = 0;
+    if (L == 0) {
+        found = min(m, k);
+        for (int i = t; i < found; i += NT) rank_of[i] = (unsigned short)i;
+        __syncthreads();
+    } else {
+        // de-duplicate growing prefixes of the ranking until k distinct rows are found (the first prefix nearly always is)
+        for (int P = min(m, 1024);; P = min(m, P * 2)) {
+            const int plen = pow2_at_least(max(P, 2));
+            for (int i = t; i < plen; i += NT) {
+                if (i < P) {
+                    const unsigned int pos = 0xffffffffu - (unsigned int)(keys[i] & 0xffffffffu);
+                    hs[i] = (hash_row(row_of(pos), L) & ~0x1fffull) | (unsigned long long)i;   // 51 hash bits | rank (13 bits)
+                } else hs[i] = ~0ull;
+            }
+            __syncthreads();
+            bitonic_sort<false>(hs, plen);   // ascending: equal hashes adjacent, by rank
+            // a candidate is a repeat iff an earlier member of its hash run has the same row (the run is walked from its
+            // head: a batch of identical rows costs one comparison per row, not a quadratic number)
+            for (int i = t; i < P; i += NT) {
+                const unsigned long long e = hs[i];
+                const int rk = (int)(e & 0x1fffull);
+                bool dup = false;
+                int j = i;
+                while (j > 0 && (hs[j - 1] >> 13) == (e >> 13)) --j;
+                if (j < i) {
+                    const uint8_t *mine = row_of(0xffffffffu - (unsigned int)(keys[rk] & 0xffffffffu));
+                    for (; j < i && !dup; ++j) {
+                        const int rj = (int)(hs[j] & 0x1fffull);
+                        dup = rows_equal(mine, row_of(0xffffffffu - (unsigned int)(keys[rj] & 0xffffffffu)), L);
+                    }
+                }
+                rank_of[rk] = dup ? 1 : 0;   // scratch: repeat flag by rank
+            }
+            __syncthreads();
+            // ordered compaction of the survivors: block scan over ranks, each thread owns a contiguous span
+            const int span = (P + NT - 1) / NT, lo = t * span, hi = min(P, lo + span);
+            int mine_cnt = 0;
+            for (int i = lo; i < hi; ++i) mine_cnt += rank_of[i] ? 0 : 1;
+            s_scan[t] = mine_cnt;
+            __syncthreads();
+            for (int off = 1; off < NT; off <<= 1) {
+                const int v = (t >= off) ? s_scan[t - off] : 0;
+                __syncthreads();
+                s_scan[t] += v;
+                __syncthreads();
+            }
+            if (t == NT - 1) s_found = s_scan[t];
+            int base = s_scan[t] - mine_cnt;
+            __syncthreads();
+            // survivors' ranks into hs (as plain ints, reusing the buffer after the scan consumed the flags)
+            unsigned int *surv = reinterpret_cast<unsigned int *>(hs);
+            __syncthreads();
+            for (int i = lo; i < hi; ++i)
+                if (!rank_of[i] && base < k) surv[base++] = (unsigned int)i;
+            __syncthreads();
+            found = min(s_found, k);
+            if (found >= k || P >= m) {
+                for (int i = t; i < found; i += NT) rank_of[i] = (unsigned short)surv[i];
+                __syncthreads();
+                break;
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = t; i < k; i += NT) {
+        if (i < found) {
+            const unsigned long long key = keys[rank_of[i]];
+            const unsigned int pos = 0xffffffffu - (unsigned int)(key & 0xffffffffu);
+            top_scores[i] = unord32((unsigned int)(key >> 32));
+            top_idx[i] = idx_of(pos);
+        } else {
+            top_scores[i] = -INFINITY;
+            top_idx[i] = -1;
+        }
+    }
+    if (top_rows != nullptr && L > 0) {
+        for (int i = t; i < k * L; i += NT) {
+            const int w = i / L, b = i - w * L;
+            uint8_t v = 0;
+            if (w < found) v = row_of(0xffffffffu - (unsigned int)(keys[rank_of[w]] & 0xffffffffu))[b];
+            top_rows[i] = v;
+        }
+    }
+    if (t == 0) *n_found = found;
+}
+
+struct SelParams {
+    const float *scores;
+    long long n;
+    int k, unique;
+    long long index_offset;
+    const uint8_t *rows;
+    int row_len;
+    float *top_scores;
+    long long *top_idx;
+    uint8_t *top_rows;
+    int *status;          // [0] = 1: fewer than k distinct rows among the candidates although the batch has more rows
+    SelWork *work;
+    unsigned long long *cand;
+};
+
+__global__ void __launch_bounds__(NT, 1) topk_select_kernel(const SelParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);       // CAP keys; first NBIN words double as the level histogram
+    unsigned long long *hs = keys + CAP;
+    unsigned short *rank_of = reinterpret_cast<unsigned short *>(hs + CAP);
+    unsigned int *sh = reinterpret_cast<unsigned int *>(smem_raw);
+    __shared__ unsigned int s_bin, s_above, s_cnt;
+    __shared__ unsigned int s_part[NT];
+    cg::grid_group grid = cg::this_grid();
+    const int t = threadIdx.x;
+    const long long stride = (long long)gridDim.x * NT;
+    const long long gtid = (long long)blockIdx.x * NT + t;
+    SelWork *w = p.work;
+
+    // the workspace cleans itself: no separate init launch
+    for (long long i = gtid; i < (long long)(NLEVEL * NBIN); i += stride) (&w->hist[0][0])[i] = 0;
+    if (gtid == 0) w->count = 0;
+    grid.sync();
+
+    const unsigned int want = (unsigned int)min(p.n, (long long)(p.unique ? max(p.k, KSLACK) : p.k));
+    unsigned long long prefix = 0;
+    int bits_done = 0;
+    unsigned int krem = want, above_total = 0;
+    unsigned long long thr_prefix = 0;
+    int thr_bits = 0;
+    if (p.n > 0) {
+        for (int level = 0; level < NLEVEL; ++level) {
+            const int dbits = min(DIGIT, 64 - bits_done);
+            const int shift = 64 - bits_done - dbits;
+            for (int i = t; i < NBIN; i += NT) sh[i] = 0;
+            __syncthreads();
+            for (long long i = gtid; i < p.n; i += stride) {
+                const unsigned long long key = make_key(__ldg(p.scores + i), (unsigned int)i);
+                if (bits_done > 0 && (key >> (64 - bits_done)) != prefix) continue;
+                atomicAdd(&sh[(unsigned int)(key >> shift) & ((1u << dbits) - 1u)], 1u);
+            }
+            __syncthreads();
+            for (int i = t; i < NBIN; i += NT)
+                if (sh[i]) atomicAdd(&w->hist[level][i], sh[i]);
+            grid.sync();
+            // every CTA finds the bin that holds rank `krem` counting from the top: suffix sums over 4096 bins,
+            // 8 consecutive bins per thread
+            const unsigned int *h = w->hist[level];
+            constexpr int PER = NBIN / NT;
+            unsigned int loc[PER], tot = 0;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) { loc[i] = __ldcg(h + t * PER + i); tot += loc[i]; }
+            s_part[t] = tot;
+            __syncthreads();
+            // suffix[t] = sum of s_part[t+1 ..]: count in all bins above this thread's span
+            for (int off = 1; off < NT; off <<= 1) {
+                const unsigned int v = (t + off < NT) ? s_part[t + off] : 0u;
+                __syncthreads();
+                s_part[t] += v;
+                __syncthreads();
+            }
+            unsigned int cum = s_part[t] - tot;  // bins above my span
+            if (cum < krem && cum + tot >= krem) {
+#pragma unroll
+                for (int i = PER - 1; i >= 0; --i) {
+                    if (cum + loc[i] >= krem) { s_bin = (unsigned int)(t * PER + i); s_above = cum; s_cnt = loc[i]; break; }
+                    cum += loc[i];
+                }
+            }
+            __syncthreads();
+            const unsigned int b = s_bin, above = s_above, cnt = s_cnt;
+            __syncthreads();
+            thr_prefix = (prefix << dbits) | b;
+            thr_bits = bits_done + dbits;
+            if (above_total + above + cnt <= (unsigned int)CAP || thr_bits == 64) break;
+            prefix = thr_prefix; bits_done = thr_bits; krem -= above; above_total += above;
+        }
+        // collect every key at or above the threshold prefix
+        for (long long i = gtid; i < p.n; i += stride) {
+            const unsigned long long key = make_key(__ldg(p.scores + i), (unsigned int)i);
+            if ((key >> (64 - thr_bits)) >= thr_prefix) {
+                const unsigned int slot = atomicAdd(&w->count, 1u);
+                if (slot < (unsigned int)CAP) p.cand[slot] = key;
+            }
+        }
+    }
+    grid.sync();
+    if (blockIdx.x != 0) return;
+    const int m = (int)min(__ldcg(&w->count), (unsigned int)CAP);
+    for (int i = t; i < m; i += NT) keys[i] = __ldcg(p.cand + i);
+    __syncthreads();
+    __shared__ int s_nfound;
+    const uint8_t *rows = p.rows;
+    const int L = (p.unique && rows != nullptr) ? p.row_len : 0;
+    const long long off = p.index_offset;
+    finalize(keys, hs, rank_of, m, p.k, L,
+             [rows, L2 = p.row_len](unsigned int pos) { return rows + (size_t)pos * L2; },
+             [off](unsigned int pos) { return (long long)pos + off; },
+             p.top_scores, p.top_idx, p.top_rows, &s_nfound);
+    if (rows == nullptr && p.top_rows != nullptr)   // an empty shard still sends a well-defined message
+        for (int i = t; i < p.k * p.row_len; i += NT) p.top_rows[i] = 0;
+    // rows of the winners are wanted even when ranking rows rather than distinct rows
+    if (!p.unique && p.top_rows != nullptr && p.rows != nullptr) {
+        __syncthreads();
+        for (int i = t; i < p.k * p.row_len; i += NT) {
+            const int wi = i / p.row_len, b = i - wi * p.row_len;
+            const long long gi = p.top_idx[wi];
+            p.top_rows[i] = gi >= 0 ? rows[(size_t)(gi - off) * p.row_len + b] : (uint8_t)0;
+        }
+    }
+    __syncthreads();
+    if (t == 0 && p.status != nullptr)
+        p.status[0] = (p.unique && s_nfound < p.k && (long long)m < p.n) ? 1 : 0;
+}
+
+struct MergeParams {
+    const unsigned char *gathered;   // world messages
+    int world, k, row_len;
+    long long msg_bytes, off_score, off_rows;
+    float *top_scores;
+    long long *top_idx;
+    uint8_t *top_rows;
+};
+
+__global__ void __launch_bounds__(NT, 1) screen_merge_kernel(const MergeParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);
+    unsigned long long *hs = keys + CAP;
+    unsigned short *rank_of = reinterpret_cast<unsigned short *>(hs + CAP);
+    __shared__ int s_m, s_nfound;
+    const int t = threadIdx.x, total = p.world * p.k;
+    if (t == 0) s_m = 0;
+    __syncthreads();
+    // position j = rank-major order of the gathered lists: shards own increasing index ranges and each list is sorted
+    // (score desc, index asc), so ties by position are ties by global index
+    for (int j = t; j < total; j += NT) {
+        const int r = j / p.k, i = j - r * p.k;
+        const unsigned char *msg = p.gathered + (size_t)r * p.msg_bytes;
+        const long long gi = reinterpret_cast<const long long *>(msg)[i];
+        if (gi < 0) continue;   // an absent winner (fewer than k candidates on that shard)
+        const float sc = reinterpret_cast<const float *>(msg + p.off_score)[i];
+        keys[atomicAdd(&s_m, 1)] = make_key(sc, (unsigned int)j);
+    }
+    __syncthreads();
+    const unsigned char *g = p.gathered;
+    const int k = p.k, L = p.row_len;
+    const long long mb = p.msg_bytes, orow = p.off_rows;
+    finalize(keys, hs, rank_of, s_m, k, L,
+             [g, k, L, mb, orow](unsigned int j) {
+                 const int r = (int)j / k, i = (int)j - r * k;
+                 return reinterpret_cast<const uint8_t *>(g + (size_t)r * mb + orow + (size_t)i * L);
+             },
+             [g, k, mb](unsigned int j) {
+                 const int r = (int)j / k, i = (int)j - r * k;
+                 return reinterpret_cast<const long long *>(g + (size_t)r * mb)[i];
+             },
+             p.top_scores, p.top_idx, p.top_rows, &s_nfound);
+}
+
+constexpr size_t FINAL_SMEM = (size_t)CAP * 8 * 2 + (size_t)CAP * 2;
+
+}  // namespace
+
+extern "C" {
+
+int64_t flexs_topk_select_workspace_bytes(void) { return (int64_t)((sizeof(SelWork) + 255) / 256 * 256 + (size_t)CAP * 8); }
+
+int flexs_topk_select_dev(const float *d_scores, int64_t n, int k, int64_t index_offset, const uint8_t *d_rows,
+                          int row_len, int unique, float *d_top_scores, int64_t *d_top_idx, uint8_t *d_top_rows,
+                          int *d_status, void *d_work, void *stream) {
+    FX_REQUIRE(k >= 1 && k <= 4096, "k must be in [1, 4096]");
+    FX_REQUIRE(n >= 0 && n < (1ll << 32), "n must be below 2^32");
+    FX_REQUIRE(d_top_scores && d_top_idx && d_work, "null buffer");
+    FX_REQUIRE(n == 0 || d_scores, "null scores");
+    FX_REQUIRE(!unique || n == 0 || (d_rows && row_len >= 1), "unique ranking needs the rows");
+    FX_REQUIRE(d_top_rows == nullptr || n == 0 || (d_rows && row_len >= 1), "winner rows need the rows");
+    SelParams p;
+    p.scores = d_scores; p.n = n; p.k = k; p.unique = unique ? 1 : 0; p.index_offset = index_offset;
+    p.rows = n > 0 ? d_rows : nullptr; p.row_len = row_len;
+    p.top_scores = d_top_scores; p.top_idx = reinterpret_cast<long long *>(d_top_idx); p.top_rows = d_top_rows;
+    p.status = d_status;
+    p.work = reinterpret_cast<SelWork *>(d_work);
+    p.cand = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(d_work) + (sizeof(SelWork) + 255) / 256 * 256);
+    int dev = 0, sms = 148;
+    FX_CUDA(cudaGetDevice(&dev));
+    FX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    FX_CUDA(cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FINAL_SMEM));
+    // a small batch does not need the whole GPU; every CTA of a cooperative launch must be resident (1 per SM here)
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + NT * 8 - 1) / (NT * 8), sms));
+    void *args[] = {&p};
+    FX_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(topk_select_kernel), dim3(grid), dim3(NT), args, FINAL_SMEM,
+                                        (cudaStream_t)stream));
+    return FLEXS_OK;
+}
+
+int64_t flexs_screen_message_bytes(int k, int seq_len) {
+    if (k < 1 || seq_len < 0) return FLEXS_EINVAL;
+    return ((int64_t)k * 12 + (int64_t)k * seq_len + 15) / 16 * 16;
+}
+
+int flexs_screen_merge_dev(const void *d_gathered, int world, int k, int seq_len, float *d_top_scores,
+                           int64_t *d_top_idx, uint8_t *d_top_rows, void *stream) {
+    FX_REQUIRE(world >= 1 && k >= 1 && seq_len >= 0, "bad sizes");
+    FX_REQUIRE((int64_t)world * k <= CAP, "world * k must not exceed 8192");
+    FX_REQUIRE(d_gathered && d_top_scores && d_top_idx, "null buffer");
+    MergeParams p;
+    p.gathered = reinterpret_cast<const unsigned char *>(d_gathered);
+    p.world = world; p.k = k; p.row_len = seq_len;
+    p.msg_bytes = flexs_screen_message_bytes(k, seq_len);
+    p.off_score = (long long)k * 8;
+    p.off_rows = (long long)k * 12;
+    p.top_scores = d_top_scores; p.top_idx = reinterpret_cast<long long *>(d_top_idx); p.top_rows = d_top_rows;
+    FX_CUDA(cudaFuncSetAttribute(screen_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FINAL_SMEM));
+    screen_merge_kernel<<<1, NT, FINAL_SMEM, (cudaStream_t)stream>>>(p);
+    FX_CUDA(cudaGetLastError());
+    return FLEXS_OK;
+}
+
+}  // extern "C"

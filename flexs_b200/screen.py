@@ -3,11 +3,12 @@
 This is the multi-GPU form of the selection every explorer ends with
 (``np.argsort(preds)[: -B : -1]``, adalead.py:171-175 / cbas_dbas.py:197-201 / cmaes.py:117-122, and
 ``[::-1][:B]``, dyna_ppo.py:315-319).  Candidates are independent, so rank r of G scores the contiguous
-block ``[r*N/G, (r+1)*N/G)`` with the fused surrogate kernel, drops repeated sequences (the reference ranks the
-keys of a dict: ``flexs_dedup_scores_dev``), selects its own top-k with ``flexs_topk_dev`` (indices offset to global
-positions) and the ranks exchange ONE ``all_gather`` of ``k`` (score, index, sequence) triples — ``G*k*(16+L)``
-bytes over NVLink — before every rank runs the same final merge, which de-duplicates once more (a sequence may have
-reached the top-k of two shards).  There is no other collective on the path; weights are replicated.
+block ``[r*N/G, (r+1)*N/G)`` with the fused surrogate kernel and selects its own top-k over DISTINCT sequences (the
+reference ranks the keys of a dict) with one launch of ``flexs_topk_select_dev``, which writes (global index, score,
+sequence) triples straight into the rank's message; the ranks exchange ONE ``all_gather`` of those messages —
+``G*k*(12+L)`` bytes over NVLink — and every rank runs the same one-launch merge (``flexs_screen_merge_dev``), which
+de-duplicates once more (a sequence may have reached the top-k of two shards).  There is no other collective on the
+path; weights are replicated.
 
 One process per GPU (``torch.distributed``, backend ``nccl``); the helpers that only move tensors work on
 any backend, which is how the CPU test-suite exercises them with ``gloo`` at world size 2.
@@ -26,50 +27,57 @@ def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
-def _seq_words(k: int, seq_len: int) -> int:
-    """int64 words that hold ``k`` sequences of ``seq_len`` bytes."""
-    return (k * seq_len + 7) // 8
+def message_bytes(k: int, seq_len: int) -> int:
+    """Bytes of one rank's message: ``[k] int64 global index | [k] float32 score | [k][seq_len] uint8 rows``, padded to
+    16 bytes (mirrors ``flexs_screen_message_bytes``; pure arithmetic so the CPU tests can use it)."""
+    return (k * 12 + k * seq_len + 15) // 16 * 16
 
 
-def pack_topk(scores, idx, seqs=None):
-    """``float32[k]`` scores + ``int64[k]`` indices (+ ``uint8[k, L]`` winner sequences) -> one int64 message:
-    indices, score bits, then the sequence bytes padded to a whole number of words."""
+def message_views(msg, k: int, seq_len: int):
+    """``(idx int64[k], scores float32[k], rows uint8[k, seq_len])`` views INTO a uint8 message buffer (any device):
+    ``flexs_topk_select_dev`` writes its three outputs straight through them, nothing is packed afterwards."""
     import torch
 
-    k = scores.shape[0]
-    extra = 0 if seqs is None else _seq_words(k, seqs.shape[1])
-    out = torch.zeros(2 * k + extra, dtype=torch.int64, device=scores.device)
-    out[:k] = idx
-    out[k:2 * k] = scores.contiguous().view(torch.int32).to(torch.int64)
-    if seqs is not None:
-        out[2 * k:].view(torch.uint8)[: k * seqs.shape[1]] = seqs.contiguous().view(-1)
-    return out
+    idx = msg[: 8 * k].view(torch.int64)
+    scores = msg[8 * k: 12 * k].view(torch.float32)
+    rows = msg[12 * k: 12 * k + k * seq_len].view(k, seq_len) if seq_len else None
+    return idx, scores, rows
 
 
-def unpack_topk(gathered, world: int, k: int, seq_len: int = 0):
-    """Inverse of :func:`pack_topk` for the concatenation of ``world`` messages:
-    ``(scores[world*k], idx[world*k])`` and, with ``seq_len``, the ``uint8[world*k, seq_len]`` sequences."""
-    import torch
-
-    extra = _seq_words(k, seq_len) if seq_len else 0
-    g = gathered.view(world, 2 * k + extra)
-    idx = g[:, :k].reshape(-1).contiguous()
-    scores = g[:, k:2 * k].reshape(-1).to(torch.int32).contiguous().view(torch.float32)
-    if not seq_len:
-        return scores, idx
-    seqs = g[:, 2 * k:].contiguous().view(torch.uint8).view(world, extra * 8)[:, : k * seq_len].reshape(world * k, seq_len)
-    return scores, idx, seqs.contiguous()
-
-
-def all_gather_topk(message, group=None):
-    """The single collective of the path: every rank receives every rank's packed top-k list."""
+def all_gather_messages(msg, group=None):
+    """The single collective of the path: every rank receives every rank's message (rank-major)."""
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
-    out = torch.empty(world * message.numel(), dtype=message.dtype, device=message.device)
-    dist.all_gather_into_tensor(out, message, group=group)
+    out = torch.empty(world * msg.numel(), dtype=msg.dtype, device=msg.device)
+    dist.all_gather_into_tensor(out, msg, group=group)
     return out
+
+
+def merge_reference(gathered: np.ndarray, world: int, k: int, seq_len: int):
+    """numpy statement of what ``flexs_screen_merge_dev`` computes from the gathered messages: rank by (score desc,
+    gathered position asc), drop absent entries (index < 0) and — with ``seq_len`` — later copies of a sequence, keep k.
+    Used by the CPU tests (gloo) and as the checker of the GPU tests."""
+    mb = message_bytes(k, seq_len)
+    g = np.ascontiguousarray(gathered, dtype=np.uint8).reshape(world, mb)
+    idx = np.concatenate([g[r, : 8 * k].view(np.int64) for r in range(world)])
+    sc = np.concatenate([g[r, 8 * k: 12 * k].view(np.float32) for r in range(world)])
+    rows = np.concatenate([g[r, 12 * k: 12 * k + k * seq_len].reshape(k, seq_len) for r in range(world)]) if seq_len else None
+    pos = np.flatnonzero(idx >= 0)
+    order = pos[np.lexsort((pos, -sc[pos].astype(np.float64)))]
+    out, seen = [], set()
+    for j in order:
+        if rows is not None:
+            key = rows[j].tobytes()
+            if key in seen:
+                continue
+            seen.add(key)
+        out.append(j)
+        if len(out) == k:
+            break
+    out = np.array(out, dtype=np.int64)
+    return sc[out], idx[out], (rows[out] if rows is not None else None)
 
 
 class VirtualScreen:
@@ -77,6 +85,10 @@ class VirtualScreen:
 
     ``k`` is the number of winners to return: explorers that reproduce the reference's ``[: -B : -1]``
     slice pass ``sequences_batch_size - 1``.
+
+    Per call and rank: the surrogate's forward launches, ONE selection launch (``flexs_topk_select_dev``: top-k over
+    distinct sequences, winners' rows included, written straight into the message), ONE ``all_gather`` of
+    ``message_bytes(k, L)`` bytes per rank, ONE merge launch (``flexs_screen_merge_dev``).  Buffers are cached.
     """
 
     def __init__(self, model, k: int, group=None, unique: bool = True):
@@ -86,6 +98,8 @@ class VirtualScreen:
         if not hasattr(model, "get_fitness_device"):
             raise TypeError("VirtualScreen needs a B200 surrogate (CNN, MLP or an Ensemble of identical ones)")
         self.model, self.k, self.group, self.unique = model, int(k), group, bool(unique)
+        self._buf = {}
+        self.fallbacks = 0   # selections that needed the full hash de-duplication (almost-all-repeats batches)
 
     def _world(self) -> Tuple[int, int]:
         import torch.distributed as dist
@@ -94,88 +108,85 @@ class VirtualScreen:
             return dist.get_rank(self.group), dist.get_world_size(self.group)
         return 0, 1
 
-    def local_topk(self, idx, index_offset: int = 0):
-        """Score ``uint8[n, L]`` residue indices resident on this GPU and select the local top-k.
-
-        Returns ``(top_scores[k], top_idx[k], scores[n])`` (CUDA tensors, no host sync).  Charges
-        ``model.cost`` like ``get_fitness`` does.
-        """
+    def _buffers(self, device, seq_len: int, world: int):
         import torch
 
         from flexs_b200 import _native
 
+        key = (device, seq_len, world)
+        if key not in self._buf:
+            mb = message_bytes(self.k, seq_len)
+            self._buf[key] = dict(
+                msg=torch.zeros(mb, dtype=torch.uint8, device=device),
+                work=torch.empty(_native.topk_select_workspace_bytes(), dtype=torch.uint8, device=device),
+                status=torch.zeros(1, dtype=torch.int32, device=device),
+                gathered=torch.empty(world * mb, dtype=torch.uint8, device=device) if world > 1 else None,
+                fin=torch.zeros(mb, dtype=torch.uint8, device=device) if world > 1 else None)
+        return self._buf[key]
+
+    def local_topk(self, idx, index_offset: int = 0, check: bool = True):
+        """Score ``uint8[n, L]`` residue indices resident on this GPU and select the local top-k.
+
+        Returns ``(top_scores[k], top_idx[k], scores[n])`` (CUDA tensors; the first two are views into this rank's
+        message, whose third part holds the winners' rows).  Charges ``model.cost`` like ``get_fitness`` does.
+        ``check`` reads one int back (a stream sync) to learn whether the lazy de-duplication found k distinct
+        sequences among the best rows and, if not, re-selects after hashing the whole batch; callers that must not
+        sync pass ``check=False`` and inspect ``last_status`` themselves."""
+        import torch
+
+        from flexs_b200 import _native
+
+        idx = idx.contiguous()
         scores = self.model.get_fitness_device(idx)
-        n = int(scores.shape[0])
+        n, L = int(idx.shape[0]), int(idx.shape[1])
         dev = scores.device
-        work = torch.empty(_native.topk_workspace_bytes(n, self.k), dtype=torch.uint8, device=dev)
-        top_s = torch.empty(self.k, dtype=torch.float32, device=dev)
-        top_i = torch.empty(self.k, dtype=torch.int64, device=dev)
+        buf = self._buffers(dev, L, self._world()[1])
+        top_i, top_s, top_rows = message_views(buf["msg"], self.k, L)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream().cuda_stream
-            ranked = scores
-            if self.unique:
-                idx = idx.contiguous()
+            _native.topk_select_dev(scores.data_ptr(), n, self.k, index_offset, idx.data_ptr(), L, self.unique,
+                                    top_s.data_ptr(), top_i.data_ptr(), top_rows.data_ptr(), buf["status"].data_ptr(),
+                                    buf["work"].data_ptr(), stream)
+            self.last_status = buf["status"]
+            if check and self.unique and int(buf["status"].item()) != 0:
+                # almost every row of the batch is a repeat: hash all rows (dedup.cu), then select among first occurrences
+                self.fallbacks += 1
                 ranked = torch.empty_like(scores)
                 dwork = torch.empty(_native.dedup_workspace_bytes(n), dtype=torch.uint8, device=dev)
-                _native.dedup_scores_dev(idx.data_ptr(), n, int(idx.shape[1]), scores.data_ptr(), ranked.data_ptr(),
-                                         dwork.data_ptr(), stream)
-            _native.topk_dev(ranked.data_ptr(), n, self.k, index_offset, 0, top_s.data_ptr(), top_i.data_ptr(),
-                             work.data_ptr(), stream)
-            if self.unique:
-                top_i = torch.where(torch.isinf(top_s), torch.full_like(top_i, -1), top_i)  # fewer than k distinct
+                _native.dedup_scores_dev(idx.data_ptr(), n, L, scores.data_ptr(), ranked.data_ptr(), dwork.data_ptr(), stream)
+                _native.topk_select_dev(ranked.data_ptr(), n, self.k, index_offset, idx.data_ptr(), L, False,
+                                        top_s.data_ptr(), top_i.data_ptr(), top_rows.data_ptr(), 0, buf["work"].data_ptr(), stream)
+                absent = torch.isinf(top_s) & (top_s < 0)     # repeats carry -inf: fewer than k distinct sequences
+                top_i.masked_fill_(absent, -1)
         return top_s, top_i, scores
 
-    def merge(self, top_s, top_i, top_seqs=None):
-        """All-gather the per-shard lists and reduce them to the global top-k (identical on every rank).
-
-        Shards own increasing index ranges and each list is already ordered (score desc, index asc), so
-        breaking score ties by position in the gathered array equals breaking them by global index.  With
-        ``top_seqs`` (the winners' residues, ``uint8[k, L]``) the gathered list is de-duplicated first: the copy
-        from the lower rank, i.e. the lower global index, survives."""
+    def merge(self, seq_len: int, device):
+        """All-gather this rank's message and reduce the ``world`` lists to the global top-k (identical on every
+        rank): returns ``(scores[k], indices[k])`` views of the merged message."""
         import torch
 
         from flexs_b200 import _native
 
         rank, world = self._world()
+        buf = self._buffers(device, seq_len, world)
         if world == 1:
+            top_i, top_s, _ = message_views(buf["msg"], self.k, seq_len)
             return top_s, top_i
-        if top_seqs is None:
-            gathered = all_gather_topk(pack_topk(top_s, top_i), self.group)
-            g_scores, g_idx = unpack_topk(gathered, world, self.k)
-        else:
-            L = int(top_seqs.shape[1])
-            gathered = all_gather_topk(pack_topk(top_s, top_i, top_seqs), self.group)
-            g_scores, g_idx, g_seqs = unpack_topk(gathered, world, self.k, L)
-            m = world * self.k
-            dwork = torch.empty(_native.dedup_workspace_bytes(m), dtype=torch.uint8, device=g_scores.device)
-            with torch.cuda.device(g_scores.device):
-                _native.dedup_scores_dev(g_seqs.data_ptr(), m, L, g_scores.data_ptr(), g_scores.data_ptr(),
-                                         dwork.data_ptr(), torch.cuda.current_stream().cuda_stream)
-        dev = g_scores.device
-        work = torch.empty(_native.topk_workspace_bytes(world * self.k, self.k), dtype=torch.uint8, device=dev)
-        fin_s = torch.empty(self.k, dtype=torch.float32, device=dev)
-        fin_i = torch.empty(self.k, dtype=torch.int64, device=dev)
-        with torch.cuda.device(dev):
-            _native.topk_dev(g_scores.data_ptr(), world * self.k, self.k, 0, g_idx.data_ptr(), fin_s.data_ptr(),
-                             fin_i.data_ptr(), work.data_ptr(), torch.cuda.current_stream().cuda_stream)
-        if top_seqs is not None:
-            fin_i = torch.where(torch.isinf(fin_s), torch.full_like(fin_i, -1), fin_i)
+        import torch.distributed as dist
+
+        dist.all_gather_into_tensor(buf["gathered"], buf["msg"], group=self.group)   # the single collective of the path
+        fin_i, fin_s, fin_rows = message_views(buf["fin"], self.k, seq_len)
+        with torch.cuda.device(device):
+            _native.screen_merge_dev(buf["gathered"].data_ptr(), world, self.k, seq_len if self.unique else 0,
+                                     fin_s.data_ptr(), fin_i.data_ptr(), fin_rows.data_ptr() if self.unique else 0,
+                                     torch.cuda.current_stream().cuda_stream)
         return fin_s, fin_i
 
-    def screen_indices(self, idx_local, index_offset: int = 0):
+    def screen_indices(self, idx_local, index_offset: int = 0, check: bool = True):
         """``idx_local``: this rank's shard (CUDA ``uint8[n_local, L]``) whose first row has global index
         ``index_offset``.  Returns the global ``(scores[k], indices[k])`` as CUDA tensors."""
-        top_s, top_i, _ = self.local_topk(idx_local, index_offset)
-        if not self.unique or self._world()[1] == 1:
-            return self.merge(top_s, top_i)
-        if idx_local.shape[0] == 0:                         # an empty shard (fewer candidates than ranks)
-            import torch
-
-            seqs = torch.zeros((self.k, idx_local.shape[1]), dtype=torch.uint8, device=idx_local.device)
-        else:
-            rows = (top_i - index_offset).clamp(min=0)      # absent winners (-1) borrow row 0; their score is -inf
-            seqs = idx_local[rows].contiguous()
-        return self.merge(top_s, top_i, seqs)
+        self.local_topk(idx_local, index_offset, check)
+        return self.merge(int(idx_local.shape[1]), idx_local.device)
 
     def screen(self, sequences, alphabet: Optional[str] = None):
         """Host entry: every rank passes the SAME full candidate list (strings or ``uint8[N, L]`` indices);
@@ -191,7 +202,10 @@ class VirtualScreen:
             else s_utils.encode_sequences(sequences, alphabet)
         rank, world = self._world()
         start, stop = shard_bounds(len(idx), rank, world)
-        device = torch.device("cuda", torch.cuda.current_device())
+        dev_index = getattr(self.model, "device", None)
+        if dev_index is None and hasattr(self.model, "models"):
+            dev_index = getattr(self.model.models[0], "device", None)
+        device = torch.device("cuda", torch.cuda.current_device() if dev_index is None else dev_index)
         shard = torch.from_numpy(np.ascontiguousarray(idx[start:stop])).to(device)
         top_s, top_i = self.screen_indices(shard, start)
         top_s, top_i = top_s.cpu().numpy(), top_i.cpu().numpy()

@@ -167,6 +167,33 @@ int64_t flexs_dedup_workspace_bytes(int64_t n);
 int flexs_dedup_scores_dev(const uint8_t *d_idx, int64_t n, int seq_len, const float *d_scores,
                            float *d_scores_out, void *d_work, void *stream);
 
+/* ---- K3c: single-launch selection and the multi-GPU merge -----------------------------------
+ * flexs_topk_select_dev is flexs_topk_dev (+ flexs_dedup_scores_dev when `unique`) as ONE
+ * cooperative kernel launch: radix select with 12-bit digits that stops as soon as the candidates
+ * fit a one-CTA sort, then — for `unique` — de-duplication of the best rows only, in rank order
+ * (equal rows must carry equal scores, which a deterministic surrogate guarantees).  Same result
+ * as the two-call path, bit for bit; when the best max(k, 4096) rows do not hold k distinct
+ * sequences although the batch has more rows, d_status[0] = 1 and the outputs are incomplete: the
+ * caller then runs flexs_dedup_scores_dev + flexs_topk_dev (d_status may be NULL when !unique).
+ * d_rows uint8[n, row_len] (may be NULL when !unique and d_top_rows is NULL); d_top_rows (may be
+ * NULL) receives the winners' rows, uint8[k, row_len].  d_work: flexs_topk_select_workspace_bytes().
+ *
+ * A rank's message of a sharded screen (screen.py; adalead.py:171-175 over G shards) is
+ *   [k] int64 global index | [k] float32 score | [k][seq_len] uint8 rows, padded to 16 bytes
+ * (flexs_screen_message_bytes); the three d_top_* pointers of flexs_topk_select_dev can point
+ * straight into it.  flexs_screen_merge_dev takes the all-gathered messages of `world` ranks
+ * (rank-major) and returns the global top-k, dropping a sequence that reached the list of two
+ * shards (the lower global index survives; seq_len = 0: no de-duplication).  world * k <= 8192. */
+int64_t flexs_topk_select_workspace_bytes(void);
+int flexs_topk_select_dev(const float *d_scores, int64_t n, int k, int64_t index_offset,
+                          const uint8_t *d_rows, int row_len, int unique, float *d_top_scores,
+                          int64_t *d_top_idx, uint8_t *d_top_rows, int *d_status, void *d_work,
+                          void *stream);
+int64_t flexs_screen_message_bytes(int k, int seq_len);
+int flexs_screen_merge_dev(const void *d_gathered, int world, int k, int seq_len,
+                           float *d_top_scores, int64_t *d_top_idx, uint8_t *d_top_rows,
+                           void *stream);
+
 /* ---- K5: candidate generation helpers -------------------------------------------------
  * flexs_mutate_dev replaces generate_random_mutant (sequence_utils.py:87-108) applied to
  * n parents at once: every residue is, with probability mu, replaced by a uniform draw

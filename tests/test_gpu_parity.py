@@ -677,3 +677,193 @@ def test_virtual_screen_single_rank_matches_numpy():
     # tie-free batches agree with the reference's own slice
     if len(np.unique(scores)) == n:
         np.testing.assert_array_equal(top_seqs, seqs[np.argsort(scores)[: -B: -1]])
+
+
+@pytest.mark.parametrize("L,alphabet", [(100, su.DNAA), (237, su.AAS), (8, su.DNAA), (11, "ABCDEFG")])
+def test_packed_wire_format_device_round_trip_bit_exact(L, alphabet):
+    """The packed wire format (include/flexs_b200.h): host packers (numpy and the C pass over str objects) and the
+    device pack / unpack kernels agree bit for bit; a value outside the alphabet is reported with its position."""
+    A = len(alphabet)
+    n = 3001
+    idx = np.random.default_rng(L).integers(0, A, size=(n, L), dtype=np.uint8)
+    packed = su.pack_indices(idx, A)
+    assert packed.shape == (n, _native.packed_row_bytes(L, A))
+    assert int(_native.lib().flexs_packed_row_bytes(L, A)) == packed.shape[1]
+    assert int(_native.lib().flexs_bits_per_residue(A)) == _native.bits_per_residue(A)
+    np.testing.assert_array_equal(su.pack_sequences(list(su.decode_indices(idx, alphabet)), alphabet), packed)
+    np.testing.assert_array_equal(su.unpack_indices(packed, L, A), idx)
+    d_packed = torch.from_numpy(packed).cuda()
+    d_idx = torch.empty((n, L), dtype=torch.uint8, device="cuda")
+    status = torch.zeros(2, dtype=torch.int64, device="cuda")
+    _native.unpack_dev(d_packed.data_ptr(), n, L, A, d_idx.data_ptr(), status.data_ptr())
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(d_idx.cpu().numpy(), idx)
+    assert status.tolist()[0] == 0
+    d_back = torch.zeros_like(d_packed)
+    _native.pack_dev(d_idx.data_ptr(), n, L, A, d_back.data_ptr())
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(d_back.cpu().numpy(), packed)
+    if (1 << _native.bits_per_residue(A)) > A:   # a bit pattern that is not a residue
+        bad = idx.copy().astype(np.uint16)
+        bad[7, 3] = A
+        planes = ((bad[:, :, None] >> np.arange(_native.bits_per_residue(A))) & 1).astype(np.uint8).reshape(n, -1)
+        d_bad = torch.from_numpy(np.packbits(planes, axis=1, bitorder="little")).cuda()
+        _native.unpack_dev(d_bad.data_ptr(), n, L, A, d_idx.data_ptr(), status.data_ptr())
+        torch.cuda.synchronize()
+        assert status.tolist() == [1, 7 * L + 3]
+
+
+def test_score_host_packed_matches_byte_route_and_strings():
+    """flexs_model_score_host_packed == flexs_model_score_host == the device-resident forward, bit for bit (the same
+    kernels behind a different first stage), across several chunks; and Model.get_fitness(list[str]) takes that route
+    for large lists, raising the reference's ValueError for a foreign character."""
+    import flexs_b200 as flexs
+
+    for L, alphabet, n in ((100, su.DNAA, 700_000), (237, su.AAS, 20_000)):
+        A = len(alphabet)
+        cnn = flexs.baselines.models.CNN(L, 32, 100, alphabet, seed=1)
+        idx = np.random.default_rng(1).integers(0, A, size=(n, L), dtype=np.uint8)
+        want = cnn._score_device(torch.from_numpy(idx).cuda()).cpu().numpy()
+        got = cnn.native.score_host_packed(su.pack_indices(idx, A))
+        np.testing.assert_array_equal(got, want)
+        seqs = list(su.decode_indices(idx[:9000], alphabet))
+        cost0 = cnn.cost
+        np.testing.assert_array_equal(cnn.get_fitness([str(s) for s in seqs]), want[:9000])
+        assert cnn.cost == cost0 + 9000
+        bad = [str(s) for s in seqs]
+        bad[4321] = bad[4321][:5] + "!" + bad[4321][6:]
+        with pytest.raises(ValueError, match="4321"):
+            cnn.get_fitness(bad)
+        with pytest.raises(ValueError):
+            cnn.native.score_host_packed(np.zeros((4, 3), dtype=np.uint8))
+
+
+def _select(scores, k, rows=None, unique=False, offset=0, want_rows=False):
+    n = len(scores)
+    d = torch.from_numpy(np.ascontiguousarray(scores, dtype=np.float32)).cuda()
+    d_rows = torch.from_numpy(np.ascontiguousarray(rows)).cuda() if rows is not None else None
+    L = rows.shape[1] if rows is not None else 0
+    work = torch.empty(_native.topk_select_workspace_bytes(), dtype=torch.uint8, device="cuda")
+    ts = torch.empty(k, dtype=torch.float32, device="cuda")
+    ti = torch.empty(k, dtype=torch.int64, device="cuda")
+    tr = torch.full((k, max(L, 1)), 255, dtype=torch.uint8, device="cuda") if want_rows else None
+    status = torch.full((1,), -7, dtype=torch.int32, device="cuda")
+    _native.topk_select_dev(d.data_ptr(), n, k, offset, d_rows.data_ptr() if d_rows is not None else 0, L, unique,
+                            ts.data_ptr(), ti.data_ptr(), tr.data_ptr() if tr is not None else 0, status.data_ptr(),
+                            work.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return ts.cpu().numpy(), ti.cpu().numpy(), (tr.cpu().numpy() if tr is not None else None), int(status.item())
+
+
+@pytest.mark.parametrize("n,k", [(1, 1), (5, 8), (1000, 99), (70_000, 4096), (3_000_001, 99), (1 << 22, 1000)])
+def test_topk_select_single_launch_matches_numpy(n, k):
+    """flexs_topk_select_dev == np.lexsort((position, -score)) bit for bit, ties included; also == flexs_topk_dev."""
+    rng = np.random.default_rng(n + k)
+    for kind in ("normal", "ties", "wall"):
+        if kind == "normal":
+            s = rng.normal(size=n).astype(np.float32)
+        elif kind == "ties":
+            s = (rng.integers(-30, 30, size=n) / 4).astype(np.float32)
+            s[rng.integers(0, n, size=max(1, n // 50))] = -0.0
+        else:
+            s = np.full(n, 1.25, dtype=np.float32)          # every score equal: the descent runs into the position bits
+        order = np.lexsort((np.arange(n), -s.astype(np.float64)))[:k]
+        ts, ti, _, st = _select(s, k, offset=1000)
+        m = min(n, k)
+        np.testing.assert_array_equal(ti[:m], order + 1000, err_msg=kind)
+        np.testing.assert_array_equal(ts[:m].view(np.int32) & 0x7fffffff, s[order].view(np.int32) & 0x7fffffff)
+        assert np.all(ti[m:] == -1) and np.all(np.isneginf(ts[m:])) and st == 0
+        if n <= 70_000:
+            rs, ri = _topk(s, k, offset=1000)
+            np.testing.assert_array_equal(ri, ti)
+
+
+@pytest.mark.parametrize("L,A,n,k", [(8, 4, 200_000, 99), (100, 4, 300_000, 99), (14, 4, 50_000, 1000), (237, 20, 20_000, 99)])
+def test_topk_select_distinct_rows_lazy_dedup_exact(L, A, n, k):
+    """`unique`: the k best DISTINCT rows through their first occurrence == the reference's ranking of dict keys,
+    with the winners' rows written next to them; equal rows carry equal scores (a deterministic surrogate)."""
+    rng = np.random.default_rng(L)
+    pool = rng.integers(0, A, size=(max(64, n // 7), L), dtype=np.uint8)       # ~7 copies of every row
+    pick = rng.integers(0, len(pool), size=n)
+    rows = pool[pick]
+    pool_scores = (rng.integers(-2000, 2000, size=len(pool)) / 16).astype(np.float32)   # ties between different rows too
+    s = pool_scores[pick]
+    _, first = np.unique(rows, axis=0, return_index=True)
+    first = np.sort(first)
+    order = first[np.lexsort((first, -s[first].astype(np.float64)))][:k]
+    ts, ti, tr, st = _select(s, k, rows=rows, unique=True, offset=5, want_rows=True)
+    assert st == 0
+    np.testing.assert_array_equal(ti[: len(order)], order + 5)
+    np.testing.assert_array_equal(ts[: len(order)], s[order])
+    np.testing.assert_array_equal(tr[: len(order)], rows[order])
+    # rows only (no de-duplication) still returns the winners' rows
+    ts2, ti2, tr2, _ = _select(s, k, rows=rows, unique=False, want_rows=True)
+    o2 = np.lexsort((np.arange(n), -s.astype(np.float64)))[:k]
+    np.testing.assert_array_equal(ti2, o2)
+    np.testing.assert_array_equal(tr2, rows[o2])
+
+
+def test_topk_select_reports_when_the_best_rows_hold_too_few_distinct_sequences():
+    """A batch that is almost all repeats: the best 4096 rows hold fewer than k distinct sequences although the batch has
+    more — status 1, and VirtualScreen falls back to hashing every row (dedup.cu): still the exact answer."""
+    import flexs_b200 as flexs
+    from flexs_b200.screen import VirtualScreen
+
+    L, n, k = 8, 120_000, 99
+    cnn = flexs.baselines.models.CNN(L, 32, 100, su.DNAA, seed=5)
+    base = np.random.default_rng(1).integers(0, 4, size=(150, L), dtype=np.uint8)
+    base_scores = cnn.get_fitness(base)
+    best = base[np.argsort(-base_scores)[:40]]
+    idx = np.concatenate([np.repeat(best, 2900, axis=0), base])     # 116 000 copies of the 40 best, then everything once
+    idx = idx[np.random.default_rng(2).permutation(len(idx))][:n]
+    scores = cnn.get_fitness(idx)
+    _, _, _, st = _select(scores, k, rows=idx, unique=True)
+    assert st == 1
+    _, first = np.unique(idx, axis=0, return_index=True)
+    first = np.sort(first)
+    order = first[np.lexsort((first, -scores[first].astype(np.float64)))][:k]
+    vs = VirtualScreen(cnn, k=k)
+    top_i, top_s = vs.screen(idx)
+    assert vs.fallbacks == 1
+    np.testing.assert_array_equal(top_i, order)
+    np.testing.assert_array_equal(top_s, scores[order])
+
+
+@pytest.mark.parametrize("world,k,L", [(8, 99, 100), (2, 1000, 14), (4, 99, 0), (3, 7, 237)])
+def test_screen_merge_kernel_matches_reference_merge(world, k, L):
+    """flexs_screen_merge_dev on synthetic gathered messages (repeats across ranks, absent winners, score ties) ==
+    screen.merge_reference, the numpy statement the gloo tests pin."""
+    from flexs_b200 import screen
+
+    rng = np.random.default_rng(world * 1000 + k)
+    mb = screen.message_bytes(k, L)
+    assert mb == _native.screen_message_bytes(k, L)
+    gathered = torch.zeros(world * mb, dtype=torch.uint8)
+    shared_rows = rng.integers(0, 4, size=(k, max(L, 1)), dtype=np.uint8)
+    shared_scores = np.sort((rng.integers(0, 400, size=k) / 8).astype(np.float32))[::-1]
+    for r in range(world):
+        idx_v, sc_v, rows_v = screen.message_views(gathered[r * mb:(r + 1) * mb], k, L)
+        own = rng.random(k) < 0.6
+        rows = np.where(own[:, None], rng.integers(0, 4, size=(k, max(L, 1)), dtype=np.uint8), shared_rows)
+        sc = np.where(own, (rng.integers(0, 400, size=k) / 8).astype(np.float32), shared_scores).astype(np.float32)
+        o = np.argsort(-sc, kind="stable")
+        sc, rows = sc[o], rows[o]
+        gi = np.sort(rng.choice(1 << 20, size=k, replace=False)) + (r << 20)
+        if r == world - 1:
+            sc[-3:] = -np.inf; gi[-3:] = -1
+        sc_v.copy_(torch.from_numpy(sc)); idx_v.copy_(torch.from_numpy(gi))
+        if L:
+            rows_v.copy_(torch.from_numpy(rows))
+    want_s, want_i, want_rows = screen.merge_reference(gathered.numpy(), world, k, L)
+    d = gathered.cuda()
+    out = torch.zeros(mb, dtype=torch.uint8, device="cuda")
+    fi, fs, fr = screen.message_views(out, k, L)
+    _native.screen_merge_dev(d.data_ptr(), world, k, L, fs.data_ptr(), fi.data_ptr(), fr.data_ptr() if L else 0,
+                             torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    m = len(want_i)
+    np.testing.assert_array_equal(fi.cpu().numpy()[:m], want_i)
+    np.testing.assert_array_equal(fs.cpu().numpy()[:m], want_s)
+    if L:
+        np.testing.assert_array_equal(fr.cpu().numpy()[:m], want_rows)
+    assert np.all(fi.cpu().numpy()[m:] == -1)

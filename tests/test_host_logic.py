@@ -271,3 +271,37 @@ def test_packstr_extension_matches_pure_python_route():
     assert su.sequences_to_char_array(seqs[:4], seq_len=37).shape == (4, 37)
     with pytest.raises(ValueError):
         su.sequences_to_char_array(seqs[:4], seq_len=36)
+
+
+def test_packed_wire_format_host_packers_agree():
+    """The two host packers of the wire format of include/flexs_b200.h (numpy on index arrays, the multi-threaded C pass
+    over str objects) produce identical rows; unpack inverts them; error behaviour follows str.index."""
+    import numpy as np
+    import pytest
+
+    from flexs_b200.utils import sequence_utils as su
+
+    rng = np.random.default_rng(0)
+    for alphabet, L, n in ((su.DNAA, 100, 3000), (su.AAS, 237, 1200), (su.DNAA, 8, 50), (su.AAS, 735, 400), ("AB", 9, 10), ("ABCDEFG", 11, 77)):
+        A = len(alphabet)
+        idx = rng.integers(0, A, size=(n, L), dtype=np.uint8)
+        seqs = [str(s) for s in su.decode_indices(idx, alphabet)]
+        packed = su.pack_indices(idx, A)
+        bits = su.bits_per_residue(A)
+        assert packed.dtype == np.uint8 and packed.shape == (n, (L * bits + 7) // 8)
+        np.testing.assert_array_equal(su.pack_sequences(seqs, alphabet), packed)
+        np.testing.assert_array_equal(su.pack_sequences(np.array(seqs), alphabet), packed)   # numpy route
+        np.testing.assert_array_equal(su.unpack_indices(packed, L, A), idx)
+        # definition: residue i occupies bits [i*b, (i+1)*b) of the row's little-endian bit stream
+        i = L - 1
+        stream = int.from_bytes(packed[0].tobytes(), "little")
+        assert (stream >> (i * bits)) & ((1 << bits) - 1) == idx[0, i]
+    big = [su.DNAA[i % 4] * 100 for i in range(5000)]      # large enough for the threaded path
+    with pytest.raises(ValueError, match="sequence 4999"):
+        su.pack_sequences(big[:-1] + ["A" * 99 + "N"], su.DNAA)
+    with pytest.raises(ValueError, match="same length"):
+        su.pack_sequences(big[:-1] + ["A" * 99], su.DNAA)
+    with pytest.raises(TypeError):
+        su.pack_sequences(big[:-1] + [7], su.DNAA)
+    with pytest.raises(ValueError):
+        su.pack_indices(np.full((2, 5), 4, dtype=np.uint8), 4)

@@ -1,6 +1,6 @@
-"""CPU, world_size 2 over gloo: the host-side plumbing of the sharded virtual screen — block partition,
-message packing, the single all-gather and the unpacking.  (The kernels themselves need a GPU; the final
-merge is re-done here in numpy with the documented tie rule to pin what every rank must agree on.)"""
+"""CPU, world_size 2 over gloo: the host-side plumbing of the sharded virtual screen — block partition, message
+layout, the single all-gather.  (The kernels themselves need a GPU; the final merge is done here by
+screen.merge_reference, the numpy statement of flexs_screen_merge_dev, which the GPU tests check the kernel against.)"""
 import os
 import socket
 
@@ -23,35 +23,42 @@ def test_shard_bounds_cover_and_balance():
             assert max(sizes) - min(sizes) <= 1
 
 
-def test_pack_unpack_roundtrip_bit_exact():
-    k, world = 7, 3
-    rng = np.random.default_rng(0)
-    msgs, all_s, all_i = [], [], []
-    for r in range(world):
-        s = torch.from_numpy(rng.normal(size=k).astype(np.float32))
-        s[0] = float("-inf"); s[1] = -0.0
-        i = torch.from_numpy(rng.integers(-1, 1 << 40, size=k))
-        msgs.append(screen.pack_topk(s, i)); all_s.append(s); all_i.append(i)
-    s2, i2 = screen.unpack_topk(torch.cat(msgs), world, k)
-    assert torch.equal(i2, torch.cat(all_i))
-    assert torch.equal(s2.view(torch.int32), torch.cat(all_s).view(torch.int32))
-
-
-def test_pack_unpack_with_sequences_roundtrip():
-    """The unique screen ships the winners' residues in the same message (one collective): indices, score bits,
-    then k*L bytes padded to int64 words."""
-    k, world, L = 5, 3, 13   # 65 bytes: not a multiple of 8
+def test_message_layout_views_and_reference_merge():
+    """One rank's message is [k] int64 index | [k] float32 score | [k][L] rows, padded to 16 bytes; the selection kernel
+    writes through views into it, the merge reads the all-gathered concatenation.  Pins the layout (bit-exact through
+    -inf, -0.0 and 40-bit indices) and the merge rule (score desc, gathered position asc, later copies of a sequence and
+    absent entries dropped) in numpy — what flexs_screen_merge_dev must reproduce on every rank."""
+    k, world, L = 5, 3, 13
+    assert screen.message_bytes(k, L) == 128 and screen.message_bytes(k, 0) == 64 and screen.message_bytes(99, 100) % 16 == 0
     rng = np.random.default_rng(1)
     msgs, all_s, all_i, all_q = [], [], [], []
     for r in range(world):
-        s = torch.from_numpy(rng.normal(size=k).astype(np.float32))
-        i = torch.from_numpy(rng.integers(-1, 1 << 40, size=k))
+        msg = torch.zeros(screen.message_bytes(k, L), dtype=torch.uint8)
+        idx_v, sc_v, rows_v = screen.message_views(msg, k, L)
+        s = torch.from_numpy(np.sort(rng.normal(size=k).astype(np.float32))[::-1].copy())
+        i = torch.from_numpy(np.sort(rng.integers(r << 38, (r + 1) << 38, size=k)))
         q = torch.from_numpy(rng.integers(0, 20, size=(k, L), dtype=np.uint8))
-        msgs.append(screen.pack_topk(s, i, q)); all_s.append(s); all_i.append(i); all_q.append(q)
-    assert msgs[0].numel() == 2 * k + 9
-    s2, i2, q2 = screen.unpack_topk(torch.cat(msgs), world, k, L)
-    assert torch.equal(i2, torch.cat(all_i)) and torch.equal(q2, torch.cat(all_q))
-    assert torch.equal(s2.view(torch.int32), torch.cat(all_s).view(torch.int32))
+        if r == 1:
+            s[-1] = float("-inf"); i[-1] = -1            # an absent winner
+            s[0] = all_s[0][2]; q[0] = all_q[0][2]       # a sequence that also reached rank 0's list, same score
+        sc_v.copy_(s); idx_v.copy_(i); rows_v.copy_(q)
+        msgs.append(msg); all_s.append(s); all_i.append(i); all_q.append(q)
+    gathered = torch.cat(msgs).numpy()
+    fs, fi, fq = screen.merge_reference(gathered, world, k, L)
+    cat_s, cat_i = torch.cat(all_s).numpy(), torch.cat(all_i).numpy()
+    assert len(fs) == k and np.all(np.diff(fs) <= 0) and np.all(fi >= 0)
+    assert all_i[1][0].item() not in fi.tolist()         # the repeated sequence is reported through rank 0's copy only
+    for sc, gi in zip(fs, fi):                            # every winner is one of the messages' (score, index) pairs, bit-exact
+        j = int(np.flatnonzero(cat_i == gi)[0])
+        assert np.float32(sc).view(np.int32) == cat_s[j].view(np.int32)
+    assert len({bytes(r) for r in fq}) == k
+    # without rows: plain ranking of the valid entries
+    m2 = torch.zeros(screen.message_bytes(k, 0), dtype=torch.uint8)
+    i2, s2, r2 = screen.message_views(m2, k, 0)
+    assert r2 is None
+    s2.copy_(torch.tensor([3.0, 2.0, -0.0, 0.0, float("-inf")])); i2.copy_(torch.tensor([7, 1, 9, 4, -1]))
+    fs, fi, _ = screen.merge_reference(m2.numpy(), 1, k, 0)
+    assert fi.tolist() == [7, 1, 9, 4] and np.signbit(fs[2])
 
 
 def _free_port():
@@ -69,11 +76,13 @@ def _worker(rank, world, port, n, k, out_dir):
         start, stop = screen.shard_bounds(n, rank, world)
         local = scores_all[start:stop]
         order = np.lexsort((np.arange(len(local)), -local.astype(np.float64)))[:k]  # what flexs_topk_dev returns
-        top_s = torch.full((k,), float("-inf")); top_i = torch.full((k,), -1, dtype=torch.int64)
+        msg = torch.zeros(screen.message_bytes(k, 0), dtype=torch.uint8)
+        top_i, top_s, _ = screen.message_views(msg, k, 0)
+        top_s.fill_(float("-inf")); top_i.fill_(-1)
         top_s[: len(order)] = torch.from_numpy(local[order]); top_i[: len(order)] = torch.from_numpy(order + start)
-        gathered = screen.all_gather_topk(screen.pack_topk(top_s, top_i))
-        g_s, g_i = screen.unpack_topk(gathered, world, k)
-        np.savez(os.path.join(out_dir, f"r{rank}.npz"), s=g_s.numpy(), i=g_i.numpy())
+        gathered = screen.all_gather_messages(msg)                       # the single collective of the path
+        f_s, f_i, _ = screen.merge_reference(gathered.numpy(), world, k, 0)
+        np.savez(os.path.join(out_dir, f"r{rank}.npz"), g=gathered.numpy(), s=f_s, i=f_i)
     finally:
         dist.destroy_process_group()
 
@@ -83,13 +92,12 @@ def test_all_gather_of_shard_topk_world2(tmp_path, n, k):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), n, k, str(tmp_path)), nprocs=world, join=True)
     r0, r1 = np.load(tmp_path / "r0.npz"), np.load(tmp_path / "r1.npz")
-    np.testing.assert_array_equal(r0["s"], r1["s"])   # every rank holds the same gathered lists
+    np.testing.assert_array_equal(r0["g"], r1["g"])   # every rank holds the same gathered messages
     np.testing.assert_array_equal(r0["i"], r1["i"])
+    np.testing.assert_array_equal(r0["s"], r1["s"])
     # the merge every rank then performs (score desc, position asc == global index asc) equals the
     # single-process selection over the whole batch
     scores_all = np.random.default_rng(123).integers(-40, 40, size=n).astype(np.float32) / 4
     want = np.lexsort((np.arange(n), -scores_all.astype(np.float64)))[: min(k, n)]
-    valid = r0["i"] >= 0
-    pos = np.arange(len(r0["s"]))[valid]
-    merged = pos[np.lexsort((pos, -r0["s"][valid].astype(np.float64)))][: min(k, n)]
-    np.testing.assert_array_equal(r0["i"][merged], want)
+    np.testing.assert_array_equal(r0["i"], want)
+    np.testing.assert_array_equal(r0["s"], scores_all[want])
