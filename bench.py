@@ -6,8 +6,9 @@
 
 Metric (BASELINE.json): sequences scored per second in a virtual screen.  One "step" = one pass of
 the hot path over one synthetic candidate batch per GPU: fused CNN forward (uint8 residue indices in
-HBM -> fp32 scores), per-shard top-k, and — for N > 1 — ONE NCCL all-gather of the per-shard top-k
-lists followed by the final merge on every rank.  Weak scaling: the per-GPU batch is fixed.
+HBM -> fp32 scores), per-shard top-k over distinct sequences (one launch), and — for N > 1 — ONE NCCL
+all-gather of the per-shard top-k messages followed by the one-launch merge on every rank, all through
+the product class flexs_b200.screen.VirtualScreen.  Weak scaling: the per-GPU batch is fixed.
 
 Headline workload: the configuration the metric's target is quoted on in BASELINE.json's north_star
 ("100-mer x 4-alphabet CNN surrogate"), canonical hyper-parameters F=32, H=100, k=5
@@ -88,8 +89,9 @@ def plugin_api_timings(device):
 
 
 def dedup_timing(device):
-    """K3b: exact de-duplication + top-k of a device-resident batch (what VirtualScreen adds after the forward pass),
-    CUDA events.  1M draws from the 65 536 8-mers (>= 93 % repeats) and 2^22 random 100-mers (no repeats)."""
+    """K3 / K3b / K3c: ranking of a device-resident batch over DISTINCT sequences (what VirtualScreen adds after the
+    forward pass), CUDA events: the single-launch selection (select.cu) beside the hash de-duplication + 11-launch radix
+    select it replaces.  1M draws from the 65 536 8-mers (>= 93 % repeats) and 2^22 random 100-mers (no repeats)."""
     import torch
 
     from flexs_b200 import _native
@@ -97,29 +99,44 @@ def dedup_timing(device):
     out = {}
     for tag, L, n in (("8mer_1M", 8, 1 << 20), ("100mer_4M", 100, 1 << 22)):
         idx = torch.randint(0, 4, (n, L), dtype=torch.uint8, device=device)
-        scores = torch.randn(n, device=device)
+        # equal rows must carry equal scores (a deterministic surrogate): score = a function of the row
+        w = torch.randn(L, 4, device=device)
+        scores = w[torch.arange(L, device=device), idx.long()].sum(dim=1).contiguous()
         masked = torch.empty_like(scores)
         dwork = torch.empty(_native.dedup_workspace_bytes(n), dtype=torch.uint8, device=device)
         twork = torch.empty(_native.topk_workspace_bytes(n, TOPK), dtype=torch.uint8, device=device)
+        swork = torch.empty(_native.topk_select_workspace_bytes(), dtype=torch.uint8, device=device)
         ts = torch.empty(TOPK, dtype=torch.float32, device=device)
         ti = torch.empty(TOPK, dtype=torch.int64, device=device)
+        ts2, ti2 = torch.empty_like(ts), torch.empty_like(ti)
+        status = torch.zeros(8, dtype=torch.int32, device=device)
         s = torch.cuda.current_stream().cuda_stream
 
-        def run():
+        def two_call():
             _native.dedup_scores_dev(idx.data_ptr(), n, L, scores.data_ptr(), masked.data_ptr(), dwork.data_ptr(), s)
             _native.topk_dev(masked.data_ptr(), n, TOPK, 0, 0, ts.data_ptr(), ti.data_ptr(), twork.data_ptr(), s)
 
-        for _ in range(3):
-            run()
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        ev[0].record()
-        for _ in range(5):
-            run()
-        ev[1].record()
-        torch.cuda.synchronize()
-        ms = ev[0].elapsed_time(ev[1]) / 5
-        out[tag] = {"dedup_plus_topk_ms": ms, "sequences_per_s": n / (ms / 1e3),
-                    "distinct_in_top": int(len({bytes(r) for r in idx[ti.clamp(min=0)].cpu().numpy()}))}
+        def single():
+            _native.topk_select_dev(scores.data_ptr(), n, TOPK, 0, idx.data_ptr(), L, True, ts2.data_ptr(), ti2.data_ptr(), 0,
+                                    status.data_ptr(), swork.data_ptr(), s)
+
+        res = {}
+        for name, fn in (("dedup_plus_topk_ms", two_call), ("select_single_launch_ms", single)):
+            for _ in range(3):
+                fn()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ev[0].record()
+            for _ in range(5):
+                fn()
+            ev[1].record()
+            torch.cuda.synchronize()
+            res[name] = ev[0].elapsed_time(ev[1]) / 5
+        st = status.cpu().tolist()
+        res["identical_winners"] = bool(torch.equal(ti, ti2) and torch.equal(ts, ts2)) and st[0] == 0
+        res["select_diagnostics"] = {"radix_levels": st[1], "candidates": st[2], "select_us": st[3] / 1e3, "final_cta_us": st[4] / 1e3}
+        res["sequences_per_s"] = n / (res["select_single_launch_ms"] / 1e3)
+        res["distinct_in_top"] = int(len({bytes(r) for r in idx[ti2.clamp(min=0)].cpu().numpy()}))
+        out[tag] = res
     return out
 
 
@@ -249,75 +266,73 @@ def cnn_shapes(L, A, F, H, K):
     return [(K, A, F), (F,), (K, F, F), (F,), (A - 1, F, F), (F,), (F, H), (H,), (H, H), (H,), (H, 1), (1,)]
 
 
-class Screen:
-    """One rank's share of the virtual screen: forward + top-k (+ all-gather + merge)."""
+ALPHABETS = {4: "TGCA", 20: "ILVAGMFYWEDQNHCRKSTP"}
 
-    def __init__(self, L, A, F, H, K, members, batch, rank, world, device):
+
+def mlp_shapes(L, A, H):
+    return [(L * A, H), (H,), (H, H), (H,), (H, H), (H,), (H, 1), (1,)]
+
+
+class Screen:
+    """One rank's share of the virtual screen, through the PRODUCT classes: a ``flexs_b200`` surrogate (``CNN`` / ``MLP`` /
+    fused ``Ensemble``) under ``flexs_b200.screen.VirtualScreen`` (unique=True: the reference ranks the keys of a dict).
+    A step = forward over the rank's shard + one selection launch (+ ONE all-gather + one merge launch for N > 1)."""
+
+    def __init__(self, L, A, F, H, K, members, batch, rank, world, device, kind="cnn"):
         import torch
 
-        from flexs_b200 import _native
+        import flexs_b200 as flexs
+        from flexs_b200.screen import VirtualScreen
 
-        self.torch, self.native = torch, _native
-        self.L, self.batch, self.rank, self.world, self.device = L, batch, rank, world, device
-        self.model = _native.NativeModel("cnn", seq_len=L, alphabet_size=A, num_filters=F, hidden_size=H,
-                                         kernel_size=K, n_members=members, device=device.index)
+        self.torch = torch
+        self.L, self.A, self.batch, self.rank, self.world, self.device = L, A, batch, rank, world, device
+        alphabet = ALPHABETS[A]
+        models = []
         for mem in range(members):
-            self.model.set_weights(make_weights(cnn_shapes(L, A, F, H, K), mem), mem)
+            if kind == "cnn":
+                m = flexs.baselines.models.CNN(L, F, H, alphabet, kernel_size=K, device=device.index, seed=mem)
+                m.set_weights(make_weights(cnn_shapes(L, A, F, H, K), mem))
+            else:
+                m = flexs.baselines.models.MLP(L, H, alphabet, device=device.index, seed=mem)
+                m.set_weights(make_weights(mlp_shapes(L, A, H), mem))
+            models.append(m)
+        self.surrogate = models[0] if members == 1 else flexs.Ensemble(models)
+        self.model = models[0].native if members == 1 else self.surrogate._fused_model().native   # the native object scored
         gen = torch.Generator(device=device)
         gen.manual_seed(1234 + rank)
         self.idx = torch.randint(0, A, (batch, L), dtype=torch.uint8, device=device, generator=gen)
-        self.scores = torch.empty(batch, dtype=torch.float32, device=device)
         self.k = TOPK
-        self.ws = torch.empty(_native.topk_workspace_bytes(batch, self.k), dtype=torch.uint8, device=device)
-        self.top_s = torch.empty(self.k, dtype=torch.float32, device=device)
-        self.top_i = torch.empty(self.k, dtype=torch.int64, device=device)
-        if world > 1:
-            self.pack = torch.empty(2 * self.k, dtype=torch.int64, device=device)
-            self.gathered = torch.empty(world * 2 * self.k, dtype=torch.int64, device=device)
-            self.g_scores = torch.empty(world * self.k, dtype=torch.float32, device=device)
-            self.g_idx = torch.empty(world * self.k, dtype=torch.int64, device=device)
-            self.ws2 = torch.empty(_native.topk_workspace_bytes(world * self.k, self.k), dtype=torch.uint8, device=device)
-            self.fin_s = torch.empty(self.k, dtype=torch.float32, device=device)
-            self.fin_i = torch.empty(self.k, dtype=torch.int64, device=device)
+        self.vs = VirtualScreen(self.surrogate, k=self.k, unique=True)
         self.fwd_ms = []
-        self.launches = 0
+        self.status_sum = torch.zeros(1, dtype=torch.int32, device=device)
+        self.scores = None
+        self.result = None
 
-    def step(self, time_forward=False):
-        torch, nat = self.torch, self.native
-        stream = torch.cuda.current_stream().cuda_stream
-        l0 = self.model.launch_count
-        if time_forward:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        self.model.forward_dev(self.idx.data_ptr(), self.batch, self.scores.data_ptr(), stream)
-        if time_forward:
-            e1.record()
-            self._pending = (e0, e1)
-        nat.topk_dev(self.scores.data_ptr(), self.batch, self.k, self.rank * self.batch, 0, self.top_s.data_ptr(),
-                     self.top_i.data_ptr(), self.ws.data_ptr(), stream)
-        self.launches += (self.model.launch_count - l0) + 11
-        if self.world > 1:
-            import torch.distributed as dist
+    @property
+    def launches(self):
+        return self._model_launches + self.vs.launches
 
-            self.pack[: self.k] = self.top_i
-            self.pack[self.k:] = self.top_s.view(torch.int32).to(torch.int64)
-            dist.all_gather_into_tensor(self.gathered, self.pack)   # the single collective of the path
-            g = self.gathered.view(self.world, 2, self.k)
-            self.g_idx.copy_(g[:, 0, :].reshape(-1))
-            self.g_scores.copy_(g[:, 1, :].reshape(-1).to(torch.int32).view(torch.float32))
-            nat.topk_dev(self.g_scores.data_ptr(), self.world * self.k, self.k, 0, self.g_idx.data_ptr(),
-                         self.fin_s.data_ptr(), self.fin_i.data_ptr(), self.ws2.data_ptr(), stream)
-            self.launches += 11
+    def reset_counters(self):
+        self._l0 = self.model.launch_count
+        self._model_launches = 0
+        self.vs.launches = 0
+        self.vs.forward_events = []
+        self.status_sum.zero_()
 
-    def collect_forward_time(self):
-        e0, e1 = self._pending
-        self.fwd_ms.append(e0.elapsed_time(e1))
+    def step(self):
+        # check=False: no host sync inside the timed region; the selection's status flags are summed on the device and
+        # read after it (0 = the lazy de-duplication found k distinct sequences every time)
+        _, _, self.scores = self.vs.local_topk(self.idx, self.rank * self.batch, check=False)
+        self.status_sum += self.vs.last_status[:1]
+        self.result = self.vs.merge(self.L, self.device)
+        self._model_launches = self.model.launch_count - self._l0
 
 
 def timed_steps(screen, steps, warmup, world, device):
     """W warm-up steps, then exactly K steps between barrier+synchronize, CUDA events, max over ranks."""
     import torch
 
+    screen.reset_counters()
     for _ in range(warmup):
         screen.step()
     torch.cuda.synchronize(device)
@@ -328,13 +343,11 @@ def timed_steps(screen, steps, warmup, world, device):
     torch.cuda.synchronize(device)
     sampler = ClockSampler(device.index)
     sampler.start()
-    screen.launches = 0
+    screen.reset_counters()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
-    pend = []
     for _ in range(steps):
-        screen.step(time_forward=True)
-        pend.append(screen._pending)
+        screen.step()
     end.record()
     torch.cuda.synchronize(device)
     if world > 1:
@@ -344,7 +357,9 @@ def timed_steps(screen, steps, warmup, world, device):
     torch.cuda.synchronize(device)
     clocks = sampler.stop()
     ms = start.elapsed_time(end)
-    screen.fwd_ms = [a.elapsed_time(b) for a, b in pend]
+    screen.fwd_ms = [a.elapsed_time(b) for a, b in screen.vs.forward_events]
+    screen.vs.forward_events = None
+    assert int(screen.status_sum.item()) == 0, "selection fell short of k distinct sequences: the step must use check=True"
     if world > 1:
         import torch.distributed as dist
 
@@ -355,17 +370,21 @@ def timed_steps(screen, steps, warmup, world, device):
 
 
 def measure_e2e(screen, L, A, steps, world, device):
-    """Same metric through the reference-facing call with HOST buffers: pinned residue characters in,
-    host scores out (flexs_model_score_host = what Model.get_fitness calls), copies inside the timing."""
+    """Same metric through the reference-facing C-ABI call with HOST buffers (what Model.get_fitness calls for a large
+    list): candidates in pinned host memory in the packed wire format of include/flexs_b200.h (2 bits per DNA residue),
+    host scores out; H2D + unpack + forward + D2H inside the timing."""
     import torch
 
-    alphabet = "TGCA"[:A] if A == 4 else "ILVAGMFYWEDQNHCRKSTP"[:A]
-    table = torch.tensor(list(alphabet.encode()), dtype=torch.uint8)
-    chars = table[screen.idx.cpu().long()].contiguous().pin_memory()
+    from flexs_b200 import _native
+
+    rb = _native.packed_row_bytes(L, A)
+    d_packed = torch.empty((screen.batch, rb), dtype=torch.uint8, device=device)
+    _native.pack_dev(screen.idx.data_ptr(), screen.batch, L, A, d_packed.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    packed = d_packed.cpu().pin_memory()
     out = torch.empty(screen.batch, dtype=torch.float32).pin_memory()
-    chars_np, out_np = chars.numpy(), out.numpy()
-    screen.model.score_host(chars_np[:4096], alphabet)          # allocate staging, warm up
-    screen.model.score_host(chars_np, alphabet, out_np)
+    packed_np, out_np = packed.numpy(), out.numpy()
+    screen.model.score_host_packed(packed_np[:4096])             # allocate staging, warm up
+    screen.model.score_host_packed(packed_np, out_np)
     torch.cuda.synchronize(device)
     if world > 1:
         import torch.distributed as dist
@@ -374,7 +393,7 @@ def measure_e2e(screen, L, A, steps, world, device):
     l0 = screen.model.launch_count
     t0 = time.perf_counter()
     for _ in range(steps):
-        screen.model.score_host(chars_np, alphabet, out_np)
+        screen.model.score_host_packed(packed_np, out_np)
     dt = time.perf_counter() - t0
     launches = screen.model.launch_count - l0
     if world > 1:
@@ -383,11 +402,39 @@ def measure_e2e(screen, L, A, steps, world, device):
         t = torch.tensor([dt], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-    # sanity: identical to the device-resident path
-    same = bool(np.array_equal(out_np, screen.scores.cpu().numpy()))
-    return {"value": world * screen.batch * steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(screen.batch * L),
+    same = bool(np.array_equal(out_np, screen.scores.cpu().numpy()))   # identical to the device-resident path
+    return {"value": world * screen.batch * steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(screen.batch * rb),
             "d2h_bytes_per_step": int(screen.batch * 4), "steps": steps, "matches_device_path": same,
-            "api": "flexs_model_score_host (Model.get_fitness)", "gpu_launches": int(launches)}
+            "api": "flexs_model_score_host_packed: pinned host rows in the packed wire format (2 bits per residue)",
+            "gpu_launches": int(launches)}
+
+
+def measure_e2e_strings(screen, L, A, device, n=1 << 20):
+    """The reference's own signature, end to end: ``CNN.get_fitness(list[str])`` (flexs/landscape.py:29-45) on a Python
+    list of n strings — the C pass over the str objects (alphabet lookup + bit packing, multi-threaded), pageable ->
+    pinned staging, H2D, unpack, forward, D2H, all inside the timing.  Rank 0 only."""
+    import torch
+
+    from flexs_b200.utils import sequence_utils as su
+
+    alphabet = ALPHABETS[A]
+    idx = screen.idx[:n].cpu().numpy()
+    seqs = su.decode_indices(idx, alphabet).tolist()
+    model = screen.surrogate
+    want = screen.scores[:n].cpu().numpy()
+    model.get_fitness(seqs[:8192])
+    t0 = time.perf_counter(); su.pack_sequences(seqs, alphabet); pack_s = time.perf_counter() - t0
+    times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        got = model.get_fitness(seqs)
+        times.append(time.perf_counter() - t0)
+    torch.cuda.synchronize(device)
+    dt = float(np.median(times))
+    return {"value": n / dt, "unit": UNIT, "n": n, "seconds": dt, "host_pack_seconds": pack_s,
+            "host_threads": su.host_threads(), "matches_device_path": bool(np.array_equal(got, want)),
+            "api": "flexs_b200.baselines.models.CNN.get_fitness(list[str])",
+            "note": "bounded by touching one Python str object per sequence on the host, not by PCIe or the GPU"}
 
 
 def cpu_baseline(L, A, F, H, K, members=1, seconds_target=12.0):
@@ -538,16 +585,24 @@ def main():
             "kernel": "cnn_k9_kernel (+ cnn_k9_dense_kernel)",
             "tensor_flop_executed_per_seq": 2 * mac_exec, "tensor_tflops_executed": exec_tf,
             "tensor_frac_executed": exec_tf / peaks["bf16_tflops"],
-            # dram__bytes_read+write of one cnn_k9_kernel launch, `ncu --set full` (profiles/r01_k9_ncu_summary.txt:
-            # 321.6 MB for 1 048 576 sequences = 54.5 MB table first touch + 255 B per sequence: 100 B residues in,
-            # 128 B pooled features out, the rest spill of the feature tiles the dense kernel reads back)
-            "traffic": 54.5e6 + 254.7 * seq_per_launch, "traffic_unit": "bytes per cnn_k9_kernel launch",
-            "traffic_source": "ncu capture, scaled to this launch size",
             "sequences_per_launch": seq_per_launch,
             "note": "compute-bound path: `achieved` counts the algorithmic flops of the whole layer stack once per MAC "
                     "(SURVEY.md 8d), although conv1+conv2 are served by a table lookup and conv3/dense run 3 fp16 hi/lo "
                     "split products per MAC; tensor_tflops_executed is what the tensor pipe really ran",
         })
+        # traffic = dram__bytes_read.sum + dram__bytes_write.sum of ONE cnn_k9_kernel launch, read from the committed
+        # `ncu --set full` capture of the shipped kernel (profiles/r02_k9_ncu.json, written by tools/ncu_extract.py from
+        # the .ncu-rep): per-sequence bytes scale with the launch size, the first touch of the L2-resident table does not
+        cap_path = REPO / "profiles" / "r02_k9_ncu.json"
+        if cap_path.exists():
+            cap = json.load(open(cap_path))
+            per_seq = (cap["dram_bytes_per_launch"] - cap["table_bytes"]) / cap["sequences_per_launch"]
+            roofline.update({"traffic": cap["table_bytes"] + per_seq * seq_per_launch,
+                             "traffic_unit": "bytes per cnn_k9_kernel launch",
+                             "traffic_source": f"{cap_path.name}: {cap['dram_bytes_per_launch']:.4g} B measured for "
+                                               f"{cap['sequences_per_launch']} sequences, scaled to this launch size",
+                             "traffic_over_algorithmic": (cap["table_bytes"] + per_seq * seq_per_launch) /
+                                                         ((L_NS + 4) * seq_per_launch)})
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -555,32 +610,41 @@ def main():
         "config": {"workload": "north_star_cnn_100x4", "seq_len": L_NS, "alphabet": A_NS, "num_filters": F_NS,
                    "hidden": H_NS, "kernel_size": K_NS, "per_gpu_batch": args.batch, "topk": TOPK,
                    "parallelism": f"candidate-shard x{world}, one all-gather of per-shard top-k" if world > 1 else "single GPU",
+                   "screen": "flexs_b200.screen.VirtualScreen(unique=True): forward + one selection launch"
+                             + (" + one all-gather + one merge launch" if world > 1 else ""),
                    "l2_policy": f"inputs larger than L2 ({args.batch * L_NS / 1e6:.0f} MB of uint8 per GPU per step)"},
         "clocks": clocks, "roofline": roofline, "gpu_launches": int(screen.launches),
     }
     if not args.skip_extras:
         line["e2e"] = measure_e2e(screen, L_NS, A_NS, max(2, min(args.steps, 4)), world, device)
+        if rank == 0:
+            line["e2e_strings"] = measure_e2e_strings(screen, L_NS, A_NS, device)
         if rank == 0 and world == 1:
             line["cpu_baseline"] = cpu_baseline(L_NS, A_NS, F_NS, H_NS, K_NS)
         elif rank == 0:
             line["cpu_baseline"] = None
         others = {}
-        for tag, (L, A, members, batch) in {"tfbind8_cnn_1M (configs[1])": (8, 4, 1, 1 << 20),
-                                            "rna14_ens3cnn_1M (configs[2])": (14, 4, 3, 1 << 20),
-                                            "aav735_cnn (configs[3], per-GPU shard)": (735, 20, 1, 1 << 15),
-                                            "aav90_cnn (AAV registry window)": (90, 20, 1, 1 << 18),
-                                            "gfp237_cnn (configs[4], per-GPU shard)": (237, 20, 1, 1 << 17)}.items():
-            sc = Screen(L, A, F_NS, H_NS, K_NS, members, batch, rank, world, device)
+        for tag, (L, A, members, batch, kind) in {"tfbind8_cnn_1M (configs[1])": (8, 4, 1, 1 << 20, "cnn"),
+                                                  "tfbind8_mlp_1M (configs[0] surrogate)": (8, 4, 1, 1 << 20, "mlp"),
+                                                  "mlp_100x4_H100": (100, 4, 1, 1 << 21, "mlp"),
+                                                  "rna14_ens3cnn_1M (configs[2])": (14, 4, 3, 1 << 20, "cnn"),
+                                                  "aav735_cnn (configs[3], per-GPU shard)": (735, 20, 1, 1 << 15, "cnn"),
+                                                  "aav90_cnn (AAV registry window)": (90, 20, 1, 1 << 18, "cnn"),
+                                                  "gfp237_cnn (configs[4], per-GPU shard)": (237, 20, 1, 1 << 17, "cnn")}.items():
+            sc = Screen(L, A, F_NS, H_NS, K_NS, members, batch, rank, world, device, kind=kind)
             try:
                 sc.model.set_variant(variant)
             except ValueError:  # a forced variant that this shape does not have: let the library choose
                 sc.model.set_variant(0)
             oms, _ = timed_steps(sc, max(3, args.steps), args.warmup, world, device)
             st = max(3, args.steps)
+            fa_o = flop_alg(L, A, F_NS, H_NS, K_NS) if kind == "cnn" else L * H_NS + 2 * (2 * H_NS * H_NS + H_NS)
+            tf_o = members * fa_o * batch / (np.mean(sc.fwd_ms) / 1e3) / 1e12
             others[tag] = {"value": world * batch * st / (oms / 1e3), "unit": UNIT, "ms_per_step": oms / st,
                            "kernel_ms": float(np.mean(sc.fwd_ms)), "members": members,
-                           "achieved_tflops": members * flop_alg(L, A, F_NS, H_NS, K_NS) * batch / (np.mean(sc.fwd_ms) / 1e3) / 1e12,
-                           "kernel": _native.VARIANT_NAMES[sc.model.active_variant(batch)],
+                           "achieved_tflops": tf_o, "frac_of_bf16_peak": tf_o / peaks["bf16_tflops"],
+                           "hbm_gbs_alg": (L + 4) * batch / (np.mean(sc.fwd_ms) / 1e3) / 1e9,
+                           "kernel": ("mlp" if kind == "mlp" else "") + _native.VARIANT_NAMES[sc.model.active_variant(batch)],
                            "note": "input <= L2 size (re-read from L2 between steps); compute-bound path, so unaffected"}
             del sc
         line["other_workloads"] = others

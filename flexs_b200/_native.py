@@ -53,8 +53,10 @@ _SIGNATURES = [
     ("flexs_screen_merge_dev", c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("flexs_dedup_workspace_bytes", c_int64, [c_int64]),
     ("flexs_dedup_scores_dev", c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    ("flexs_dedup_representatives_dev", c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     ("flexs_mutate_dev", c_int, [c_void_p, c_int64, c_int, c_int, c_float, c_uint64, c_uint64, c_void_p, c_void_p]),
     ("flexs_argmax_decode_dev", c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
+    ("flexs_edit_density_dev", c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     ("flexs_model_fit_dev", c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_uint64, c_void_p, c_void_p]),
     ("flexs_model_train_step_dev", c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, POINTER(c_float), c_void_p]),
     ("flexs_model_get_optimizer_state", c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64)]),
@@ -328,6 +330,12 @@ def dedup_scores_dev(d_idx: int, n: int, seq_len: int, d_scores: int, d_scores_o
                                        c_void_p(d_work), c_void_p(stream)), "dedup")
 
 
+def dedup_representatives_dev(d_idx: int, n: int, seq_len: int, d_rep: int, d_work: int, stream: int = 0) -> None:
+    """rep[i] = lowest index of a row equal to row i (exact); workspace as for ``dedup_scores_dev``."""
+    check(lib().flexs_dedup_representatives_dev(c_void_p(d_idx), n, seq_len, c_void_p(d_rep), c_void_p(d_work),
+                                                c_void_p(stream)), "dedup_representatives")
+
+
 def mutate_dev(d_parents: int, n: int, seq_len: int, alphabet_size: int, mu: float, seed: int, subsequence: int,
                d_children: int, stream: int = 0) -> None:
     check(lib().flexs_mutate_dev(c_void_p(d_parents), n, seq_len, alphabet_size, c_float(mu), c_uint64(seed),
@@ -338,6 +346,13 @@ def argmax_decode_dev(d_x: int, n: int, seq_len: int, row_stride: int, alphabet_
                       stream: int = 0) -> None:
     check(lib().flexs_argmax_decode_dev(c_void_p(d_x), n, seq_len, row_stride, alphabet_size, c_void_p(d_idx),
                                         c_void_p(stream)), "argmax_decode")
+
+
+def edit_density_dev(d_new: int, n_new: int, d_seen: int, d_seen_fitness: int, n_seen: int, seq_len: int, radius: int,
+                     d_out: int, stream: int = 0) -> None:
+    """K8: density penalty of the DyNA-PPO environment for a batch (environments/dyna_ppo.py:106-114)."""
+    check(lib().flexs_edit_density_dev(c_void_p(d_new), n_new, c_void_p(d_seen), c_void_p(d_seen_fitness), n_seen, seq_len,
+                                       radius, c_void_p(d_out), c_void_p(stream)), "edit_density")
 
 
 def _column_table(column_of_char: Optional[np.ndarray]):

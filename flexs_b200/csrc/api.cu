@@ -291,11 +291,11 @@ extern "C" {
 // Host-buffer scoring: chunk the batch, and for each chunk H2D(chars) -> encode -> forward ->
 // D2H(scores), rotating over NSLOT slots/streams so copies overlap compute.
 static int ensure_host_staging(flexs_model *m, int64_t n) {
-    // A slot holds up to ~32 MiB of residue characters: large enough that launch overheads and the tail wave of the
+    // A slot holds up to ~64 MiB of residue characters: large enough that launch overheads and the tail wave of the
     // persistent kernels stay below a few percent of a chunk, small enough that the first copy (which nothing
     // overlaps) is a small part of a multi-million-sequence call.  Slots grow on demand: a model that only ever
     // scores an explorer's 20-string batches pins a few KB, not 64 MiB.
-    int64_t cap = (32ll << 20) / std::max(1, m->L);
+    int64_t cap = (64ll << 20) / std::max(1, m->L);
     cap = std::max<int64_t>(1024, std::min<int64_t>(cap, 1 << 20)) / 128 * 128;
     const int64_t chunk = std::min(cap, std::max<int64_t>(1024, (n + 127) / 128 * 128));
     if (!m->streams[0]) {
@@ -355,7 +355,7 @@ static int score_host_impl(flexs_model_t *m, const char *h_chars, int64_t n, con
     // A chunk is a whole number of waves of the persistent kernels (sm_count groups of 128 sequences), close to
     // FLEXS_HOST_CHUNK_MB of residue characters: small enough that the first copy in and the last compute (which nothing
     // overlaps) are a small part of the call, large enough to amortise the per-chunk launches.
-    static const int64_t target_mb = std::getenv("FLEXS_HOST_CHUNK_MB") ? std::atoll(std::getenv("FLEXS_HOST_CHUNK_MB")) : 32;
+    static const int64_t target_mb = std::getenv("FLEXS_HOST_CHUNK_MB") ? std::atoll(std::getenv("FLEXS_HOST_CHUNK_MB")) : 64;
     const int64_t wave = (int64_t)m->sm_count * 128;
     int64_t per = std::max<int64_t>(1, (target_mb << 20) / std::max<int64_t>(1, L * wave)) * wave;
     per = std::min(per, m->host_chunk);
@@ -369,7 +369,20 @@ static int score_host_impl(flexs_model_t *m, const char *h_chars, int64_t n, con
         return attr.type == cudaMemoryTypeHost;
     };
     const bool in_pinned = is_pinned(h_chars), out_pinned = is_pinned(h_out);
-    const int64_t nchunks = (n + chunk - 1) / chunk;
+    // Chunk schedule: nothing overlaps the first copy in, so a multi-chunk call starts with a chunk of 1/8 of the full
+    // size and doubles up to it; the full-size chunks amortise the per-chunk launches and the tail of the persistent kernels.
+    std::vector<int64_t> sched;  // start offsets
+    {
+        int64_t pos = 0, cur = chunk;
+        if (n > chunk) cur = std::max<int64_t>(wave, chunk / 8 / wave * wave);
+        while (pos < n) {
+            sched.push_back(pos);
+            pos += std::min(cur, n - pos);
+            cur = std::min(chunk, cur * 2);
+        }
+        sched.push_back(n);
+    }
+    const int64_t nchunks = (int64_t)sched.size() - 1;
     int64_t first_bad = std::numeric_limits<int64_t>::max();
     // slot bookkeeping: what is in flight in each slot
     int64_t inflight_start[flexs_model::NSLOT], inflight_cnt[flexs_model::NSLOT];
@@ -393,7 +406,7 @@ static int score_host_impl(flexs_model_t *m, const char *h_chars, int64_t n, con
         const int slot = (int)(c % flexs_model::NSLOT);
         rc = drain(slot);
         if (rc != FLEXS_OK) return rc;
-        const int64_t start = c * chunk, cnt = std::min(chunk, n - start);
+        const int64_t start = sched[c], cnt = sched[c + 1] - start;
         cudaStream_t s = m->streams[slot];
         const void *src = h_chars + start * row_bytes;
         if (!in_pinned) { std::memcpy(m->h_pin_chars[slot], src, cnt * row_bytes); src = m->h_pin_chars[slot]; }

@@ -83,6 +83,12 @@ __global__ void dedup_mask_kernel(const float *__restrict__ scores, int64_t n, c
         out[i] = (minidx[slot_of[i]] == (long long)i) ? scores[i] : -INFINITY;
 }
 
+__global__ void dedup_rep_kernel(int64_t n, const long long *__restrict__ minidx, const unsigned int *__restrict__ slot_of,
+                                 long long *__restrict__ rep) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        rep[i] = minidx[slot_of[i]];
+}
+
 int64_t capacity_for(int64_t n) {
     int64_t cap = 1024;
     while (cap < 2 * n) cap <<= 1;
@@ -115,6 +121,26 @@ int flexs_dedup_scores_dev(const uint8_t *d_idx, int64_t n, int seq_len, const f
     dedup_clear_kernel<<<grid_cap, NT, 0, s>>>(slots, minidx, cap);
     dedup_insert_kernel<<<grid_n, NT, 0, s>>>(d_idx, n, seq_len, slots, minidx, cap, slot_of);
     dedup_mask_kernel<<<grid_n, NT, 0, s>>>(d_scores, n, minidx, slot_of, d_scores_out);
+    FX_CUDA(cudaGetLastError());
+    return FLEXS_OK;
+}
+
+int flexs_dedup_representatives_dev(const uint8_t *d_idx, int64_t n, int seq_len, int64_t *d_rep, void *d_work,
+                                    void *stream) {
+    FX_REQUIRE(n >= 0 && n < (1ll << 31), "n must be in [0, 2^31)");
+    if (n == 0) return FLEXS_OK;
+    FX_REQUIRE(d_idx && d_rep && d_work, "null buffer");
+    FX_REQUIRE(seq_len >= 1, "seq_len must be positive");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t cap = capacity_for(n);
+    unsigned long long *slots = reinterpret_cast<unsigned long long *>(d_work);
+    long long *minidx = reinterpret_cast<long long *>(slots + cap);
+    unsigned int *slot_of = reinterpret_cast<unsigned int *>(minidx + cap);
+    const int grid_cap = (int)std::min<int64_t>((cap + NT - 1) / NT, 148 * 8);
+    const int grid_n = (int)std::min<int64_t>((n + NT - 1) / NT, 148 * 8);
+    dedup_clear_kernel<<<grid_cap, NT, 0, s>>>(slots, minidx, cap);
+    dedup_insert_kernel<<<grid_n, NT, 0, s>>>(d_idx, n, seq_len, slots, minidx, cap, slot_of);
+    dedup_rep_kernel<<<grid_n, NT, 0, s>>>(n, minidx, slot_of, reinterpret_cast<long long *>(d_rep));
     FX_CUDA(cudaGetLastError());
     return FLEXS_OK;
 }

@@ -206,6 +206,35 @@ __device__ void finalize(unsigned long long *keys, unsigned long long *hs, unsig
     if (t == 0) *n_found = found;
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Visit every score once, a warp at a time over 128 consecutive elements (one 16-byte load per lane: four loads in
+// flight per thread hide the L2 latency a one-element-per-iteration loop is bound by).  fn(score, index, live) is called
+// by all 32 lanes together, four times per visit (live = the element exists), so it may use warp collectives.
+template <class Fn>
+__device__ __forceinline__ void for_each_score(const float *__restrict__ scores, long long n, Fn fn) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * NT + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * NT) >> 5;
+    const bool vec = (reinterpret_cast<uintptr_t>(scores) & 15) == 0;
+    for (long long base = warp * 128; base < n; base += nwarps * 128) {
+        const long long i0 = base + lane * 4;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (vec && i0 + 3 < n) {
+            const float4 q = __ldg(reinterpret_cast<const float4 *>(scores + i0));
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (i0 + e < n) v[e] = __ldg(scores + i0 + e);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) fn(v[e], i0 + e, i0 + e < n);
+    }
+}
+
 struct SelParams {
     const float *scores;
     long long n;
@@ -216,7 +245,7 @@ struct SelParams {
     float *top_scores;
     long long *top_idx;
     uint8_t *top_rows;
-    int *status;          // [0] = 1: fewer than k distinct rows among the candidates although the batch has more rows
+    int *status;          // int[8]; [0] = 1: fewer than k distinct rows among the candidates although the batch has more rows
     SelWork *work;
     unsigned long long *cand;
 };
@@ -235,12 +264,14 @@ __global__ void __launch_bounds__(NT, 1) topk_select_kernel(const SelParams p) {
     const long long gtid = (long long)blockIdx.x * NT + t;
     SelWork *w = p.work;
 
+    const unsigned long long t_start = globaltimer_ns();
     // the workspace cleans itself: no separate init launch
     for (long long i = gtid; i < (long long)(NLEVEL * NBIN); i += stride) (&w->hist[0][0])[i] = 0;
     if (gtid == 0) w->count = 0;
     grid.sync();
 
-    const unsigned int want = (unsigned int)min(p.n, (long long)(p.unique ? max(p.k, KSLACK) : p.k));
+    // unique: ask for 8 rows per wanted sequence (at least 4096), never more than the final sort takes
+    const unsigned int want = (unsigned int)min(p.n, (long long)(p.unique ? min(CAP, max(8 * p.k, KSLACK)) : p.k));
     unsigned long long prefix = 0;
     int bits_done = 0;
     unsigned int krem = want, above_total = 0;
@@ -252,11 +283,19 @@ __global__ void __launch_bounds__(NT, 1) topk_select_kernel(const SelParams p) {
             const int shift = 64 - bits_done - dbits;
             for (int i = t; i < NBIN; i += NT) sh[i] = 0;
             __syncthreads();
-            for (long long i = gtid; i < p.n; i += stride) {
-                const unsigned long long key = make_key(__ldg(p.scores + i), (unsigned int)i);
-                if (bits_done > 0 && (key >> (64 - bits_done)) != prefix) continue;
-                atomicAdd(&sh[(unsigned int)(key >> shift) & ((1u << dbits) - 1u)], 1u);
-            }
+            // Scores of one batch crowd into a few bins of the first digit (sign, exponent, 3 mantissa bits): the warp
+            // first agrees on who holds equal digits (match.any) and one lane adds the whole group — a handful of
+            // shared-memory atomics per warp and load instead of 32 colliding ones.
+            for_each_score(p.scores, p.n, [&](float sc, long long i, bool live) {
+                unsigned int digit = 0;
+                if (live) {
+                    const unsigned long long key = make_key(sc, (unsigned int)i);
+                    live = !(bits_done > 0 && (key >> (64 - bits_done)) != prefix);
+                    digit = (unsigned int)(key >> shift) & ((1u << dbits) - 1u);
+                }
+                const unsigned int peers = __match_any_sync(0xffffffffu, live ? digit : 0xffffffffu);
+                if (live && (unsigned int)(t & 31) == (unsigned int)(__ffs(peers) - 1)) atomicAdd(&sh[digit], (unsigned int)__popc(peers));
+            });
             __syncthreads();
             for (int i = t; i < NBIN; i += NT)
                 if (sh[i]) atomicAdd(&w->hist[level][i], sh[i]);
@@ -294,16 +333,18 @@ __global__ void __launch_bounds__(NT, 1) topk_select_kernel(const SelParams p) {
             prefix = thr_prefix; bits_done = thr_bits; krem -= above; above_total += above;
         }
         // collect every key at or above the threshold prefix
-        for (long long i = gtid; i < p.n; i += stride) {
-            const unsigned long long key = make_key(__ldg(p.scores + i), (unsigned int)i);
+        for_each_score(p.scores, p.n, [&](float sc, long long i, bool live) {
+            if (!live) return;
+            const unsigned long long key = make_key(sc, (unsigned int)i);
             if ((key >> (64 - thr_bits)) >= thr_prefix) {
                 const unsigned int slot = atomicAdd(&w->count, 1u);
                 if (slot < (unsigned int)CAP) p.cand[slot] = key;
             }
-        }
+        });
     }
     grid.sync();
     if (blockIdx.x != 0) return;
+    const unsigned long long t_collected = globaltimer_ns();
     const int m = (int)min(__ldcg(&w->count), (unsigned int)CAP);
     for (int i = t; i < m; i += NT) keys[i] = __ldcg(p.cand + i);
     __syncthreads();
@@ -327,8 +368,14 @@ __global__ void __launch_bounds__(NT, 1) topk_select_kernel(const SelParams p) {
         }
     }
     __syncthreads();
-    if (t == 0 && p.status != nullptr)
+    if (t == 0 && p.status != nullptr) {
         p.status[0] = (p.unique && s_nfound < p.k && (long long)m < p.n) ? 1 : 0;
+        // diagnostics: radix levels used, candidates sorted, ns spent selecting / in the final one-CTA stage
+        p.status[1] = thr_bits / DIGIT + (thr_bits % DIGIT ? 1 : 0);
+        p.status[2] = m;
+        p.status[3] = (int)(t_collected - t_start);
+        p.status[4] = (int)(globaltimer_ns() - t_collected);
+    }
 }
 
 struct MergeParams {

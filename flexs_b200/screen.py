@@ -100,6 +100,8 @@ class VirtualScreen:
         self.model, self.k, self.group, self.unique = model, int(k), group, bool(unique)
         self._buf = {}
         self.fallbacks = 0   # selections that needed the full hash de-duplication (almost-all-repeats batches)
+        self.launches = 0    # selection + merge kernels launched by this object (the surrogate counts its own)
+        self.forward_events = None   # set to a list: local_topk appends a (start, end) CUDA event pair around the forward
 
     def _world(self) -> Tuple[int, int]:
         import torch.distributed as dist
@@ -119,7 +121,7 @@ class VirtualScreen:
             self._buf[key] = dict(
                 msg=torch.zeros(mb, dtype=torch.uint8, device=device),
                 work=torch.empty(_native.topk_select_workspace_bytes(), dtype=torch.uint8, device=device),
-                status=torch.zeros(1, dtype=torch.int32, device=device),
+                status=torch.zeros(8, dtype=torch.int32, device=device),   # [0] = fell short; [1..4] diagnostics
                 gathered=torch.empty(world * mb, dtype=torch.uint8, device=device) if world > 1 else None,
                 fin=torch.zeros(mb, dtype=torch.uint8, device=device) if world > 1 else None)
         return self._buf[key]
@@ -137,7 +139,13 @@ class VirtualScreen:
         from flexs_b200 import _native
 
         idx = idx.contiguous()
+        if self.forward_events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         scores = self.model.get_fitness_device(idx)
+        if self.forward_events is not None:
+            ev[1].record()
+            self.forward_events.append(ev)
         n, L = int(idx.shape[0]), int(idx.shape[1])
         dev = scores.device
         buf = self._buffers(dev, L, self._world()[1])
@@ -148,7 +156,8 @@ class VirtualScreen:
                                     top_s.data_ptr(), top_i.data_ptr(), top_rows.data_ptr(), buf["status"].data_ptr(),
                                     buf["work"].data_ptr(), stream)
             self.last_status = buf["status"]
-            if check and self.unique and int(buf["status"].item()) != 0:
+            self.launches += 1
+            if check and self.unique and int(buf["status"][0].item()) != 0:
                 # almost every row of the batch is a repeat: hash all rows (dedup.cu), then select among first occurrences
                 self.fallbacks += 1
                 ranked = torch.empty_like(scores)
@@ -180,6 +189,7 @@ class VirtualScreen:
             _native.screen_merge_dev(buf["gathered"].data_ptr(), world, self.k, seq_len if self.unique else 0,
                                      fin_s.data_ptr(), fin_i.data_ptr(), fin_rows.data_ptr() if self.unique else 0,
                                      torch.cuda.current_stream().cuda_stream)
+        self.launches += 1
         return fin_s, fin_i
 
     def screen_indices(self, idx_local, index_offset: int = 0, check: bool = True):

@@ -167,6 +167,13 @@ int64_t flexs_dedup_workspace_bytes(int64_t n);
 int flexs_dedup_scores_dev(const uint8_t *d_idx, int64_t n, int seq_len, const float *d_scores,
                            float *d_scores_out, void *d_work, void *stream);
 
+/* The same table as a lookup: d_rep[i] = the lowest row index whose content equals row i (d_rep[i] == i
+ * for a first occurrence).  With the rows of a cache in front of a batch, d_rep answers "already seen?
+ * and where is its value?" for every candidate at once — the `seq in seen` / `seq in measured` dict
+ * lookups of cmaes.py:85-90 and dyna_ppo.py:310-314.  Same workspace as flexs_dedup_scores_dev.   */
+int flexs_dedup_representatives_dev(const uint8_t *d_idx, int64_t n, int seq_len, int64_t *d_rep,
+                                    void *d_work, void *stream);
+
 /* ---- K3c: single-launch selection and the multi-GPU merge -----------------------------------
  * flexs_topk_select_dev is flexs_topk_dev (+ flexs_dedup_scores_dev when `unique`) as ONE
  * cooperative kernel launch: radix select with 12-bit digits that stops as soon as the candidates
@@ -174,7 +181,9 @@ int flexs_dedup_scores_dev(const uint8_t *d_idx, int64_t n, int seq_len, const f
  * (equal rows must carry equal scores, which a deterministic surrogate guarantees).  Same result
  * as the two-call path, bit for bit; when the best max(k, 4096) rows do not hold k distinct
  * sequences although the batch has more rows, d_status[0] = 1 and the outputs are incomplete: the
- * caller then runs flexs_dedup_scores_dev + flexs_topk_dev (d_status may be NULL when !unique).
+ * caller then runs flexs_dedup_scores_dev + flexs_topk_dev.  d_status is int32[8] (may be NULL when
+ * !unique): [1..4] are diagnostics (radix levels used, candidates sorted, ns selecting, ns in the
+ * final one-CTA stage).
  * d_rows uint8[n, row_len] (may be NULL when !unique and d_top_rows is NULL); d_top_rows (may be
  * NULL) receives the winners' rows, uint8[k, row_len].  d_work: flexs_topk_select_workspace_bytes().
  *
@@ -209,6 +218,15 @@ int flexs_mutate_dev(const uint8_t *d_parents, int64_t n, int seq_len, int alpha
  * first `alphabet_size` of each row are compared; first maximum wins (np.argmax).         */
 int flexs_argmax_decode_dev(const float *d_x, int64_t n, int seq_len, int row_stride,
                             int alphabet_size, uint8_t *d_idx, void *stream);
+
+/* ---- K8: the density penalty of the DyNA-PPO environment ----------------------------------
+ * Replaces DynaPPOEnvironment.sequence_density (flexs/environments/dyna_ppo.py:106-114) applied to a
+ * whole batch: d_out[i] = sum over the n_seen rows o with 0 < d(new_i, o) <= radius of
+ * d_seen_fitness[o] / d(new_i, o), d = Levenshtein distance (the reference calls editdistance.eval,
+ * radius 2).  Rows are uint8[*, seq_len] residue indices; sums in float64, fixed order.            */
+int flexs_edit_density_dev(const uint8_t *d_new, int64_t n_new, const uint8_t *d_seen,
+                           const double *d_seen_fitness, int64_t n_seen, int seq_len, int radius,
+                           double *d_out, void *stream);
 
 /* ---- K4: training --------------------------------------------------------------------
  * Replaces keras Model.fit as called at keras_model.py:61-67 with the compile() of

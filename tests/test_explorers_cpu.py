@@ -191,3 +191,28 @@ def test_noisy_abstract_model_and_evaluate_drivers():
     res = flexs.evaluate.adaptivity(land, lambda r, b, q: Adalead(FakeModel(), r, b, q, "ATCATCAT", "ATCG", eval_batch_size=1),
                                     num_rounds=[1, 2], total_ground_truth_measurements=8, total_model_queries=24)
     assert [r[0] for r in res] == [1, 2]
+
+
+def test_device_sep_cma_matches_host_sampler_update():
+    """flexs_b200.utils.cma_device.SepCMA (torch tensors; here on the CPU) applies the same separable CMA update as the
+    host sampler flexs_b200.utils.cma given the same samples and values."""
+    import numpy as np
+    import torch
+
+    from flexs_b200.utils import cma, cma_device
+
+    n, pop = 600, 24
+    x0 = np.zeros(n); x0[::3] = 1
+    host = cma.CMAEvolutionStrategy(x0, 0.4, {"popsize": pop, "seed": 1}, full_cov_max_dim=16)
+    dev = cma_device.SepCMA(torch.from_numpy(x0), 0.4, pop, seed=1)
+    assert host.separable and dev.mu == host.mu
+    for _ in range(6):
+        X = np.array(host.ask())
+        f = ((X - 0.3) ** 2).sum(axis=1)
+        host.tell(list(X), list(f))
+        dev.tell(torch.from_numpy(X).float(), torch.from_numpy(f))
+        assert np.abs(host.mean - dev.mean.numpy()).max() < 1e-5
+        assert abs(host.sigma - dev.sigma) / host.sigma < 1e-6
+        assert np.abs(host.diagC - dev.diagC.numpy()).max() < 1e-5
+    samples = dev.ask()
+    assert samples.shape == (pop, n) and samples.dtype == torch.float32 and torch.isfinite(samples).all()

@@ -109,3 +109,179 @@ def test_config3_aav_additive_cnn_cmaes():
     table, meta = ex.run(land, verbose=False)
     _check_run(table, meta, 1, 10)
     assert cnn.cost <= 60 + 15
+
+
+def test_config1_adalead_device_rollouts_produce_a_million_model_queries():
+    """configs[1] as BASELINE words it — AdaLead ITSELF is the 1M-candidate virtual screen: 65 536 parallel rollouts on
+    the GPU (mutate -> "not measured, not found" -> fused forward -> continue while the child is at least as good as its
+    root), >= 1e6 model queries in ONE round, cost accounting as the reference's (every scored root and child is
+    charged), B-1 distinct unmeasured proposals ranked by the model."""
+    import random
+
+    random.seed(0)
+    land = MotifLandscape("GCTCGAGC", su.DNAA)
+    cnn = flexs.baselines.models.CNN(8, num_filters=32, hidden_size=100, alphabet=su.DNAA, loss="MSE", seed=0)
+    rng = np.random.default_rng(0)
+    start_seqs = ["TTTTTTTT"] + ["".join(r) for r in np.array(list(su.DNAA))[rng.integers(0, 4, size=(63, 8))]]
+    import pandas as pd
+
+    measured = pd.DataFrame({"sequence": start_seqs, "true_score": land.get_fitness(start_seqs), "model_score": np.nan,
+                             "round": 0, "model_cost": 0, "measurement_cost": len(start_seqs)})
+    cnn.train(measured["sequence"].to_numpy(), measured["true_score"].to_numpy())
+    B, Q, W = 100, 1_100_000, 65_536
+    ex = flexs.baselines.explorers.Adalead(cnn, rounds=1, sequences_batch_size=B, model_queries_per_batch=Q,
+                                          starting_sequence="TTTTTTTT", alphabet=su.DNAA, eval_batch_size=B,
+                                          rollout_width=W)
+    assert ex._use_device()
+    cost0 = cnn.cost
+    seqs, preds = ex.propose_sequences(measured)
+    spent = cnn.cost - cost0
+    stats = ex.last_device_stats
+    assert 1_000_000 <= spent < Q + W                      # the reference overshoots by less than one step too
+    assert stats["model_queries"] == spent and stats["found"] > 10_000
+    assert len(seqs) == B - 1 == len(set(seqs)) and not set(seqs) & set(start_seqs)
+    assert (np.diff(preds) <= 0).all()
+    direct = cnn.get_fitness(list(seqs))                    # the scores are the surrogate's scores of those strings
+    np.testing.assert_allclose(preds, direct, rtol=0, atol=1e-4 * max(1e-6, float(np.abs(direct).max())))
+    # the space has 65 536 sequences: a million queries found essentially all of it, and nothing beats the proposals
+    everything = np.array(np.meshgrid(*[np.arange(4)] * 8)).reshape(8, -1).T.astype(np.uint8)
+    all_scores = cnn.get_fitness(everything)
+    unmeasured = np.array([s not in set(start_seqs) for s in su.decode_indices(everything, su.DNAA)])
+    if stats["found"] >= 65_536 - 64:
+        best = np.sort(all_scores[unmeasured])[::-1][: B - 1]
+        np.testing.assert_allclose(preds, best, rtol=0, atol=1e-4 * float(np.abs(best).max()))
+
+
+def test_adalead_device_rollouts_small_budget_and_recombination():
+    """The device path at the reference's own scale (B = 100, Q = 2000, rho = 1): same bookkeeping as the host path."""
+    import random
+
+    random.seed(1)
+    land = MotifLandscape("GCUAGCUAGCUAGC", su.RNAA)
+    cnn = flexs.baselines.models.CNN(14, 32, 100, su.RNAA, loss="MSE", seed=1)
+    ex = flexs.baselines.explorers.Adalead(cnn, rounds=2, sequences_batch_size=100, model_queries_per_batch=2000,
+                                          starting_sequence="AUAUAUAUAUAUAU", alphabet=su.RNAA, eval_batch_size=100,
+                                          rho=1, recomb_rate=0.2)
+    table, meta = ex.run(land, verbose=False)
+    _check_run(table, meta, 2, 100)
+    assert ex.last_device_stats["model_queries"] <= 2000 + 100
+    per_round = table[table["round"] > 0].groupby("round").size()
+    assert (per_round == 99).all()                          # B-1 proposals per round, all distinct and new
+    assert table["sequence"].is_unique
+
+
+def test_config3_aav735_cnn_cmaes_device_population():
+    """configs[3] at full length: AAV 735-mers x 20 letters, CNN surrogate, CMA-ES with the population on the GPU
+    (separable sampler at dimension 14 700, argmax decode, cache lookup, fused forward, tell — no strings)."""
+    L = 735
+    rng = np.random.default_rng(0)
+    wt = "".join(np.array(list(su.AAS))[rng.integers(0, 20, size=L)])
+    land = MotifLandscape(wt, su.AAS)
+    cnn = flexs.baselines.models.CNN(L, num_filters=32, hidden_size=100, alphabet=su.AAS, loss="MSE", seed=3)
+    start = su.generate_random_mutant(wt, 0.05, su.AAS) if hasattr(su, "generate_random_mutant") else wt
+    pop, Q, B = 2048, 3 * 2048 + 100, 50
+    ex = flexs.baselines.explorers.CMAES(cnn, rounds=1, sequences_batch_size=B, model_queries_per_batch=Q,
+                                        starting_sequence=start, alphabet=su.AAS, population_size=pop, max_iter=10, seed=0)
+    assert ex._use_device()
+    table, meta = ex.run(land, verbose=False)
+    _check_run(table, meta, 1, B)
+    assert 2 * pop <= cnn.cost <= Q                          # three iterations fit the budget; cached members are free
+    proposed = table[table["round"] == 1]
+    assert len(proposed) >= 1 and proposed["sequence"].str.len().eq(L).all()
+    direct = cnn.get_fitness(list(proposed["sequence"]))
+    # proposals that the model scored carry the model's score (a re-proposed measured sequence carries its true score)
+    new = ~proposed["sequence"].isin([start]).to_numpy()
+    np.testing.assert_allclose(proposed["model_score"].to_numpy()[new], direct[new], rtol=0,
+                               atol=1e-4 * float(np.abs(direct).max()))
+
+
+def test_cmaes_device_matches_host_path_semantics_on_small_problem():
+    """Same seed-free invariants on a problem both paths can run: budget, cache hits are free, B-1 proposals."""
+    land = flexs.landscapes.AdditiveAAVPackaging(phenotype="heart", start=450, end=540, data_file=AAV_FILE)
+    start = land.wild_type
+    cnn = flexs.baselines.models.CNN(90, num_filters=32, hidden_size=100, alphabet=su.AAS, loss="MSE", seed=3)
+    ex = flexs.baselines.explorers.CMAES(cnn, rounds=1, sequences_batch_size=10, model_queries_per_batch=600,
+                                        starting_sequence=start, alphabet=su.AAS, population_size=64, max_iter=20,
+                                        seed=0, device_population=True)
+    table, meta = ex.run(land, verbose=False)
+    _check_run(table, meta, 1, 10)
+    assert cnn.cost <= 600 and cnn.cost > 0
+
+
+def test_edit_density_kernel_matches_python_environment():
+    """K8 (flexs_edit_density_dev) == the host environment's sequence_density (banded Levenshtein, radius 2, the
+    reference's environments/dyna_ppo.py:106-114) on sequences with planted substitutions, insertions and deletions."""
+    from flexs_b200.baselines.explorers.dyna_ppo import bounded_edit_distance
+
+    rng = np.random.default_rng(0)
+    L, A = 31, 20
+    base = rng.integers(0, A, size=(40, L), dtype=np.uint8)
+    seen = [base]
+    for _ in range(6):                                   # neighbours at distance 1-3 of the base rows
+        v = base.copy()
+        for r in range(len(v)):
+            kind = rng.integers(0, 4)
+            p = int(rng.integers(1, L - 2))
+            if kind == 0:
+                v[r, p] = (v[r, p] + 1) % A
+            elif kind == 1:
+                v[r, p] = (v[r, p] + 1) % A; v[r, (p + 7) % L] = (v[r, (p + 7) % L] + 3) % A
+            elif kind == 2:                              # delete one residue, append one: a shift (distance <= 2)
+                v[r] = np.concatenate([v[r, :p], v[r, p + 1:], [rng.integers(0, A)]])
+            else:
+                v[r, p:p + 3] = (v[r, p:p + 3] + 5) % A  # three substitutions: outside the radius
+        seen.append(v)
+    seen = np.concatenate(seen)
+    fit = rng.normal(size=len(seen))
+    fresh = np.concatenate([base[:10], seen[45:75], rng.integers(0, A, size=(8, L), dtype=np.uint8)])
+    strs = ["".join(chr(65 + c) for c in row) for row in seen]
+    want = []
+    for row in fresh:
+        s = "".join(chr(65 + c) for c in row)
+        dens = 0.0
+        for o, f in zip(strs, fit):
+            d = bounded_edit_distance(o, s, 2)
+            if d != 0 and d <= 2:
+                dens += f / d
+        want.append(dens)
+    d_new, d_seen = torch.from_numpy(fresh).cuda(), torch.from_numpy(seen).cuda()
+    d_fit = torch.from_numpy(fit).cuda()
+    out = torch.empty(len(fresh), dtype=torch.float64, device="cuda")
+    _native.edit_density_dev(d_new.data_ptr(), len(fresh), d_seen.data_ptr(), d_fit.data_ptr(), len(seen), L, 2, out.data_ptr())
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out.cpu().numpy(), np.array(want), rtol=1e-12, atol=1e-12)
+    assert np.count_nonzero(want) > 20
+
+
+def test_config4_gfp237_cnn_dynappo_device_rollouts():
+    """configs[4]: GFP-length proteins (237 x 20), CNN surrogate, DyNA-PPO with 1024 parallel constructive episodes on
+    the GPU: every episode end is ONE fused forward over uint8[1024, 237] (no strings, no one-hot), rewards carry the
+    density penalty (K8), proposals are the B best unmeasured sequences of the model-based round."""
+    L, E, B, Q = 237, 1024, 100, 2048
+    rng = np.random.default_rng(0)
+    wt = "".join(np.array(list(su.AAS))[rng.integers(0, 20, size=L)])
+    land = MotifLandscape(wt, su.AAS)
+    cnn = flexs.baselines.models.CNN(L, num_filters=32, hidden_size=100, alphabet=su.AAS, loss="MSE", seed=4)
+    ex = flexs.baselines.explorers.DynaPPO(land, rounds=1, sequences_batch_size=B, model_queries_per_batch=Q,
+                                          starting_sequence=wt, alphabet=su.AAS, model=cnn, num_model_rounds=1,
+                                          env_batch_size=E, seed=0)
+    assert ex._dev is not None
+    table, meta = ex.run(land, verbose=False)
+    assert table["round"].max() == 1 and np.isfinite(table["true_score"]).all()
+    proposed = table[table["round"] == 1]
+    assert len(proposed) == B and proposed["sequence"].is_unique                 # B items (not B-1): dyna_ppo.py:317
+    assert proposed["sequence"].str.len().eq(L).all()
+    assert proposed["sequence"].str[-1].eq(su.AAS[0]).all()                      # the last residue is never sampled (quirk 5)
+    assert cnn.cost == Q                                                         # two episodes of 1024 model queries
+    direct = cnn.get_fitness(list(proposed["sequence"]))
+    np.testing.assert_allclose(proposed["model_score"].to_numpy(), direct, rtol=0, atol=1e-4 * float(np.abs(direct).max()))
+    assert (np.diff(proposed["model_score"].to_numpy()) <= 0).all()
+    # the agent's first-layer shortcut is exact: incremental pre-activations == the dense product on the one-hot state
+    d = ex._dev
+    act = torch.from_numpy(rng.integers(0, 20, size=(3, L - 1))).to(d.dev)
+    h = d._hidden(d.params["aW1"], d.params["ab1"], act)
+    t = 100
+    state = torch.zeros((L, 21), device=d.dev); state[:, 20] = 1
+    state[torch.arange(t), 20] = 0; state[torch.arange(t), act[1, :t]] = 1
+    dense = d.params["ab1"] + torch.einsum("lc,lch->h", state, d.params["aW1"])
+    assert torch.allclose(h[1, t], dense, atol=1e-4)

@@ -747,12 +747,12 @@ def _select(scores, k, rows=None, unique=False, offset=0, want_rows=False):
     ts = torch.empty(k, dtype=torch.float32, device="cuda")
     ti = torch.empty(k, dtype=torch.int64, device="cuda")
     tr = torch.full((k, max(L, 1)), 255, dtype=torch.uint8, device="cuda") if want_rows else None
-    status = torch.full((1,), -7, dtype=torch.int32, device="cuda")
+    status = torch.full((8,), -7, dtype=torch.int32, device="cuda")
     _native.topk_select_dev(d.data_ptr(), n, k, offset, d_rows.data_ptr() if d_rows is not None else 0, L, unique,
                             ts.data_ptr(), ti.data_ptr(), tr.data_ptr() if tr is not None else 0, status.data_ptr(),
                             work.data_ptr(), torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
-    return ts.cpu().numpy(), ti.cpu().numpy(), (tr.cpu().numpy() if tr is not None else None), int(status.item())
+    return ts.cpu().numpy(), ti.cpu().numpy(), (tr.cpu().numpy() if tr is not None else None), int(status[0].item())
 
 
 @pytest.mark.parametrize("n,k", [(1, 1), (5, 8), (1000, 99), (70_000, 4096), (3_000_001, 99), (1 << 22, 1000)])
@@ -783,7 +783,9 @@ def test_topk_select_distinct_rows_lazy_dedup_exact(L, A, n, k):
     """`unique`: the k best DISTINCT rows through their first occurrence == the reference's ranking of dict keys,
     with the winners' rows written next to them; equal rows carry equal scores (a deterministic surrogate)."""
     rng = np.random.default_rng(L)
-    pool = rng.integers(0, A, size=(max(64, n // 7), L), dtype=np.uint8)       # ~7 copies of every row
+    copies = 7 if k < 500 else 3     # the select looks at the best max(8k, 4096) rows (<= 8192)
+    pool = np.unique(rng.integers(0, A, size=(max(64, n // copies), L), dtype=np.uint8), axis=0)   # distinct rows
+    pool = pool[rng.permutation(len(pool))]
     pick = rng.integers(0, len(pool), size=n)
     rows = pool[pick]
     pool_scores = (rng.integers(-2000, 2000, size=len(pool)) / 16).astype(np.float32)   # ties between different rows too
