@@ -201,7 +201,9 @@ int flexs_model_set_variant(flexs_model_t *m, int variant) {
         if (variant == FLEXS_VARIANT_UMMA) FX_REQUIRE(cnn_umma_supported(m), "UMMA variant not available for this shape");
         if (variant == FLEXS_VARIANT_UMMA_LUT) FX_REQUIRE(cnn_k9_supported(m), "UMMA_LUT variant needs A=4, F=32, k=5, H<=112, 8 <= L <= ~175");
     } else {
-        FX_REQUIRE(variant == FLEXS_VARIANT_AUTO || variant == FLEXS_VARIANT_ENUM, "MLP has a single kernel (plus the whole-model table)");
+        FX_REQUIRE(variant == FLEXS_VARIANT_AUTO || variant == FLEXS_VARIANT_ENUM || variant == FLEXS_VARIANT_TILED ||
+                   variant == FLEXS_VARIANT_UMMA, "MLP kernels: TILED (FP32 FFMA), UMMA (tcgen05), ENUM (whole-model table)");
+        if (variant == FLEXS_VARIANT_UMMA) FX_REQUIRE(mlp_umma_supported(m), "UMMA variant of the MLP needs H <= 112 and L <= ~550");
     }
     m->variant = variant;
     return FLEXS_OK;
@@ -209,7 +211,10 @@ int flexs_model_set_variant(flexs_model_t *m, int variant) {
 
 // variant of the fused kernels (never ENUM)
 static int direct_variant(const flexs_model *m, int64_t n) {
-    if (m->kind != FLEXS_KIND_CNN) return FLEXS_VARIANT_AUTO;
+    if (m->kind != FLEXS_KIND_CNN) {
+        if (m->variant == FLEXS_VARIANT_TILED || m->variant == FLEXS_VARIANT_UMMA) return m->variant;
+        return mlp_umma_supported(m) ? FLEXS_VARIANT_UMMA : FLEXS_VARIANT_TILED;
+    }
     if (m->variant != FLEXS_VARIANT_AUTO && m->variant != FLEXS_VARIANT_ENUM) return m->variant;
     if (cnn_k9_supported(m) && n >= (m->k9_ready ? K9_MIN_N_READY : K9_MIN_N)) return FLEXS_VARIANT_UMMA_LUT;
     if (cnn_umma_supported(m)) return FLEXS_VARIANT_UMMA;
@@ -275,7 +280,8 @@ int stream_workspace(flexs_model *m, cudaStream_t s, size_t bytes, flexs_model::
 }
 
 int forward_direct(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s) {
-    if (m->kind == FLEXS_KIND_MLP) return launch_mlp(m, d_idx, n, d_out, s);
+    if (m->kind == FLEXS_KIND_MLP)
+        return direct_variant(m, n) == FLEXS_VARIANT_UMMA ? launch_mlp_umma(m, d_idx, n, d_out, s) : launch_mlp(m, d_idx, n, d_out, s);
     switch (direct_variant(m, n)) {
         case FLEXS_VARIANT_UMMA_LUT: return launch_cnn_k9(m, d_idx, n, d_out, s);
         case FLEXS_VARIANT_UMMA: return launch_cnn_umma(m, d_idx, n, d_out, s);

@@ -136,6 +136,10 @@ int launch_enum(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, c
 // the fused kernels, without the whole-model table in front of them
 int forward_direct(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s);
 int launch_mlp(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s);
+int launch_mlp_gated(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, const int *d_gate, cudaStream_t s);
+// every MLP layer on tcgen05: one-hot x [W_hi | W_lo] streamed from L2 for layer 1, K = 112 GEMMs for layers 2-3 (mlp_umma.cu)
+bool mlp_umma_supported(const flexs_model *m);
+int launch_mlp_umma(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s);
 // k3 = 19 (A = 20) shapes: stream-interleaved rows, rolling activation rings, conv2 + conv3 on tcgen05 (cnn_a20.cu)
 bool cnn_a20_supported(const flexs_model *m);
 int launch_cnn_a20(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s);

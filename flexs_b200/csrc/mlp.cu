@@ -21,6 +21,7 @@ struct MlpParams {
     int64_t n, n_batches, member_floats;
     fx::MlpOffsets o;
     int L, A, H, M;
+    const int *gate;  // non-null: every CTA returns at once unless *gate != 0 (fp16-overflow fall-back of mlp_umma.cu)
 };
 
 __device__ __forceinline__ void dense_relu(const float *__restrict__ w, const float *__restrict__ b,
@@ -53,6 +54,7 @@ __device__ __forceinline__ void dense_relu(const float *__restrict__ w, const fl
 
 __global__ void __launch_bounds__(NT) mlp_kernel(const MlpParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (p.gate != nullptr && __ldg(p.gate) == 0) return;
     const int L = p.L, A = p.A, H = p.H;
     float *xa = reinterpret_cast<float *>(smem_raw);  // [H][SBP]
     float *xb = xa + (size_t)H * SBP;                  // [H][SBP]
@@ -111,7 +113,12 @@ __global__ void __launch_bounds__(NT) mlp_kernel(const MlpParams p) {
 namespace fx {
 
 int launch_mlp(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, cudaStream_t s) {
+    return launch_mlp_gated(m, d_idx, n, d_out, nullptr, s);
+}
+
+int launch_mlp_gated(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out, const int *d_gate, cudaStream_t s) {
     MlpParams p;
+    p.gate = d_gate;
     p.idx = d_idx; p.out = d_out; p.weights = m->d_weights; p.n = n;
     p.n_batches = (n + SB - 1) / SB;
     p.member_floats = m->member_floats; p.o = mlp_offsets(m);

@@ -104,89 +104,185 @@ __device__ __forceinline__ int pow2_at_least(int v) {
     return p;
 }
 
-// Final stage, one CTA.  keys[0 .. m) hold the candidates (any order), keys has room for pow2(m) entries, hs for as many.
-// RowOf(j) -> pointer to the row of the candidate whose key's low word decodes to position j (nullptr semantics: L == 0
-// means "rank rows, not distinct rows").  IdxOf(j) -> the index to report.  Writes k winners (score desc, position asc),
-// their rows when top_rows != nullptr, and returns through *short_of whether fewer than k distinct candidates exist.
-template <class RowOf, class IdxOf>
-__device__ void finalize(unsigned long long *keys, unsigned long long *hs, unsigned short *rank_of, int m, int k, int L,
-                         RowOf row_of, IdxOf idx_of, float *top_scores, long long *top_idx, uint8_t *top_rows,
-                         int *n_found) {
+// ---- final stage, one CTA ----------------------------------------------------------------------------------------
+// bin of rank `krem` (counted from the top) in a 4096-bin histogram: suffix sums, 8 consecutive bins per thread.
+// All NT threads call it; returns through shared memory (bin, count above the bin, count in the bin).
+__device__ void find_bin(const unsigned int *hist, bool global, unsigned int krem, unsigned int &bin, unsigned int &above,
+                         unsigned int &cnt) {
+    __shared__ unsigned int s_part[NT], s_res[3];
+    const int t = threadIdx.x;
+    constexpr int PER = NBIN / NT;
+    unsigned int loc[PER], tot = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { loc[i] = global ? __ldcg(hist + t * PER + i) : hist[t * PER + i]; tot += loc[i]; }
+    s_part[t] = tot;
+    __syncthreads();
+    for (int off = 1; off < NT; off <<= 1) {   // suffix[t] = sum of s_part[t ..]
+        const unsigned int v = (t + off < NT) ? s_part[t + off] : 0u;
+        __syncthreads();
+        s_part[t] += v;
+        __syncthreads();
+    }
+    unsigned int cum = s_part[t] - tot;  // bins above my span
+    if (cum < krem && cum + tot >= krem) {
+#pragma unroll
+        for (int i = PER - 1; i >= 0; --i) {
+            if (cum + loc[i] >= krem) { s_res[0] = (unsigned int)(t * PER + i); s_res[1] = cum; s_res[2] = loc[i]; break; }
+            cum += loc[i];
+        }
+    }
+    __syncthreads();
+    bin = s_res[0]; above = s_res[1]; cnt = s_res[2];
+    __syncthreads();
+}
+
+// The candidates a grid-level descent leaves can be thousands although only the best `need` matter: the same radix
+// descent, inside the CTA over the keys in shared memory, narrows them to at most NARROW keys before anything is sorted
+// (sorting 8192 keys costs 91 bitonic stages of 8 exchanges per thread; 2048 keys cost 66 stages of 2).
+constexpr int NARROW = 2048;
+__device__ int narrow(const unsigned long long *src, int m, unsigned int need, unsigned long long *dst, unsigned int *hist) {
+    __shared__ unsigned int s_cnt;
+    const int t = threadIdx.x;
+    unsigned long long prefix = 0, thr_prefix = 0;
+    int bits_done = 0, thr_bits = 0;
+    unsigned int krem = need, above_total = 0;
+    for (int level = 0; level < NLEVEL; ++level) {
+        const int dbits = min(DIGIT, 64 - bits_done), shift = 64 - bits_done - dbits;
+        for (int i = t; i < NBIN; i += NT) hist[i] = 0;
+        __syncthreads();
+        for (int i0 = t & ~31; i0 < m; i0 += NT) {          // a warp over 32 consecutive keys, equal digits added once
+            const int i = i0 + (t & 31);
+            bool live = i < m;
+            unsigned int digit = 0;
+            if (live) {
+                const unsigned long long key = src[i];
+                live = !(bits_done > 0 && (key >> (64 - bits_done)) != prefix);
+                digit = (unsigned int)(key >> shift) & ((1u << dbits) - 1u);
+            }
+            const unsigned int peers = __match_any_sync(0xffffffffu, live ? digit : 0xffffffffu);
+            if (live && (t & 31) == __ffs(peers) - 1) atomicAdd(&hist[digit], (unsigned int)__popc(peers));
+        }
+        __syncthreads();
+        unsigned int b, above, cnt;
+        find_bin(hist, false, krem, b, above, cnt);
+        thr_prefix = (prefix << dbits) | b;
+        thr_bits = bits_done + dbits;
+        if (above_total + above + cnt <= (unsigned int)NARROW || thr_bits == 64) break;
+        prefix = thr_prefix; bits_done = thr_bits; krem -= above; above_total += above;
+    }
+    if (t == 0) s_cnt = 0;
+    __syncthreads();
+    for (int i = t; i < m; i += NT) {
+        const unsigned long long key = src[i];
+        if ((key >> (64 - thr_bits)) >= thr_prefix) dst[atomicAdd(&s_cnt, 1u)] = key;
+    }
+    __syncthreads();
+    const int m1 = (int)s_cnt;
+    __syncthreads();
+    return m1;
+}
+
+// keys[0 .. m) sorted descending (rank order).  Marks repeats among growing prefixes (starting at P0) until k distinct
+// rows are found; rank_of[0 .. found) receives the ranks of the survivors in order.  L == 0: no de-duplication.
+template <class RowOf>
+__device__ int pick_distinct(const unsigned long long *keys, unsigned long long *hs, unsigned short *rank_of, int m, int P0,
+                             int k, int L, RowOf row_of) {
     __shared__ int s_found, s_scan[NT];
     const int t = threadIdx.x;
-    const int len = pow2_at_least(max(m, 2));
-    for (int i = m + t; i < len; i += NT) keys[i] = 0ull;
-    __syncthreads();
-    bitonic_sort<true>(keys, len);
-    // keys[0..m) sorted descending: rank order.  keep[i] (bit 63 of hs reused as scratch is avoided: separate pass)
-    int found = 0;
     if (L == 0) {
-        found = min(m, k);
+        const int found = min(m, k);
         for (int i = t; i < found; i += NT) rank_of[i] = (unsigned short)i;
         __syncthreads();
-    } else {
-        // de-duplicate growing prefixes of the ranking until k distinct rows are found (the first prefix nearly always is)
-        for (int P = min(m, 1024);; P = min(m, P * 2)) {
-            const int plen = pow2_at_least(max(P, 2));
-            for (int i = t; i < plen; i += NT) {
-                if (i < P) {
-                    const unsigned int pos = 0xffffffffu - (unsigned int)(keys[i] & 0xffffffffu);
-                    hs[i] = (hash_row(row_of(pos), L) & ~0x1fffull) | (unsigned long long)i;   // 51 hash bits | rank (13 bits)
-                } else hs[i] = ~0ull;
-            }
-            __syncthreads();
-            bitonic_sort<false>(hs, plen);   // ascending: equal hashes adjacent, by rank
-            // a candidate is a repeat iff an earlier member of its hash run has the same row (the run is walked from its
-            // head: a batch of identical rows costs one comparison per row, not a quadratic number)
-            for (int i = t; i < P; i += NT) {
-                const unsigned long long e = hs[i];
-                const int rk = (int)(e & 0x1fffull);
-                bool dup = false;
-                int j = i;
-                while (j > 0 && (hs[j - 1] >> 13) == (e >> 13)) --j;
-                if (j < i) {
-                    const uint8_t *mine = row_of(0xffffffffu - (unsigned int)(keys[rk] & 0xffffffffu));
-                    for (; j < i && !dup; ++j) {
-                        const int rj = (int)(hs[j] & 0x1fffull);
-                        dup = rows_equal(mine, row_of(0xffffffffu - (unsigned int)(keys[rj] & 0xffffffffu)), L);
-                    }
+        return found;
+    }
+    for (int P = min(m, P0);; P = min(m, P * 2)) {
+        const int plen = pow2_at_least(max(P, 2));
+        for (int i = t; i < plen; i += NT) {
+            if (i < P) {
+                const unsigned int pos = 0xffffffffu - (unsigned int)(keys[i] & 0xffffffffu);
+                hs[i] = (hash_row(row_of(pos), L) & ~0x1fffull) | (unsigned long long)i;   // 51 hash bits | rank (13 bits)
+            } else hs[i] = ~0ull;
+        }
+        __syncthreads();
+        bitonic_sort<false>(hs, plen);   // ascending: equal hashes adjacent, by rank
+        // a candidate is a repeat iff an earlier member of its hash run has the same row (the run is walked from its
+        // head: a batch of identical rows costs one comparison per row, not a quadratic number)
+        for (int i = t; i < P; i += NT) {
+            const unsigned long long e = hs[i];
+            const int rk = (int)(e & 0x1fffull);
+            bool dup = false;
+            int j = i;
+            while (j > 0 && (hs[j - 1] >> 13) == (e >> 13)) --j;
+            if (j < i) {
+                const uint8_t *mine = row_of(0xffffffffu - (unsigned int)(keys[rk] & 0xffffffffu));
+                for (; j < i && !dup; ++j) {
+                    const int rj = (int)(hs[j] & 0x1fffull);
+                    dup = rows_equal(mine, row_of(0xffffffffu - (unsigned int)(keys[rj] & 0xffffffffu)), L);
                 }
-                rank_of[rk] = dup ? 1 : 0;   // scratch: repeat flag by rank
             }
+            rank_of[rk] = dup ? 1 : 0;   // scratch: repeat flag by rank
+        }
+        __syncthreads();
+        // ordered compaction of the survivors: block scan over ranks, each thread owns a contiguous span
+        const int span = (P + NT - 1) / NT, lo = t * span, hi = min(P, lo + span);
+        int mine_cnt = 0;
+        for (int i = lo; i < hi; ++i) mine_cnt += rank_of[i] ? 0 : 1;
+        s_scan[t] = mine_cnt;
+        __syncthreads();
+        for (int off = 1; off < NT; off <<= 1) {
+            const int v = (t >= off) ? s_scan[t - off] : 0;
             __syncthreads();
-            // ordered compaction of the survivors: block scan over ranks, each thread owns a contiguous span
-            const int span = (P + NT - 1) / NT, lo = t * span, hi = min(P, lo + span);
-            int mine_cnt = 0;
-            for (int i = lo; i < hi; ++i) mine_cnt += rank_of[i] ? 0 : 1;
-            s_scan[t] = mine_cnt;
-            __syncthreads();
-            for (int off = 1; off < NT; off <<= 1) {
-                const int v = (t >= off) ? s_scan[t - off] : 0;
-                __syncthreads();
-                s_scan[t] += v;
-                __syncthreads();
-            }
-            if (t == NT - 1) s_found = s_scan[t];
-            int base = s_scan[t] - mine_cnt;
-            __syncthreads();
-            // survivors' ranks into hs (as plain ints, reusing the buffer after the scan consumed the flags)
-            unsigned int *surv = reinterpret_cast<unsigned int *>(hs);
-            __syncthreads();
-            for (int i = lo; i < hi; ++i)
-                if (!rank_of[i] && base < k) surv[base++] = (unsigned int)i;
-            __syncthreads();
-            found = min(s_found, k);
-            if (found >= k || P >= m) {
-                for (int i = t; i < found; i += NT) rank_of[i] = (unsigned short)surv[i];
-                __syncthreads();
-                break;
-            }
+            s_scan[t] += v;
             __syncthreads();
         }
+        if (t == NT - 1) s_found = s_scan[t];
+        int base = s_scan[t] - mine_cnt;
+        __syncthreads();
+        unsigned int *surv = reinterpret_cast<unsigned int *>(hs);   // the hash order is spent: survivors' ranks go here
+        for (int i = lo; i < hi; ++i)
+            if (!rank_of[i] && base < k) surv[base++] = (unsigned int)i;
+        __syncthreads();
+        const int found = min(s_found, k);
+        if (found >= k || P >= m) {
+            for (int i = t; i < found; i += NT) rank_of[i] = (unsigned short)surv[i];
+            __syncthreads();
+            return found;
+        }
+        __syncthreads();
+    }
+}
+
+// k0[0 .. m) hold the candidates (any order); k1 and k2 are scratch of CAP keys each.  RowOf(pos) -> the row of the
+// candidate whose key decodes to position pos (L == 0: rank rows, not distinct rows); IdxOf(pos) -> the index to report.
+// Writes k winners (score desc, position asc), their rows when top_rows != nullptr, and the number found.
+template <class RowOf, class IdxOf>
+__device__ void finalize(unsigned long long *k0, unsigned long long *k1, unsigned long long *k2, unsigned short *rank_of,
+                         int m, int k, int L, RowOf row_of, IdxOf idx_of, float *top_scores, long long *top_idx,
+                         uint8_t *top_rows, int *n_found) {
+    const int t = threadIdx.x;
+    const unsigned long long *sorted = nullptr;
+    int found = -1;
+    const int need = (L == 0) ? k : max(k, 1024);   // rows the first attempt ranks (unique: room for repeats)
+    if (need <= 1024 && m > NARROW) {
+        const int m1 = narrow(k0, m, (unsigned int)min(m, need), k1, reinterpret_cast<unsigned int *>(k2));
+        const int len1 = pow2_at_least(max(m1, 2));
+        for (int i = m1 + t; i < len1; i += NT) k1[i] = 0ull;
+        __syncthreads();
+        bitonic_sort<true>(k1, len1);
+        const int f = pick_distinct(k1, k2, rank_of, m1, m1, k, L, row_of);
+        if (f >= k || m1 >= m) { found = f; sorted = k1; }
+    }
+    if (found < 0) {   // few candidates, a large k, or a narrowed set that is mostly repeats: rank all of them
+        const int len = pow2_at_least(max(m, 2));
+        for (int i = m + t; i < len; i += NT) k0[i] = 0ull;
+        __syncthreads();
+        bitonic_sort<true>(k0, len);
+        found = pick_distinct(k0, k2, rank_of, m, 1024, k, L, row_of);
+        sorted = k0;
     }
     for (int i = t; i < k; i += NT) {
         if (i < found) {
-            const unsigned long long key = keys[rank_of[i]];
+            const unsigned long long key = sorted[rank_of[i]];
             const unsigned int pos = 0xffffffffu - (unsigned int)(key & 0xffffffffu);
             top_scores[i] = unord32((unsigned int)(key >> 32));
             top_idx[i] = idx_of(pos);
@@ -199,7 +295,7 @@ __device__ void finalize(unsigned long long *keys, unsigned long long *hs, unsig
         for (int i = t; i < k * L; i += NT) {
             const int w = i / L, b = i - w * L;
             uint8_t v = 0;
-            if (w < found) v = row_of(0xffffffffu - (unsigned int)(keys[rank_of[w]] & 0xffffffffu))[b];
+            if (w < found) v = row_of(0xffffffffu - (unsigned int)(sorted[rank_of[w]] & 0xffffffffu))[b];
             top_rows[i] = v;
         }
     }
@@ -253,11 +349,9 @@ struct SelParams {
 __global__ void __launch_bounds__(NT, 1) topk_select_kernel(const SelParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);       // CAP keys; first NBIN words double as the level histogram
-    unsigned long long *hs = keys + CAP;
-    unsigned short *rank_of = reinterpret_cast<unsigned short *>(hs + CAP);
+    unsigned long long *k1 = keys + CAP, *k2 = k1 + CAP;
+    unsigned short *rank_of = reinterpret_cast<unsigned short *>(k2 + CAP);
     unsigned int *sh = reinterpret_cast<unsigned int *>(smem_raw);
-    __shared__ unsigned int s_bin, s_above, s_cnt;
-    __shared__ unsigned int s_part[NT];
     cg::grid_group grid = cg::this_grid();
     const int t = threadIdx.x;
     const long long stride = (long long)gridDim.x * NT;
@@ -300,33 +394,9 @@ __global__ void __launch_bounds__(NT, 1) topk_select_kernel(const SelParams p) {
             for (int i = t; i < NBIN; i += NT)
                 if (sh[i]) atomicAdd(&w->hist[level][i], sh[i]);
             grid.sync();
-            // every CTA finds the bin that holds rank `krem` counting from the top: suffix sums over 4096 bins,
-            // 8 consecutive bins per thread
-            const unsigned int *h = w->hist[level];
-            constexpr int PER = NBIN / NT;
-            unsigned int loc[PER], tot = 0;
-#pragma unroll
-            for (int i = 0; i < PER; ++i) { loc[i] = __ldcg(h + t * PER + i); tot += loc[i]; }
-            s_part[t] = tot;
-            __syncthreads();
-            // suffix[t] = sum of s_part[t+1 ..]: count in all bins above this thread's span
-            for (int off = 1; off < NT; off <<= 1) {
-                const unsigned int v = (t + off < NT) ? s_part[t + off] : 0u;
-                __syncthreads();
-                s_part[t] += v;
-                __syncthreads();
-            }
-            unsigned int cum = s_part[t] - tot;  // bins above my span
-            if (cum < krem && cum + tot >= krem) {
-#pragma unroll
-                for (int i = PER - 1; i >= 0; --i) {
-                    if (cum + loc[i] >= krem) { s_bin = (unsigned int)(t * PER + i); s_above = cum; s_cnt = loc[i]; break; }
-                    cum += loc[i];
-                }
-            }
-            __syncthreads();
-            const unsigned int b = s_bin, above = s_above, cnt = s_cnt;
-            __syncthreads();
+            // every CTA finds the bin that holds rank `krem` counting from the top
+            unsigned int b, above, cnt;
+            find_bin(w->hist[level], true, krem, b, above, cnt);
             thr_prefix = (prefix << dbits) | b;
             thr_bits = bits_done + dbits;
             if (above_total + above + cnt <= (unsigned int)CAP || thr_bits == 64) break;
@@ -352,7 +422,7 @@ __global__ void __launch_bounds__(NT, 1) topk_select_kernel(const SelParams p) {
     const uint8_t *rows = p.rows;
     const int L = (p.unique && rows != nullptr) ? p.row_len : 0;
     const long long off = p.index_offset;
-    finalize(keys, hs, rank_of, m, p.k, L,
+    finalize(keys, k1, k2, rank_of, m, p.k, L,
              [rows, L2 = p.row_len](unsigned int pos) { return rows + (size_t)pos * L2; },
              [off](unsigned int pos) { return (long long)pos + off; },
              p.top_scores, p.top_idx, p.top_rows, &s_nfound);
@@ -390,8 +460,8 @@ struct MergeParams {
 __global__ void __launch_bounds__(NT, 1) screen_merge_kernel(const MergeParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);
-    unsigned long long *hs = keys + CAP;
-    unsigned short *rank_of = reinterpret_cast<unsigned short *>(hs + CAP);
+    unsigned long long *k1 = keys + CAP, *k2 = k1 + CAP;
+    unsigned short *rank_of = reinterpret_cast<unsigned short *>(k2 + CAP);
     __shared__ int s_m, s_nfound;
     const int t = threadIdx.x, total = p.world * p.k;
     if (t == 0) s_m = 0;
@@ -410,7 +480,7 @@ __global__ void __launch_bounds__(NT, 1) screen_merge_kernel(const MergeParams p
     const unsigned char *g = p.gathered;
     const int k = p.k, L = p.row_len;
     const long long mb = p.msg_bytes, orow = p.off_rows;
-    finalize(keys, hs, rank_of, s_m, k, L,
+    finalize(keys, k1, k2, rank_of, s_m, k, L,
              [g, k, L, mb, orow](unsigned int j) {
                  const int r = (int)j / k, i = (int)j - r * k;
                  return reinterpret_cast<const uint8_t *>(g + (size_t)r * mb + orow + (size_t)i * L);
@@ -422,7 +492,7 @@ __global__ void __launch_bounds__(NT, 1) screen_merge_kernel(const MergeParams p
              p.top_scores, p.top_idx, p.top_rows, &s_nfound);
 }
 
-constexpr size_t FINAL_SMEM = (size_t)CAP * 8 * 2 + (size_t)CAP * 2;
+constexpr size_t FINAL_SMEM = (size_t)CAP * 8 * 3 + (size_t)CAP * 2;
 
 }  // namespace
 

@@ -338,22 +338,52 @@ def test_ensemble_mean_fused(members):
     m.close()
 
 
-@pytest.mark.parametrize("L,A,H,n", [(8, 4, 100, 1000), (3, 4, 1, 5), (14, 4, 200, 130), (90, 20, 100, 77)])
-def test_mlp_forward_parity(L, A, H, n):
+def _mlp_variants(model):
+    vs = []
+    for v in (_native.VARIANT_TILED, _native.VARIANT_UMMA):      # FP32 FFMA kernel / every layer on tcgen05 (H <= 112)
+        try:
+            model.set_variant(v)
+            vs.append(v)
+        except ValueError:
+            pass
+    model.set_variant(_native.VARIANT_AUTO)
+    return vs
+
+
+@pytest.mark.parametrize("L,A,H,n", [(8, 4, 100, 1000), (3, 4, 1, 5), (14, 4, 200, 130), (90, 20, 100, 77), (100, 4, 100, 2500),
+                                     (237, 20, 100, 300), (8, 4, 112, 129), (5, 7, 33, 128)])
+@pytest.mark.parametrize("wname", ["glorot", "trained"])
+def test_mlp_forward_parity(L, A, H, n, wname):
+    """Both MLP kernels (FP32 FFMA; every layer on tcgen05 with the one-hot built as an exact fp16 operand) against the
+    float64 definition of mlp.py:21-31, scale-normalised and element by element; ensembles too."""
     ms = fo.MLPShape(L, A, H)
-    ws = fo.trained_like_weights(ms.weight_shapes(), 4)
+    make = fo.glorot_weights if wname == "glorot" else fo.trained_like_weights
+    ws = make(ms.weight_shapes(), 4)
     idx = np.random.default_rng(2).integers(0, A, size=(n, L), dtype=np.uint8)
     ref = fo.mlp_forward(idx, ws, np.float64)
     m = _native.NativeModel("mlp", seq_len=L, alphabet_size=A, hidden_size=H)
     m.set_weights(ws)
-    assert rel_err(_device_forward(m, idx), ref, _floor(ref)) < TOL
+    vs = _mlp_variants(m)
+    assert _native.VARIANT_TILED in vs and ((_native.VARIANT_UMMA in vs) == (H <= 112))
+    for v in vs:
+        m.set_variant(v)
+        got = _device_forward(m, idx)
+        parity_report(f"mlp{L}x{A}_H{H}/{wname}/{_native.VARIANT_NAMES[v]}", scale_rel=rel_err(got, ref, _floor(ref)),
+                      elem_rel=elem_rel_err(got, ref)[0], n=n)
+        assert rel_err(got, ref, _floor(ref)) < TOL, v
+        assert elem_rel_err(got, ref)[0] < TOL, v
+    m.set_variant(_native.VARIANT_AUTO)
+    assert m.active_variant(n) in ((_native.VARIANT_UMMA if H <= 112 else _native.VARIANT_TILED), _native.VARIANT_ENUM)
     m.close()
     # ensemble of MLPs
-    ws2 = fo.trained_like_weights(ms.weight_shapes(), 5)
+    ws2 = make(ms.weight_shapes(), 5)
     m2 = _native.NativeModel("mlp", seq_len=L, alphabet_size=A, hidden_size=H, n_members=2)
     m2.set_weights(ws, 0); m2.set_weights(ws2, 1)
     ref2 = fo.ensemble_mean([fo.nan_to_num_f32(ref), fo.nan_to_num_f32(fo.mlp_forward(idx, ws2, np.float64))])
-    assert rel_err(_device_forward(m2, idx), ref2, _floor(ref2)) < TOL
+    for v in _mlp_variants(m2):
+        m2.set_variant(v)
+        assert rel_err(_device_forward(m2, idx), ref2, _floor(ref2)) < TOL, v
+    m2.close()
     m2.close()
 
 
@@ -869,3 +899,20 @@ def test_screen_merge_kernel_matches_reference_merge(world, k, L):
     if L:
         np.testing.assert_array_equal(fr.cpu().numpy()[:m], want_rows)
     assert np.all(fi.cpu().numpy()[m:] == -1)
+
+
+def test_mlp_fp16_range_guard_falls_back_to_fp32_kernel():
+    """The tcgen05 MLP carries hidden activations as scaled fp16 hi/lo pairs: values above 60000/8 raise the per-stream
+    flag and the gated FP32 kernel recomputes the batch — same contract as the CNN kernels."""
+    L, A, H, n = 20, 4, 100, 300
+    ms = fo.MLPShape(L, A, H)
+    ws = fo.trained_like_weights(ms.weight_shapes(), 2)
+    ws[0] = ws[0] * np.float32(3e4)          # layer-1 activations far beyond the fp16 window
+    idx = np.random.default_rng(0).integers(0, A, size=(n, L), dtype=np.uint8)
+    ref = fo.mlp_forward(idx, ws, np.float64)
+    m = _native.NativeModel("mlp", seq_len=L, alphabet_size=A, hidden_size=H)
+    m.set_weights(ws)
+    m.set_variant(_native.VARIANT_UMMA)
+    got = _device_forward(m, idx)
+    assert np.isfinite(got).all() and rel_err(got, ref, _floor(ref)) < TOL
+    m.close()
