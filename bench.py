@@ -133,7 +133,8 @@ def dedup_timing(device):
             res[name] = ev[0].elapsed_time(ev[1]) / 5
         st = status.cpu().tolist()
         res["identical_winners"] = bool(torch.equal(ti, ti2) and torch.equal(ts, ts2)) and st[0] == 0
-        res["select_diagnostics"] = {"radix_levels": st[1], "candidates": st[2], "select_us": st[3] / 1e3, "final_cta_us": st[4] / 1e3}
+        res["select_diagnostics"] = {"radix_levels": st[1], "candidates": st[2], "select_us": st[3] / 1e3, "final_cta_us": st[4] / 1e3,
+                                     "final_narrow_us": st[5] / 1e3, "final_sort_us": st[6] / 1e3, "final_dedup_us": st[7] / 1e3}
         res["sequences_per_s"] = n / (res["select_single_launch_ms"] / 1e3)
         res["distinct_in_top"] = int(len({bytes(r) for r in idx[ti2.clamp(min=0)].cpu().numpy()}))
         out[tag] = res
@@ -509,7 +510,10 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
+
+
+_JSON_OUT = sys.stdout
 
 
 def main():
@@ -525,6 +529,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner) goes to stderr
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank)
         return
@@ -656,7 +665,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 if __name__ == "__main__":

@@ -170,12 +170,19 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
 
     if (wid < W_E2) {
         // =========================== conv1 producers ===========================
-        // lane = 4 b + cc moves 8 channels (cc) of stream b: the 4 lanes of a stream read one whole 128-byte table row,
-        // the warp writes the 32 16-byte chunks of one group to 8 different bank groups, 4 rows each (4 wavefronts).
+        // lane = 4 b + cc moves 8 channels (cc) of stream b: the 4 lanes of a stream read one whole 128-byte table row with
+        // adjacent lanes (moving them 8 lanes apart made the gathers — which sit on the conv2 -> conv1 -> conv2 chain of
+        // the two-chunk ring — slower by more than the stores gained: -9 % overall).  A 128-bit shared-memory store is
+        // processed per quarter-warp (8 adjacent lanes = two rows b): writing "hi" from all lanes puts both rows on the
+        // same four bank groups (every store replayed once — ncu source view of the first version,
+        // profiles/r02_a20_ncu_summary.txt).  Odd rows therefore store their lo chunk first and their hi chunk second:
+        // chunk (4 + cc) ^ b lies in the other four bank groups, and each store instruction covers all eight.
         const int b = lane >> 2, cc = lane & 3;
         const float *t012 = reinterpret_cast<const float *>(p.uw + A20_OFF_T012) + cc * 8;
         const float *t34 = reinterpret_cast<const float *>(p.uw + A20_OFF_T34) + cc * 8;
         const uint32_t row_off = (uint32_t)(b * 128), hi_off = (uint32_t)((cc ^ b) << 4), lo_off = (uint32_t)(((4 + cc) ^ b) << 4);
+        const bool odd = (b & 1) != 0;
+        const uint32_t first_off = odd ? lo_off : hi_off, second_off = odd ? hi_off : lo_off;
         if (tid == 0 && (int64_t)blockIdx.x < p.n_items) issue_idx_load(p, smem_raw + S_IDX, &bar[B_IDX], blockIdx.x);
         uint32_t g1 = 0, itc = 0;
         for (int64_t item = blockIdx.x; item < p.n_items; item += stride, ++itc) {
@@ -222,11 +229,12 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
                     }
                     const uint32_t gr = slot * 16u + (uint32_t)(wid + 4 * i);
                     const uint32_t row = r1_addr + gr * 1024u + row_off;
-                    st_shared_v4(row + hi_off, hi4);
-                    st_shared_v4(row + lo_off, lo4);
+                    const uint4 first4 = odd ? lo4 : hi4, second4 = odd ? hi4 : lo4;
+                    st_shared_v4(row + first_off, first4);
+                    st_shared_v4(row + second_off, second4);
                     if (gr < (uint32_t)R1M) {  // head of the ring, mirrored behind its end
-                        st_shared_v4(row + R1C * 16 * 1024 + hi_off, hi4);
-                        st_shared_v4(row + R1C * 16 * 1024 + lo_off, lo4);
+                        st_shared_v4(row + R1C * 16 * 1024 + first_off, first4);
+                        st_shared_v4(row + R1C * 16 * 1024 + second_off, second4);
                     }
                 }
                 fence_async_smem();
@@ -266,12 +274,16 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
                         }
 #pragma unroll
                         for (int h8 = 0; h8 < 2; ++h8) {
+                            // the biases as two 16-byte broadcasts (scalar loads were 32 wavefronts per thread and tile)
+                            const float4 ba = *reinterpret_cast<const float4 *>(b2s + hf * 16 + h8 * 8);
+                            const float4 bb = *reinterpret_cast<const float4 *>(b2s + hf * 16 + h8 * 8 + 4);
+                            const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
                             float x[8];
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 const int col = h8 * 8 + i;
                                 const float acc = __uint_as_float(v[col]) + __uint_as_float(v2[col]);
-                                x[i] = valid ? fmaxf(fmaf(acc, inv2s, b2s[hf * 16 + col]), 0.f) : 0.f;
+                                x[i] = valid ? fmaxf(fmaf(acc, inv2s, bias[i]), 0.f) : 0.f;
                             }
                             split8(x, hi4[hf * 2 + h8], lo4[hf * 2 + h8], xmax);
                         }

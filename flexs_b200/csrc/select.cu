@@ -65,6 +65,11 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {  // 
 __device__ __forceinline__ unsigned long long hash_row(const uint8_t *__restrict__ row, int L) {
     unsigned long long h = 0x9e3779b97f4a7c15ull ^ (unsigned long long)L;
     int i = 0;
+    if ((reinterpret_cast<uintptr_t>(row) & 3) == 0) {   // word loads where the row allows (same value as the byte path)
+        const uint32_t *w32 = reinterpret_cast<const uint32_t *>(row);
+#pragma unroll 4
+        for (; i + 8 <= L; i += 8) h = mix64(h ^ ((unsigned long long)w32[i >> 2] | ((unsigned long long)w32[(i >> 2) + 1] << 32)));
+    }
     for (; i + 8 <= L; i += 8) {
         unsigned long long w = 0;
 #pragma unroll
@@ -76,7 +81,11 @@ __device__ __forceinline__ unsigned long long hash_row(const uint8_t *__restrict
     return mix64(h ^ w ^ 0xabcdef);
 }
 __device__ __forceinline__ bool rows_equal(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b, int L) {
-    for (int i = 0; i < L; ++i)
+    int i = 0;
+    if (((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 3) == 0)
+        for (; i + 4 <= L; i += 4)
+            if (*reinterpret_cast<const uint32_t *>(a + i) != *reinterpret_cast<const uint32_t *>(b + i)) return false;
+    for (; i < L; ++i)
         if (a[i] != b[i]) return false;
     return true;
 }
@@ -103,6 +112,8 @@ __device__ __forceinline__ int pow2_at_least(int v) {
     while (p < v) p <<= 1;
     return p;
 }
+
+__device__ __forceinline__ unsigned long long globaltimer_ns();
 
 // ---- final stage, one CTA ----------------------------------------------------------------------------------------
 // bin of rank `krem` (counted from the top) in a 4096-bin histogram: suffix sums, 8 consecutive bins per thread.
@@ -172,9 +183,15 @@ __device__ int narrow(const unsigned long long *src, int m, unsigned int need, u
     }
     if (t == 0) s_cnt = 0;
     __syncthreads();
-    for (int i = t; i < m; i += NT) {
-        const unsigned long long key = src[i];
-        if ((key >> (64 - thr_bits)) >= thr_prefix) dst[atomicAdd(&s_cnt, 1u)] = key;
+    for (int i0 = t & ~31; i0 < m; i0 += NT) {   // one shared-memory atomic per warp, not per selected key
+        const int i = i0 + (t & 31);
+        const unsigned long long key = i < m ? src[i] : 0ull;
+        const bool sel = i < m && (key >> (64 - thr_bits)) >= thr_prefix;
+        const unsigned int mask = __ballot_sync(0xffffffffu, sel);
+        unsigned int base = 0;
+        if ((t & 31) == 0 && mask) base = atomicAdd(&s_cnt, (unsigned int)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (sel) dst[base + __popc(mask & ((1u << (t & 31)) - 1u))] = key;
     }
     __syncthreads();
     const int m1 = (int)s_cnt;
@@ -258,18 +275,23 @@ __device__ int pick_distinct(const unsigned long long *keys, unsigned long long 
 template <class RowOf, class IdxOf>
 __device__ void finalize(unsigned long long *k0, unsigned long long *k1, unsigned long long *k2, unsigned short *rank_of,
                          int m, int k, int L, RowOf row_of, IdxOf idx_of, float *top_scores, long long *top_idx,
-                         uint8_t *top_rows, int *n_found) {
+                         uint8_t *top_rows, int *n_found, int *diag = nullptr) {
     const int t = threadIdx.x;
+    const unsigned long long td0 = globaltimer_ns();
+    unsigned long long td1 = td0, td2 = td0, td3 = td0;
     const unsigned long long *sorted = nullptr;
     int found = -1;
     const int need = (L == 0) ? k : max(k, 1024);   // rows the first attempt ranks (unique: room for repeats)
     if (need <= 1024 && m > NARROW) {
         const int m1 = narrow(k0, m, (unsigned int)min(m, need), k1, reinterpret_cast<unsigned int *>(k2));
+        td1 = globaltimer_ns();
         const int len1 = pow2_at_least(max(m1, 2));
         for (int i = m1 + t; i < len1; i += NT) k1[i] = 0ull;
         __syncthreads();
         bitonic_sort<true>(k1, len1);
-        const int f = pick_distinct(k1, k2, rank_of, m1, m1, k, L, row_of);
+        td2 = globaltimer_ns();
+        const int f = pick_distinct(k1, k2, rank_of, m1, max(256, pow2_at_least(2 * k)), k, L, row_of);
+        td3 = globaltimer_ns();
         if (f >= k || m1 >= m) { found = f; sorted = k1; }
     }
     if (found < 0) {   // few candidates, a large k, or a narrowed set that is mostly repeats: rank all of them
@@ -277,7 +299,7 @@ __device__ void finalize(unsigned long long *k0, unsigned long long *k1, unsigne
         for (int i = m + t; i < len; i += NT) k0[i] = 0ull;
         __syncthreads();
         bitonic_sort<true>(k0, len);
-        found = pick_distinct(k0, k2, rank_of, m, 1024, k, L, row_of);
+        found = pick_distinct(k0, k2, rank_of, m, max(256, pow2_at_least(2 * k)), k, L, row_of);
         sorted = k0;
     }
     for (int i = t; i < k; i += NT) {
@@ -300,6 +322,9 @@ __device__ void finalize(unsigned long long *k0, unsigned long long *k1, unsigne
         }
     }
     if (t == 0) *n_found = found;
+    if (t == 0 && diag != nullptr) {   // ns: narrowing, sort of the narrowed set, de-duplication, everything after
+        diag[0] = (int)(td1 - td0); diag[1] = (int)(td2 - td1); diag[2] = (int)(td3 - td2);
+    }
 }
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -425,7 +450,7 @@ __global__ void __launch_bounds__(NT, 1) topk_select_kernel(const SelParams p) {
     finalize(keys, k1, k2, rank_of, m, p.k, L,
              [rows, L2 = p.row_len](unsigned int pos) { return rows + (size_t)pos * L2; },
              [off](unsigned int pos) { return (long long)pos + off; },
-             p.top_scores, p.top_idx, p.top_rows, &s_nfound);
+             p.top_scores, p.top_idx, p.top_rows, &s_nfound, p.status ? p.status + 5 : nullptr);
     if (rows == nullptr && p.top_rows != nullptr)   // an empty shard still sends a well-defined message
         for (int i = t; i < p.k * p.row_len; i += NT) p.top_rows[i] = 0;
     // rows of the winners are wanted even when ranking rows rather than distinct rows
@@ -468,13 +493,21 @@ __global__ void __launch_bounds__(NT, 1) screen_merge_kernel(const MergeParams p
     __syncthreads();
     // position j = rank-major order of the gathered lists: shards own increasing index ranges and each list is sorted
     // (score desc, index asc), so ties by position are ties by global index
-    for (int j = t; j < total; j += NT) {
-        const int r = j / p.k, i = j - r * p.k;
-        const unsigned char *msg = p.gathered + (size_t)r * p.msg_bytes;
-        const long long gi = reinterpret_cast<const long long *>(msg)[i];
-        if (gi < 0) continue;   // an absent winner (fewer than k candidates on that shard)
-        const float sc = reinterpret_cast<const float *>(msg + p.off_score)[i];
-        keys[atomicAdd(&s_m, 1)] = make_key(sc, (unsigned int)j);
+    for (int j0 = t & ~31; j0 < total; j0 += NT) {
+        const int j = j0 + (t & 31);
+        bool live = j < total;
+        unsigned long long key = 0;
+        if (live) {
+            const int r = j / p.k, i = j - r * p.k;
+            const unsigned char *msg = p.gathered + (size_t)r * p.msg_bytes;
+            live = reinterpret_cast<const long long *>(msg)[i] >= 0;   // < 0: an absent winner (fewer than k candidates on that shard)
+            if (live) key = make_key(reinterpret_cast<const float *>(msg + p.off_score)[i], (unsigned int)j);
+        }
+        const unsigned int mask = __ballot_sync(0xffffffffu, live);
+        int base = 0;
+        if ((t & 31) == 0 && mask) base = atomicAdd(&s_m, __popc(mask));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (live) keys[base + __popc(mask & ((1u << (t & 31)) - 1u))] = key;
     }
     __syncthreads();
     const unsigned char *g = p.gathered;
