@@ -61,6 +61,18 @@ _SIGNATURES = [
     ("flexs_model_train_step_dev", c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, POINTER(c_float), c_void_p]),
     ("flexs_model_get_optimizer_state", c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64)]),
     ("flexs_model_reset_optimizer", c_int, [c_void_p]),
+    ("flexs_vae_create", c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_void_p)]),
+    ("flexs_vae_destroy", None, [c_void_p]),
+    ("flexs_vae_num_arrays", c_int, [c_void_p]),
+    ("flexs_vae_array_size", c_int64, [c_void_p, c_int]),
+    ("flexs_vae_set_weights", c_int, [c_void_p, POINTER(c_void_p)]),
+    ("flexs_vae_get_weights", c_int, [c_void_p, POINTER(c_void_p)]),
+    ("flexs_vae_get_gradients", c_int, [c_void_p, POINTER(c_void_p)]),
+    ("flexs_vae_reset_optimizer", c_int, [c_void_p]),
+    ("flexs_vae_train_step_dev", c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, POINTER(c_float), c_void_p]),
+    ("flexs_vae_fit_dev", c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_uint64, c_void_p, POINTER(c_int), c_void_p]),
+    ("flexs_vae_decode_dev", c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    ("flexs_vae_log_prob_dev", c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     ("flexs_additive_score_dev", c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_double, c_double, c_void_p,
                                          c_void_p, c_void_p]),
     ("flexs_lookup_score_dev", c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
@@ -253,6 +265,80 @@ class NativeModel:
         check(lib().flexs_model_train_step_dev(self._h, member, c_void_p(d_idx), c_void_p(d_labels), n,
                                                c_void_p(d_mask), ctypes.byref(loss), c_void_p(stream)), "train_step")
         return float(loss.value)
+
+
+class NativeVAE:
+    """Owns one ``flexs_vae_t*`` (K9: the CbAS / DbAS generator; see include/flexs_b200.h)."""
+
+    def __init__(self, seq_len: int, alphabet_size: int, intermediate_dim: int, latent_dim: int, device: int = 0):
+        require_cuda()
+        self.seq_len, self.alphabet_size, self.intermediate_dim, self.latent_dim, self.device = \
+            seq_len, alphabet_size, intermediate_dim, latent_dim, device
+        handle = c_void_p()
+        check(lib().flexs_vae_create(device, seq_len, alphabet_size, intermediate_dim, latent_dim, ctypes.byref(handle)), "vae_create")
+        self._h = handle
+        self.array_sizes = [int(lib().flexs_vae_array_size(self._h, i)) for i in range(lib().flexs_vae_num_arrays(self._h))]
+        d, i, z = seq_len * alphabet_size, intermediate_dim, latent_dim
+        self.array_shapes = [(d, i), (i,), (i, i), (i,), (i,), (i,), (i,), (i,), (i, i), (i,), (i, z), (z,), (i, z), (z,),
+                             (z, i), (i,), (i, i), (i,), (i, i), (i,), (i, d), (d,)]
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().flexs_vae_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_weights(self, weights: Sequence[np.ndarray]) -> None:
+        if len(weights) != len(self.array_sizes):
+            raise ValueError(f"expected {len(self.array_sizes)} arrays, got {len(weights)}")
+        flat = []
+        for w, size in zip(weights, self.array_sizes):
+            a = np.ascontiguousarray(np.asarray(w, dtype=np.float32)).reshape(-1)
+            if a.size != size:
+                raise ValueError(f"weight array has {a.size} elements, expected {size}")
+            flat.append(a)
+        check(lib().flexs_vae_set_weights(self._h, _as_ptr_array(flat)), "vae_set_weights")
+
+    def _read(self, fn, what) -> List[np.ndarray]:
+        flat = [np.empty(size, dtype=np.float32) for size in self.array_sizes]
+        check(fn(self._h, _as_ptr_array(flat)), what)
+        return [a.reshape(shp) for a, shp in zip(flat, self.array_shapes)]
+
+    def get_weights(self) -> List[np.ndarray]:
+        return self._read(lib().flexs_vae_get_weights, "vae_get_weights")
+
+    def get_gradients(self) -> List[np.ndarray]:
+        return self._read(lib().flexs_vae_get_gradients, "vae_get_gradients")
+
+    def reset_optimizer(self) -> None:
+        check(lib().flexs_vae_reset_optimizer(self._h), "vae_reset_optimizer")
+
+    def train_step_dev(self, d_idx: int, d_weights: int, n: int, d_mask1: int, d_mask2: int, d_eps: int, stream: int = 0) -> float:
+        loss = c_float(0.0)
+        check(lib().flexs_vae_train_step_dev(self._h, c_void_p(d_idx), c_void_p(d_weights), n, c_void_p(d_mask1), c_void_p(d_mask2),
+                                             c_void_p(d_eps), ctypes.byref(loss), c_void_p(stream)), "vae_train_step")
+        return float(loss.value)
+
+    def fit_dev(self, d_idx: int, d_weights: int, n_train: int, batch_size: int, epochs: int, patience: int, seed: int,
+                stream: int = 0):
+        losses = np.zeros(max(epochs, 1), dtype=np.float32)
+        ran = c_int(0)
+        check(lib().flexs_vae_fit_dev(self._h, c_void_p(d_idx), c_void_p(d_weights), n_train, batch_size, epochs, patience,
+                                      c_uint64(seed & 0xFFFFFFFFFFFFFFFF), losses.ctypes.data_as(c_void_p), ctypes.byref(ran),
+                                      c_void_p(stream)), "vae_fit")
+        return losses[: ran.value], int(ran.value)
+
+    def decode_dev(self, d_z: int, n: int, d_out: int, stream: int = 0) -> None:
+        check(lib().flexs_vae_decode_dev(self._h, c_void_p(d_z), n, c_void_p(d_out), c_void_p(stream)), "vae_decode")
+
+    def log_prob_dev(self, d_idx: int, n: int, d_eps: int, d_logp: int, stream: int = 0) -> None:
+        check(lib().flexs_vae_log_prob_dev(self._h, c_void_p(d_idx), n, c_void_p(d_eps), c_void_p(d_logp), c_void_p(stream)),
+              "vae_log_prob")
 
 
 # -- stateless kernels ------------------------------------------------------------------------

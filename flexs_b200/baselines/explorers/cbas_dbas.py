@@ -72,7 +72,7 @@ class CbAS(Explorer):
         g = self.generator
         twin = VAE(seq_length=g.seq_length, alphabet=g.alphabet, batch_size=g.batch_size, latent_dim=g.latent_dim,
                    intermediate_dim=g.intermediate_dim, epochs=g.epochs, epsilon_std=g.epsilon_std, beta=g.beta,
-                   validation_split=g.validation_split, verbose=g.verbose)
+                   validation_split=g.validation_split, verbose=g.verbose, device=getattr(g, "device", None))
         twin.vae.set_weights(g.vae.get_weights())
         return twin
 

@@ -1,10 +1,12 @@
 """VAE generator for CbAS/DbAS (reference: flexs/utils/VAE_utils.py:12-232).
 
-§8(f) "next row" #1: the generator is not the surrogate hot path, but CbAS cannot run without it and the
-reference's is a Keras model.  Same class, constructor arguments and methods (``train_model``, ``generate``,
-``calculate_log_probability``) and the same architecture / losses / sampling procedure; the network runs in
-torch on the surrogate's GPU (falls back to torch-CPU so the explorer logic stays testable without a GPU —
-this module is not on the roofline path and is slated to move onto the dense-stack kernels next round).
+§8(f) "next row" #1: the generator is not the surrogate hot path, but CbAS cannot run without it, it dominates the
+explorer's wall-clock (a refit after every 100 proposals), and the reference's is a Keras model.  Same class,
+constructor arguments and methods (``train_model``, ``generate``, ``calculate_log_probability``) and the same
+architecture / losses / sampling procedure.  With a CUDA device the network is K9 of libflexs_b200
+(csrc/vae.cu: ``flexs_vae_*`` — the whole fit runs on the device with one host synchronisation per epoch, the
+decoder pass and the reconstruction log-probability are single calls on residue indices); without one the torch
+module below stands in so the explorer logic stays testable on a CPU box (it is not a product path).
 
 Reference behaviours kept on purpose:
   * encoder Dense(elu) -> Dropout(0.3) -> Dense(elu) -> BatchNorm -> Dense(elu) -> (z_mean, z_log_var);
@@ -85,19 +87,100 @@ class VAEModel(nn.Module):
         self.load_state_dict(state)
 
 
+class NativeVAEModel:
+    """``VAEModel`` on the B200 kernels (K9): owns a ``flexs_vae_t`` and mirrors the Keras model's surface that
+    CbAS touches — ``get_weights`` / ``set_weights`` (cbas_dbas.py:130-144 clones the prior), ``generate`` and ``predict``."""
+
+    def __init__(self, seq_length: int, alphabet_size: int, intermediate_dim: int, latent_dim: int, device: int = 0,
+                 seed: Optional[int] = None):
+        from flexs_b200 import _native
+
+        self.seq_length, self.alphabet_size = seq_length, alphabet_size
+        self.original_dim, self.latent_dim, self.device = seq_length * alphabet_size, latent_dim, device
+        self.native = _native.NativeVAE(seq_length, alphabet_size, intermediate_dim, latent_dim, device)
+        rng = np.random.default_rng(seed)
+        weights = []
+        for i, shp in enumerate(self.native.array_shapes):   # Keras defaults: glorot-uniform kernels, zero biases, BN (1, 0, 0, 1)
+            if len(shp) == 2:
+                lim = np.sqrt(6.0 / (shp[0] + shp[1]))
+                weights.append(rng.uniform(-lim, lim, size=shp).astype(np.float32))
+            else:
+                weights.append(np.ones(shp, np.float32) if i in (4, 7) else np.zeros(shp, np.float32))
+        self.native.set_weights(weights)
+
+    def get_weights(self) -> List[np.ndarray]:
+        return self.native.get_weights()
+
+    def set_weights(self, weights: List[np.ndarray]) -> None:
+        self.native.set_weights(weights)
+
+    def _dev(self):
+        return torch.device("cuda", self.device)
+
+    def generate(self) -> np.ndarray:
+        """Decode one standard-normal latent sample (:71-74)."""
+        z = torch.as_tensor(np.random.randn(1, self.latent_dim), dtype=torch.float32, device=self._dev())
+        out = torch.empty((1, self.original_dim), dtype=torch.float32, device=self._dev())
+        with torch.cuda.device(self._dev()):
+            self.native.decode_dev(z.data_ptr(), 1, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        return out.cpu().numpy()
+
+    def log_probability(self, idx: np.ndarray) -> np.ndarray:
+        """calculate_log_probability (:189-217) on residue indices; the latent noise ``predict`` draws comes from numpy."""
+        n = len(idx)
+        dev = self._dev()
+        d_idx = torch.from_numpy(np.ascontiguousarray(idx, dtype=np.uint8)).to(dev)
+        eps = torch.as_tensor(np.random.randn(n, self.latent_dim), dtype=torch.float32, device=dev)
+        out = torch.empty(n, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            self.native.log_prob_dev(d_idx.data_ptr(), n, eps.data_ptr(), out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        return out.cpu().numpy()
+
+
 class VAE:
     """Wrapper exposing the interface CbAS/DbAS use."""
 
     def __init__(self, seq_length: int, alphabet: str, batch_size: int = 10, latent_dim: int = 2,
                  intermediate_dim: int = 250, epochs: int = 10, epsilon_std: float = 1.0, beta: float = 1,
-                 validation_split: float = 0.2, verbose: bool = True):
+                 validation_split: float = 0.2, verbose: bool = True, device: Optional[int] = None,
+                 seed: Optional[int] = None):
         self.batch_size, self.latent_dim, self.intermediate_dim = batch_size, latent_dim, intermediate_dim
         self.epochs, self.epsilon_std, self.beta = epochs, epsilon_std, beta
         self.validation_split, self.verbose = validation_split, verbose
         self.name = f"VAE_latent_dim={latent_dim}_intermediate_dim={intermediate_dim}"
         self.alphabet, self.seq_length = alphabet, seq_length
-        self.vae = VAEModel(len(alphabet) * seq_length, intermediate_dim, latent_dim).to(_device())
-        self._opt = torch.optim.Adam(self.vae.parameters(), lr=1e-4, eps=1e-7)
+        self.device, self.seed = device, seed
+        self._fits = 0
+        self.last_fit_losses = None
+        if torch.cuda.is_available():
+            self.vae = NativeVAEModel(seq_length, len(alphabet), intermediate_dim, latent_dim,
+                                      torch.cuda.current_device() if device is None else device, seed)
+            self._opt = None
+        else:   # GPU-less box: torch stand-in, explorer logic only
+            self.vae = VAEModel(len(alphabet) * seq_length, intermediate_dim, latent_dim).to(_device())
+            self._opt = torch.optim.Adam(self.vae.parameters(), lr=1e-4, eps=1e-7)
+
+    @property
+    def native(self) -> bool:
+        return isinstance(self.vae, NativeVAEModel)
+
+    def _train_native(self, samples, weights):
+        """``fit`` (:141-151) on the device: the LAST ``validation_split`` of the data is held out (Keras takes it before
+        shuffling), mini-batches of ``batch_size`` reshuffled every epoch, early stopping on the training loss, patience 3."""
+        idx = s_utils.encode_sequences(list(samples), self.alphabet)
+        n_train = len(idx) - int(len(idx) * self.validation_split)
+        dev = torch.device("cuda", self.vae.device)
+        d_idx = torch.from_numpy(np.ascontiguousarray(idx[:n_train])).to(dev)
+        d_w = torch.as_tensor(np.asarray(weights, dtype=np.float32)[:n_train], device=dev)
+        seed = (0 if self.seed is None else int(self.seed)) * 1000003 + self._fits + 1
+        self._fits += 1
+        with torch.cuda.device(dev):
+            losses, ran = self.vae.native.fit_dev(d_idx.data_ptr(), d_w.data_ptr(), n_train, max(2, self.batch_size), self.epochs, 3,
+                                                  seed, torch.cuda.current_stream().cuda_stream)
+        self.last_fit_losses = losses
+        if self.verbose:
+            for e, l in enumerate(losses):
+                print(f"Epoch {e + 1}/{self.epochs} - loss: {l:.4f}")
 
     def _one_hots(self, sequences) -> np.ndarray:
         idx = s_utils.encode_sequences(list(sequences), self.alphabet)
@@ -107,6 +190,8 @@ class VAE:
 
     def train_model(self, samples, weights):
         """Fit on ``samples`` weighted by ``weights`` (:132-151)."""
+        if self.native:
+            return self._train_native(samples, weights)
         x = self._one_hots(samples).reshape(len(samples), -1)
         w = np.asarray(weights, dtype=np.float32)
         n_train = len(x) - int(len(x) * self.validation_split)   # Keras holds out the LAST fraction
@@ -168,6 +253,8 @@ class VAE:
     def calculate_log_probability(self, sequences: SEQUENCES_TYPE, vae: Optional[VAEModel] = None):
         """log-probability of reconstructing each sequence (:189-217)."""
         vae = vae or self.vae
+        if isinstance(vae, NativeVAEModel):
+            return vae.log_probability(s_utils.encode_sequences(list(sequences), self.alphabet))
         one_hots = self._one_hots(sequences)
         decoded = vae.predict(one_hots.reshape(len(one_hots), -1)).reshape(one_hots.shape)
         per_res = (decoded * one_hots).max(axis=2) / decoded.sum(axis=2)

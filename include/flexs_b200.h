@@ -63,6 +63,7 @@ enum {
 };
 
 typedef struct flexs_model flexs_model_t;
+typedef struct flexs_vae flexs_vae_t;
 
 int flexs_abi_version(void);
 const char *flexs_last_error(void);
@@ -278,6 +279,44 @@ int flexs_additive_score_dev(const uint8_t *d_seq, int64_t n, int seq_len,
 int flexs_lookup_score_dev(const uint8_t *d_seq, int64_t n, int seq_len,
                            const uint8_t *h_column_of_char, int base, const double *d_table,
                            int64_t table_len, double *d_out, void *stream);
+
+/* ---- K9: the VAE generator of CbAS / DbAS ---------------------------
+ * Replaces flexs/utils/VAE_utils.py: VAEModel (:28-92: encoder Dense-ELU, Dropout(0.3), Dense-ELU,
+ * BatchNorm, Dense-ELU, z_mean / z_log_var, sampling; decoder Dense-ELU x2, Dropout(0.3), Dense-ELU,
+ * Dense-sigmoid; loss = sum_d BCE + KL), compile (:127: Adam 1e-4, clipvalue 0.5), fit (:141-151),
+ * generate's decoder pass (:71-74) and calculate_log_probability (:189-217).  22 weight arrays in
+ * Keras get_weights() order: W1 (L*A, I) b1 | W2 (I, I) b2 | BatchNorm gamma beta moving_mean
+ * moving_variance | W3 b3 | Wm (I, Z) bm | Wv (I, Z) bv | W4 (Z, I) b4 | W5 b5 | W6 b6 | W7 (I, L*A) b7.
+ * Sequences are residue indices uint8[n, seq_len]; the one-hot input is never built.
+ *
+ * flexs_vae_fit_dev: `epochs` passes over rows [0, n_train) of d_idx with sample weights d_weights
+ * (the caller holds out the validation split, VAE_utils.py:148), mini-batches of batch_size reshuffled
+ * every epoch, early stopping when the epoch's mean loss has not improved for `patience` epochs
+ * (:139; 0 = never); h_losses[e] = mean loss of epoch e, *epochs_run = epochs actually run.  One
+ * host synchronisation per epoch.  flexs_vae_train_step_dev is the parity unit: one optimiser step
+ * on exactly the given batch with caller-supplied dropout masks (float [n, I], values 0 or 1/0.7)
+ * and latent noise (float [n, Z]); flexs_vae_get_gradients reads the gradients it computed.
+ * flexs_vae_decode_dev: decoder on d_z float[n, Z] -> d_out float[n, L*A] (inference mode).
+ * flexs_vae_log_prob_dev: log-probability of reconstructing each sequence (:189-217, float64,
+ * nan_to_num applied); d_eps float[n, Z] is the latent noise predict() draws (NULL: z = z_mean).  */
+int flexs_vae_create(int device, int seq_len, int alphabet_size, int intermediate_dim, int latent_dim,
+                     flexs_vae_t **out);
+void flexs_vae_destroy(flexs_vae_t *v);
+int flexs_vae_num_arrays(const flexs_vae_t *v);
+int64_t flexs_vae_array_size(const flexs_vae_t *v, int i);
+int flexs_vae_set_weights(flexs_vae_t *v, const float *const *h_arrays);
+int flexs_vae_get_weights(flexs_vae_t *v, float *const *h_arrays);
+int flexs_vae_get_gradients(flexs_vae_t *v, float *const *h_arrays);
+int flexs_vae_reset_optimizer(flexs_vae_t *v);
+int flexs_vae_train_step_dev(flexs_vae_t *v, const uint8_t *d_idx, const float *d_weights, int64_t n,
+                             const float *d_mask1, const float *d_mask2, const float *d_eps,
+                             float *h_loss, void *stream);
+int flexs_vae_fit_dev(flexs_vae_t *v, const uint8_t *d_idx, const float *d_weights, int64_t n_train,
+                      int batch_size, int epochs, int patience, uint64_t seed, float *h_losses,
+                      int *epochs_run, void *stream);
+int flexs_vae_decode_dev(flexs_vae_t *v, const float *d_z, int64_t n, float *d_out, void *stream);
+int flexs_vae_log_prob_dev(flexs_vae_t *v, const uint8_t *d_idx, int64_t n, const float *d_eps,
+                           double *d_logp, void *stream);
 
 #ifdef __cplusplus
 }
