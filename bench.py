@@ -83,9 +83,29 @@ def plugin_api_timings(device):
                     "get_fitness_20seq_latency_us_median": float(np.median(lat) * 1e6),
                     "get_fitness_20seq_latency_us_p90": float(np.quantile(lat, 0.9) * 1e6)}
         del model
+    out["vae_generator"] = vae_timings(device)
     out["table_landscapes"] = landscape_timings(device)
     out["unique_ranking"] = dedup_timing(device)
     return out
+
+
+def vae_timings(device):
+    """K9: one refit of the CbAS generator as cbas_dbas.py:183 drives it — 1000 14-mers, batch 10,
+    10 epochs = 800 optimiser steps (validation split 0.2) — and one 100-proposal cycle's decode + log-probability calls."""
+    from flexs_b200.utils import sequence_utils as su
+    from flexs_b200.utils.VAE_utils import VAE
+
+    seqs = su.generate_random_sequences(14, 1000, su.RNAA)
+    vae = VAE(seq_length=14, alphabet=su.RNAA, batch_size=10, latent_dim=2, intermediate_dim=250, epochs=10, verbose=False, seed=0)
+    vae.train_model(seqs[:100], np.ones(100))                # warm-up: workspace allocation
+    t0 = time.perf_counter(); vae.train_model(seqs, np.ones(1000)); fit_s = time.perf_counter() - t0
+    steps = len(vae.last_fit_losses) * 80
+    t0 = time.perf_counter()
+    for _ in range(10):
+        vae.calculate_log_probability(seqs[:100])
+    lp_s = (time.perf_counter() - t0) / 10
+    return {"refit_1000seq_s": fit_s, "epochs_run": int(len(vae.last_fit_losses)), "ms_per_optimizer_step": 1e3 * fit_s / max(steps, 1),
+            "log_probability_100seq_us": lp_s * 1e6, "native": bool(vae.native)}
 
 
 def dedup_timing(device):

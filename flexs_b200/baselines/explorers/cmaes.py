@@ -97,7 +97,7 @@ class CMAES(Explorer):
         # (cmaes.py:76-80) and is consulted BEFORE `measured` (:85-90) — it sits in front
         cache_rows = torch.cat([measured_rows[best_row: best_row + 1], measured_rows])
         cache_vals = torch.cat([torch.tensor([truth[best_row]], dtype=torch.float64),
-                                torch.from_numpy(truth)]).to(dev)
+                                torch.from_numpy(truth.copy())]).to(dev)
         n_static = int(cache_rows.shape[0])          # entries [1, n_static) are `measured`: never proposed
         seen_flag = torch.zeros(n_static, dtype=torch.bool, device=dev)
         seen_flag[0] = True

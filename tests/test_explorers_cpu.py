@@ -216,3 +216,50 @@ def test_device_sep_cma_matches_host_sampler_update():
         assert np.abs(host.diagC - dev.diagC.numpy()).max() < 1e-5
     samples = dev.ask()
     assert samples.shape == (pop, n) and samples.dtype == torch.float32 and torch.isfinite(samples).all()
+
+
+def test_cbas_dbas_decisions_match_reference_code(golden, monkeypatch):
+    """SURVEY.md §8 row a9, value parity: this repo's CbAS.propose_sequences and the REFERENCE's own (run by
+    tests/golden/make_golden_cbas.py) drive the same deterministic fake generator and hash model from the same seed and
+    must make identical decisions — the threshold gamma, the importance weights, which proposals are masked, the pool the
+    generator is re-fit on (every train_model call is logged), the final ranking and model.cost."""
+    import random
+
+    import numpy as np
+    import pandas as pd
+
+    import flexs_b200 as flexs
+    from flexs_b200.baselines.explorers import cbas_dbas
+    from flexs_b200.utils import sequence_utils as su
+    from tests.golden.fake_vae import FakeVAE
+    from tests.golden.make_golden import hash_model_score
+
+    class HashModel(flexs.Model):
+        def __init__(self):
+            super().__init__("hash")
+
+        def train(self, *a, **k):
+            pass
+
+        def _fitness_function(self, sequences):
+            return np.array([hash_model_score(s) for s in sequences])
+
+    monkeypatch.setattr(cbas_dbas, "VAE", FakeVAE)     # the prior is cloned by constructing a VAE (cbas_dbas.py:125-144)
+    ref = golden("ref_cbas.json")
+    rng = np.random.default_rng(7)
+    seqs = ["".join(su.RNAA[i] for i in row) for row in rng.integers(0, 4, size=(60, 12))]
+    frame = pd.DataFrame({"sequence": seqs, "true_score": [hash_model_score(s[::-1]) for s in seqs], "model_score": np.nan,
+                          "round": [1] * 60, "model_cost": 0, "measurement_cost": 60})
+    for algo in ("cbas", "dbas"):
+        random.seed(11)
+        model = HashModel()
+        gen = FakeVAE(seq_length=12, alphabet=su.RNAA)
+        ex = flexs.baselines.explorers.CbAS(model, gen, rounds=1, starting_sequence="AUGCAUGCAUGC", sequences_batch_size=20,
+                                           model_queries_per_batch=350, alphabet=su.RNAA, algo=algo, Q=0.7, cycle_batch_size=100)
+        got_seqs, got_preds = ex.propose_sequences(frame)
+        want = ref[algo]
+        assert [str(s) for s in got_seqs] == want["sequences"]
+        np.testing.assert_array_equal(np.asarray(got_preds, dtype=np.float64), np.asarray(want["preds"]))
+        assert model.cost == want["model_cost"] == 400
+        assert gen.train_log == want["train_log"]
+        assert len(got_seqs) == 19                                  # the [: -B : -1] slice keeps B-1

@@ -36,9 +36,8 @@ def test_vae_train_step_matches_oracle(L, A, I, Z, B):
     loss, grads, new_mean, new_var = vo.loss_and_grads(ws, idx, A, sw, eps, m1, m2)
     vae = _native.NativeVAE(L, A, I, Z)
     vae.set_weights(ws)
-    got_loss = vae.train_step_dev(_cuda(idx, np.uint8).data_ptr(), _cuda(sw, np.float32).data_ptr(), B,
-                                  _cuda(m1, np.float32).data_ptr(), _cuda(m2, np.float32).data_ptr(),
-                                  _cuda(eps, np.float32).data_ptr())
+    dev = [_cuda(idx, np.uint8), _cuda(sw, np.float32), _cuda(m1, np.float32), _cuda(m2, np.float32), _cuda(eps, np.float32)]
+    got_loss = vae.train_step_dev(dev[0].data_ptr(), dev[1].data_ptr(), B, dev[2].data_ptr(), dev[3].data_ptr(), dev[4].data_ptr())
     assert abs(got_loss - loss) <= 2e-5 * abs(loss)
     got_grads = vae.get_gradients()
     for name, g, ref in zip(vo.NAMES, got_grads, grads):
@@ -71,14 +70,16 @@ def test_vae_decode_and_log_probability_match_oracle():
     vae.set_weights(ws)
     z = rng.normal(size=(17, Z))
     out = torch.empty((17, L * A), dtype=torch.float32, device="cuda")
-    vae.decode_dev(_cuda(z, np.float32).data_ptr(), 17, out.data_ptr())
+    d_z = _cuda(z, np.float32)
+    vae.decode_dev(d_z.data_ptr(), 17, out.data_ptr())
     torch.cuda.synchronize()
     np.testing.assert_allclose(out.cpu().numpy(), vo.decode(ws, z), rtol=0, atol=2e-6)
     idx = rng.integers(0, A, size=(n, L), dtype=np.uint8)
     eps = rng.normal(size=(n, Z))
+    d_idx, d_eps = _cuda(idx, np.uint8), _cuda(eps, np.float32)
     for e in (None, eps):
         lp = torch.empty(n, dtype=torch.float64, device="cuda")
-        vae.log_prob_dev(_cuda(idx, np.uint8).data_ptr(), n, _cuda(e, np.float32).data_ptr() if e is not None else 0, lp.data_ptr())
+        vae.log_prob_dev(d_idx.data_ptr(), n, d_eps.data_ptr() if e is not None else 0, lp.data_ptr())
         torch.cuda.synchronize()
         np.testing.assert_allclose(lp.cpu().numpy(), vo.log_probability(ws, idx, A, e), rtol=2e-5, atol=1e-4)
     vae.close()
