@@ -212,6 +212,53 @@ __device__ int pick_distinct(const unsigned long long *keys, unsigned long long 
         __syncthreads();
         return found;
     }
+    // Fast path.  Equal rows carry equal scores, so in rank order a row can only repeat an earlier member of its own run
+    // of equal scores: the head of a run is always new, everyone else walks back through the run (usually one step: the
+    // copy next to it) comparing rows.  No hashing, no second sort.  A run longer than RUN_MAX (a wall of tied scores
+    // over different rows) sends the whole call to the hash path below.
+    {
+        constexpr int RUN_MAX = 64;
+        __shared__ int s_long;
+        if (t == 0) s_long = 0;
+        __syncthreads();
+        for (int i = t; i < m; i += NT) {
+            const unsigned int sc = (unsigned int)(keys[i] >> 32);
+            bool dup = false;
+            if (i > 0 && (unsigned int)(keys[i - 1] >> 32) == sc) {
+                const uint8_t *mine = row_of(0xffffffffu - (unsigned int)(keys[i] & 0xffffffffu));
+                int j = i - 1, steps = 0;
+                for (; j >= 0 && (unsigned int)(keys[j] >> 32) == sc && !dup && steps < RUN_MAX; --j, ++steps)
+                    dup = rows_equal(mine, row_of(0xffffffffu - (unsigned int)(keys[j] & 0xffffffffu)), L);
+                if (!dup && steps == RUN_MAX && j >= 0 && (unsigned int)(keys[j] >> 32) == sc) s_long = 1;
+            }
+            rank_of[i] = dup ? 1 : 0;
+        }
+        __syncthreads();
+        if (!s_long) {
+            const int span = (m + NT - 1) / NT, lo = t * span, hi = min(m, lo + span);
+            int mine_cnt = 0;
+            for (int i = lo; i < hi; ++i) mine_cnt += rank_of[i] ? 0 : 1;
+            s_scan[t] = mine_cnt;
+            __syncthreads();
+            for (int off = 1; off < NT; off <<= 1) {
+                const int v = (t >= off) ? s_scan[t - off] : 0;
+                __syncthreads();
+                s_scan[t] += v;
+                __syncthreads();
+            }
+            if (t == NT - 1) s_found = s_scan[t];
+            int base = s_scan[t] - mine_cnt;
+            unsigned int *surv = reinterpret_cast<unsigned int *>(hs);
+            for (int i = lo; i < hi; ++i)
+                if (!rank_of[i] && base < k) surv[base++] = (unsigned int)i;
+            __syncthreads();
+            const int found = min(s_found, k);
+            for (int i = t; i < found; i += NT) rank_of[i] = (unsigned short)surv[i];
+            __syncthreads();
+            return found;
+        }
+        __syncthreads();
+    }
     for (int P = min(m, P0);; P = min(m, P * 2)) {
         const int plen = pow2_at_least(max(P, 2));
         for (int i = t; i < plen; i += NT) {

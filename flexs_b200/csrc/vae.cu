@@ -34,6 +34,9 @@ struct flexs_vae {
     float *ws = nullptr;                // activations of one batch
     int64_t ws_floats = 0;
     int maxB = 0;
+    long long *d_state = nullptr;       // fit(): [0] optimiser steps done, [1] offset into the permutation array (device-side
+                                        // so that one captured CUDA graph replays for every mini-batch)
+    cudaStream_t fit_stream = nullptr;  // graphs cannot be captured on the legacy default stream
 };
 
 namespace {
@@ -58,9 +61,11 @@ __device__ __forceinline__ void philox(uint64_t counter, uint64_t key, uint32_t 
 }
 
 // dropout keep masks (value 1/(1-p) or 0) and standard-normal latent noise for one step
-__global__ void k_noise(float *mask1, float *mask2, float *eps, int nmask, int neps, uint64_t seed, uint64_t step) {
+__global__ void k_noise(float *mask1, float *mask2, float *eps, int nmask, int neps, uint64_t seed, uint64_t step,
+                        const long long *d_state) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t r[4];
+    if (d_state) step = (uint64_t)d_state[0] + 1;
     if (i < nmask) {
         philox((uint64_t)i, seed ^ (step * 0x9E3779B97F4A7C15ull), r);
         mask1[i] = ((r[0] >> 8) * (1.0f / 16777216.0f) >= DROP) ? 1.f / (1.f - DROP) : 0.f;
@@ -80,11 +85,12 @@ __device__ __forceinline__ float act_fwd(float z, int act) {
 }
 
 // layer 1 on the one-hot input: y[b,o] = act(b1[o] + sum_l W1[l*A + idx[row(b), l], o]) * mask
-__global__ void k_gather_fwd(const uint8_t *idx, const int *perm, const float *w, const float *bias, const float *mask, float *y,
-                             int B, int L, int A, int out, int act) {
+__global__ void k_gather_fwd(const uint8_t *idx, const int *perm, const long long *d_state, const float *w, const float *bias,
+                             const float *mask, float *y, int B, int L, int A, int out, int act) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * out) return;
     const int b = i / out, o = i - b * out;
+    if (perm && d_state) perm += d_state[1];
     const uint8_t *row = idx + (size_t)(perm ? perm[b] : b) * L;
     float acc = bias[o];
     for (int l = 0; l < L; ++l) acc += w[(size_t)(l * A + row[l]) * out + o];
@@ -144,10 +150,12 @@ __global__ void k_sample(const float *zm, const float *zlv, const float *eps, fl
 //   recon_b = sum_d BCE(x_bd, out_bd)  (= original_dim * mean_d, keras clips probabilities to [1e-7, 1 - 1e-7])
 //   kl_b    = -0.5 * mean_z(1 + lv - m^2 - exp(lv));   loss = sum_b weight_b (recon_b + kl_b) / B
 // gpre7[b,d] = weight_b / B * (out - x) (sigmoid + BCE; zero where the clip is active), gzm / gzlv receive the KL part.
-__global__ void k_loss(const float *out, const uint8_t *idx, const int *perm, const float *weights, const float *zm,
-                       const float *zlv, float *gpre7, float *gzm, float *gzlv, double *loss_accum, int B, int L, int A, int Z) {
+__global__ void k_loss(const float *out, const uint8_t *idx, const int *perm, const long long *d_state, const float *weights,
+                       const float *zm, const float *zlv, float *gpre7, float *gzm, float *gzlv, double *loss_accum, int B, int L,
+                       int A, int Z) {
     __shared__ double s_part[256];
     const int D = L * A;
+    if (perm && d_state) perm += d_state[1];
     double acc = 0.0;
     for (int i = threadIdx.x; i < B * D; i += blockDim.x) {
         const int b = i / D, d = i - b * D;
@@ -192,10 +200,11 @@ __global__ void k_dense_bwd_w(const float *x, const float *gy, float *gw, float 
 }
 
 // layer-1 weight gradient: gW1[l*A + a, o] = sum_{b : idx[row(b), l] == a} gy[b,o]
-__global__ void k_gather_bwd_w(const uint8_t *idx, const int *perm, const float *gy, float *gw, float *gb, int B, int L, int A,
-                               int out) {
+__global__ void k_gather_bwd_w(const uint8_t *idx, const int *perm, const long long *d_state, const float *gy, float *gw, float *gb,
+                               int B, int L, int A, int out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int D = L * A;
+    if (perm && d_state) perm += d_state[1];
     if (i < D * out) {
         const int k = i / out, o = i - k * out, l = k / A, a = k - l * A;
         float acc = 0.f;
@@ -258,11 +267,14 @@ __global__ void k_add(const float *a, const float *b, float *out, int n) {
 }
 
 // Keras Adam with clipvalue: g clipped to [-0.5, 0.5] elementwise; lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t)
-__global__ void k_adam_clip(float *w, const float *g, float *m, float *v, int64_t count, float lr_t, const int64_t *skip_lo,
+__global__ void k_adam_clip(float *w, const float *g, float *m, float *v, int64_t count, float lr_t, const long long *d_state,
                             int64_t skip_a, int64_t skip_b) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count || (i >= skip_a && i < skip_b)) return;   // the BatchNorm moving statistics are not trained
-    (void)skip_lo;
+    if (d_state) {
+        const double t = (double)(d_state[0] + 1);
+        lr_t = (float)((double)ADAM_LR * sqrt(1.0 - pow((double)ADAM_B2, t)) / (1.0 - pow((double)ADAM_B1, t)));
+    }
     const float gi = fminf(fmaxf(g[i], -CLIP), CLIP);
     const float mi = ADAM_B1 * m[i] + (1.f - ADAM_B1) * gi;
     const float vi = ADAM_B2 * v[i] + (1.f - ADAM_B2) * gi * gi;
@@ -287,6 +299,12 @@ __global__ void k_log_prob(const float *out, const uint8_t *idx, double *lp, int
     lp[b] = acc;
 }
 
+// end of a graph-replayed step: one more optimiser step done, the next mini-batch starts B rows further into the permutation
+__global__ void k_advance(long long *d_state, int B, int steps) {
+    d_state[0] += steps;
+    d_state[1] += B;
+}
+
 __global__ void k_mul(const float *a, const float *b, float *out, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = a[i] * b[i];
@@ -303,7 +321,9 @@ struct Ws {
 
 int64_t ws_floats_for(const flexs_vae *v, int B) {
     const int64_t I = v->I, D = v->D, Z = v->Z, W = std::max(I, D);
-    return 64 + (int64_t)B * (11 * I + D + 2 * W + 7 * Z) + I + 32 * 4;
+    // 12 [B, I] arrays, out [B, D], two gradient buffers [B, max(I, D)], 7 [B, Z] arrays, istd [I], the loss; every array is
+    // rounded up to 4 floats by carve()
+    return 64 + (int64_t)B * (12 * I + D + 2 * W + 7 * Z) + I + 32 * 4;
 }
 
 Ws carve(const flexs_vae *v, int B) {
@@ -344,9 +364,10 @@ void decode(flexs_vae *v, const Ws &w, const float *z, int B, bool train, cudaSt
 }
 
 // encoder + sampling + decoder for B rows.  train: dropout masks and BatchNorm batch statistics; eps == nullptr: z = z_mean
-void forward(flexs_vae *v, const Ws &w, const uint8_t *idx, const int *perm, int B, bool train, const float *eps, cudaStream_t s) {
+void forward(flexs_vae *v, const Ws &w, const uint8_t *idx, const int *perm, int B, bool train, const float *eps, cudaStream_t s,
+             const long long *d_state = nullptr) {
     const int I = v->I, Z = v->Z, L = v->L, A = v->A;
-    k_gather_fwd<<<blocks((int64_t)B * I), 256, 0, s>>>(idx, perm, AT(W1), AT(B1), nullptr, w.h1, B, L, A, I, 1);
+    k_gather_fwd<<<blocks((int64_t)B * I), 256, 0, s>>>(idx, perm, d_state, AT(W1), AT(B1), nullptr, w.h1, B, L, A, I, 1);
     const float *x2 = w.h1;
     if (train) { k_mul<<<blocks((int64_t)B * I), 256, 0, s>>>(w.h1, w.mask1, w.h1m, B * I); x2 = w.h1m; }
     k_dense_fwd<<<blocks((int64_t)B * I), 256, 0, s>>>(x2, AT(W2), AT(B2), nullptr, w.h2, B, I, I, 1);
@@ -359,10 +380,11 @@ void forward(flexs_vae *v, const Ws &w, const uint8_t *idx, const int *perm, int
 }
 
 // gradients of the loss for the batch that forward(train) just ran; adds sum_b weight_b * loss_b to *w.loss
-void backward(flexs_vae *v, const Ws &w, const uint8_t *idx, const int *perm, const float *weights, int B, cudaStream_t s) {
+void backward(flexs_vae *v, const Ws &w, const uint8_t *idx, const int *perm, const float *weights, int B, cudaStream_t s,
+              const long long *d_state = nullptr) {
     const int I = v->I, D = v->D, Z = v->Z, L = v->L, A = v->A;
     const int nBI = blocks((int64_t)B * I), nBZ = blocks((int64_t)B * Z);
-    k_loss<<<1, 256, 0, s>>>(w.out, idx, perm, weights, w.zm, w.zlv, w.ga, w.gzm, w.gzlv, w.loss, B, L, A, Z);   // ga = d loss / d pre7
+    k_loss<<<1, 256, 0, s>>>(w.out, idx, perm, d_state, weights, w.zm, w.zlv, w.ga, w.gzm, w.gzlv, w.loss, B, L, A, Z);   // ga = d loss / d pre7
     // decoder, last layer first; "gp" = gradient at a layer's pre-activation
     k_dense_bwd_w<<<blocks((int64_t)I * D + D), 256, 0, s>>>(w.g3, w.ga, GR(W7), GR(B7), B, I, D);
     k_dense_bwd_x<<<nBI, 256, 0, s>>>(AT(W7), w.ga, nullptr, w.g3, w.gb, B, I, D, 1);        // gb = gp6
@@ -384,15 +406,29 @@ void backward(flexs_vae *v, const Ws &w, const uint8_t *idx, const int *perm, co
     k_bn_bwd<<<blocks(I), 256, 0, s>>>(w.gb, w.xhat, w.istd, AT(BNG), w.h2, w.ga, GR(BNG), GR(BNB), B, I);   // ga = gp2
     k_dense_bwd_w<<<blocks((int64_t)I * I + I), 256, 0, s>>>(w.h1m, w.ga, GR(W2), GR(B2), B, I, I);
     k_dense_bwd_x<<<nBI, 256, 0, s>>>(AT(W2), w.ga, w.mask1, w.h1, w.gb, B, I, I, 1);        // gb = gp1
-    k_gather_bwd_w<<<blocks((int64_t)D * I + I), 256, 0, s>>>(idx, perm, w.gb, GR(W1), GR(B1), B, L, A, I);
+    k_gather_bwd_w<<<blocks((int64_t)D * I + I), 256, 0, s>>>(idx, perm, d_state, w.gb, GR(W1), GR(B1), B, L, A, I);
 }
 
-void adam(flexs_vae *v, cudaStream_t s) {
-    v->step += 1;
-    const double t = (double)v->step;
-    const float lr_t = (float)(ADAM_LR * std::sqrt(1.0 - std::pow((double)ADAM_B2, t)) / (1.0 - std::pow((double)ADAM_B1, t)));
-    k_adam_clip<<<blocks(v->total), 256, 0, s>>>(v->w, v->g, v->m, v->v, v->total, lr_t, nullptr, v->offs[BNM],
+// d_state == nullptr: the host counts the steps (train_step_dev); else the step number lives on the device (fit_dev)
+void adam(flexs_vae *v, cudaStream_t s, const long long *d_state = nullptr) {
+    float lr_t = 0.f;
+    if (!d_state) {
+        v->step += 1;
+        const double t = (double)v->step;
+        lr_t = (float)(ADAM_LR * std::sqrt(1.0 - std::pow((double)ADAM_B2, t)) / (1.0 - std::pow((double)ADAM_B1, t)));
+    }
+    k_adam_clip<<<blocks(v->total), 256, 0, s>>>(v->w, v->g, v->m, v->v, v->total, lr_t, d_state, v->offs[BNM],
                                                   v->offs[BNV] + v->sizes[BNV]);
+}
+
+// one optimiser step on the B rows perm[d_state[1] ..] with everything step-dependent read from d_state: capturable
+void graph_step(flexs_vae *v, const Ws &w, const uint8_t *idx, const int *perm, const float *weights, int B, uint64_t seed,
+                cudaStream_t s) {
+    k_noise<<<blocks((int64_t)B * v->I), 256, 0, s>>>(w.mask1, w.mask2, w.eps, B * v->I, B * v->Z, seed, 0, v->d_state);
+    forward(v, w, idx, perm, B, true, w.eps, s, v->d_state);
+    backward(v, w, idx, perm, weights, B, s, v->d_state);
+    adam(v, s, v->d_state);
+    k_advance<<<1, 1, 0, s>>>(v->d_state, B, 1);
 }
 
 }  // namespace
@@ -429,7 +465,8 @@ int flexs_vae_create(int device, int seq_len, int alphabet_size, int intermediat
 void flexs_vae_destroy(flexs_vae_t *v) {
     if (!v) return;
     cudaSetDevice(v->device);
-    cudaFree(v->w); cudaFree(v->g); cudaFree(v->m); cudaFree(v->v); cudaFree(v->ws);
+    cudaFree(v->w); cudaFree(v->g); cudaFree(v->m); cudaFree(v->v); cudaFree(v->ws); cudaFree(v->d_state);
+    if (v->fit_stream) cudaStreamDestroy(v->fit_stream);
     delete v;
 }
 
@@ -515,32 +552,61 @@ int flexs_vae_fit_dev(flexs_vae_t *v, const uint8_t *d_idx, const float *d_weigh
     }
     int *d_perm = nullptr;
     FX_CUDA(cudaMalloc(&d_perm, sizeof(int) * perm.size()));
-    FX_CUDA(cudaMemcpyAsync(d_perm, perm.data(), sizeof(int) * perm.size(), cudaMemcpyHostToDevice, s));
+    if (!v->d_state) FX_CUDA(cudaMalloc(&v->d_state, 2 * sizeof(long long)));
+    if (!v->fit_stream) FX_CUDA(cudaStreamCreateWithFlags(&v->fit_stream, cudaStreamNonBlocking));
+    cudaStream_t fs = v->fit_stream;
+    // the fit runs on its own stream (a graph cannot be captured on the legacy default stream), ordered after the caller's
+    cudaEvent_t ev;
+    FX_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    FX_CUDA(cudaEventRecord(ev, s));
+    FX_CUDA(cudaStreamWaitEvent(fs, ev, 0));
+    FX_CUDA(cudaMemcpyAsync(d_perm, perm.data(), sizeof(int) * perm.size(), cudaMemcpyHostToDevice, fs));
+    const long long state0[2] = {(long long)v->step, 0};
+    FX_CUDA(cudaMemcpyAsync(v->d_state, state0, sizeof(state0), cudaMemcpyHostToDevice, fs));
+    Ws w = carve(v, Bmax);
+    // ONE optimiser step (~45 launches) captured as a CUDA graph and replayed for every full mini-batch: the step number and
+    // the position in the permutation are device-side state, so nothing in the graph changes between replays
+    const int64_t n_full = n_train / batch_size;
+    const int B_last = (int)(n_train - n_full * batch_size);
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    if (n_full > 0) {
+        FX_CUDA(cudaStreamBeginCapture(fs, cudaStreamCaptureModeThreadLocal));
+        graph_step(v, w, d_idx, d_perm, d_weights, batch_size, seed, fs);
+        FX_CUDA(cudaStreamEndCapture(fs, &graph));
+        FX_CUDA(cudaGraphInstantiate(&exec, graph, nullptr, nullptr, 0));
+    }
     double best = 1e300;
     int bad = 0, ran = 0;
-    Ws w = carve(v, Bmax);
+    int64_t steps_done = 0;
     for (int e = 0; e < epochs; ++e) {
-        FX_CUDA(cudaMemsetAsync(w.loss, 0, sizeof(double), s));
+        FX_CUDA(cudaMemsetAsync(w.loss, 0, sizeof(double), fs));
         int64_t counted = 0;
-        for (int64_t start = 0; start < n_train; start += batch_size) {
-            const int B = (int)std::min<int64_t>(batch_size, n_train - start);
-            if (B < 2) continue;   // BatchNorm needs more than one sample in training mode
-            const int *pb = d_perm + (size_t)e * n_train + start;
-            k_noise<<<blocks((int64_t)B * v->I), 256, 0, s>>>(w.mask1, w.mask2, w.eps, B * v->I, B * v->Z, seed, (uint64_t)v->step + 1);
-            forward(v, w, d_idx, pb, B, true, w.eps, s);
-            backward(v, w, d_idx, pb, d_weights, B, s);
-            adam(v, s);
-            counted += B;
+        for (int64_t b = 0; b < n_full; ++b) FX_CUDA(cudaGraphLaunch(exec, fs));
+        counted += n_full * batch_size;
+        steps_done += n_full;
+        if (B_last >= 2) {   // the ragged last mini-batch: same kernels, launched directly
+            graph_step(v, w, d_idx, d_perm, d_weights, B_last, seed, fs);
+            counted += B_last;
+            steps_done += 1;
+        } else if (B_last == 1) {
+            k_advance<<<1, 1, 0, fs>>>(v->d_state, 1, 0);   // BatchNorm needs more than one sample in training mode: skipped
         }
         double h = 0.0;
-        FX_CUDA(cudaMemcpyAsync(&h, w.loss, sizeof(double), cudaMemcpyDeviceToHost, s));
-        FX_CUDA(cudaStreamSynchronize(s));
+        FX_CUDA(cudaMemcpyAsync(&h, w.loss, sizeof(double), cudaMemcpyDeviceToHost, fs));
+        FX_CUDA(cudaStreamSynchronize(fs));
         const double epoch_loss = h / (double)std::max<int64_t>(counted, 1);
         if (h_losses) h_losses[e] = (float)epoch_loss;
         ran = e + 1;
         if (epoch_loss < best - 1e-12) { best = epoch_loss; bad = 0; }
         else if (patience > 0 && ++bad >= patience) break;   // EarlyStopping(monitor="loss", patience=3), VAE_utils.py:139
     }
+    v->step += steps_done;
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    FX_CUDA(cudaEventRecord(ev, fs));
+    FX_CUDA(cudaStreamWaitEvent(s, ev, 0));   // later work on the caller's stream sees the trained weights
+    cudaEventDestroy(ev);
     cudaFree(d_perm);
     FX_CUDA(cudaGetLastError());
     if (epochs_run) *epochs_run = ran;
