@@ -376,12 +376,15 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
                 for (int j = 0; j < 32; ++j) mx[j] = -INFINITY;
                 const int fg = (up8 ? 2 : 0) + (up16 ? 1 : 0);
                 float4 *wr = reinterpret_cast<float4 *>(stg + lq * 256 + (fg * 8 + b) * 8);
-                wr[0] = make_float4(k8[0], k8[1], k8[2], k8[3]);
-                wr[1] = make_float4(k8[4], k8[5], k8[6], k8[7]);
+                // the two 16-byte halves of a stream's 8 maxima swap places for streams 4-7: a quarter-warp (8 streams, 32 B
+                // apart) then covers all eight 16-byte bank groups per store instead of four twice (ncu source view: 2-way)
+                const int sw = (b >> 2) & 1;
+                wr[sw] = make_float4(k8[0], k8[1], k8[2], k8[3]);
+                wr[sw ^ 1] = make_float4(k8[4], k8[5], k8[6], k8[7]);
             }
             asm volatile("bar.sync 2, 128;" ::: "memory");
             const int pr = lane >> 3, f = 8 * lq + 2 * pr;
-            const float *rd = stg + (lq * 8 + b) * 8 + 2 * pr;
+            const float *rd = stg + (lq * 8 + b) * 8 + ((2 * pr) ^ (((b >> 2) & 1) << 2));   // the writers' half swap
             float2 t = *reinterpret_cast<const float2 *>(rd);
 #pragma unroll
             for (int w4 = 1; w4 < 4; ++w4) {

@@ -425,8 +425,11 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
                 for (int j = 0; j < 32; ++j) mx[j] = -INFINITY;
                 const int fg = (up8 ? 2 : 0) + (up16 ? 1 : 0);
                 float4 *wr = reinterpret_cast<float4 *>(slot + (fg * 8 + b) * 8);
-                wr[0] = make_float4(k8[0], k8[1], k8[2], k8[3]);
-                wr[1] = make_float4(k8[4], k8[5], k8[6], k8[7]);
+                // the two 16-byte halves of a stream's 8 maxima swap places for streams 4-7: a quarter-warp (8 streams, 32 B
+                // apart) then covers all eight 16-byte bank groups per store instead of four twice (ncu source view: 2-way)
+                const int sw = (b >> 2) & 1;
+                wr[sw] = make_float4(k8[0], k8[1], k8[2], k8[3]);
+                wr[sw ^ 1] = make_float4(k8[4], k8[5], k8[6], k8[7]);
             };
             // Step 2: the 4 warps of the set (4 positions each) meet in the set's double-buffered staging area — plain
             // stores, a 128-thread barrier, warp lq reduces filters 8 lq .. 8 lq + 7.  Step 3: scale, bias, ReLU, one plain
@@ -439,7 +442,7 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
                 if (par == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
                 else asm volatile("bar.sync 4, 128;" ::: "memory");
                 const int pr = lane >> 3, f = 8 * lq + 2 * pr, sl = item * 8 + b;
-                const float *rd = stg + (lq * 8 + b) * 8 + 2 * pr;
+                const float *rd = stg + (lq * 8 + b) * 8 + ((2 * pr) ^ (((b >> 2) & 1) << 2));   // the writers' half swap
                 float2 t = *reinterpret_cast<const float2 *>(rd);
 #pragma unroll
                 for (int w4 = 1; w4 < 4; ++w4) {
