@@ -14,7 +14,7 @@
 // starts at a chunk boundary; the head of each ring is mirrored behind its end so every window is contiguous.  Nothing
 // is ever recomputed (no halo): "same" padding (cnn.py:33-47; TF rule left = (k-1)/2) is the zero groups before position
 // 0 and after position T-1, which the epilogues write as zeros.
-//      h1 group v  <->  position v - 11      conv2 tile q reads h1 groups [16q, 16q + 20)   ring: 2 chunks + 4 mirrored
+//      h1 group v  <->  position v - 11      conv2 tile q reads h1 groups [16q, 16q + 20)   ring: 2 (or 3) chunks + 4 mirrored
 //      h2 group u  <->  position u - 9       conv3 tile q reads h2 groups [16q, 16q + 34)   ring: 3 chunks + 18 mirrored
 //
 // Roles (14 warps, no CTA-wide barrier inside the loop; everything meets through mbarriers):
@@ -48,7 +48,7 @@ using namespace u2;
 constexpr int KC3 = 19, NA = 20;
 constexpr int NT = 448;                     // 14 warps
 constexpr int W_E2 = 4, W_E3 = 8, W_I2 = 12, W_I3 = 13;
-constexpr int R1C = 2, R1M = K - 1, R1G = R1C * 16 + R1M;      // h1 ring: 36 groups
+constexpr int R1M = K - 1;                                      // h1 ring: r1c (2 or 3) chunks + 4 mirrored groups
 constexpr int R2C = 3, R2M = KC3 - 1, R2G = R2C * 16 + R2M;    // h2 ring: 66 groups
 constexpr int GS = DSLOTS;                  // sequences per feature tile of the dense kernel
 
@@ -60,12 +60,15 @@ constexpr int A20_MEMBER_BYTES = (A20_OFF_T34 + NA * NA * F * 4 + 255) / 256 * 2
 
 // shared memory map (the rings need 1024-byte alignment: SWIZZLE_128B atoms)
 constexpr int S_BAR = 0, S_TM = 512, S_B2S = 640, S_B3 = 768;
-constexpr int S_W2 = 1024, S_W3 = S_W2 + K * UWTAP, S_R1 = S_W3 + KC3 * UWTAP, S_R2 = S_R1 + R1G * 1024;
-constexpr int S_STAGE = S_R2 + R2G * 1024, S_IDX = S_STAGE + 2 * 4 * 256 * 4;
-static_assert(S_R1 % 1024 == 0 && S_R2 % 1024 == 0, "rings must be aligned to the swizzle atom");
+constexpr int S_W2 = 1024, S_W3 = S_W2 + K * UWTAP, S_R1 = S_W3 + KC3 * UWTAP;
+static_assert(S_R1 % 1024 == 0, "rings must be aligned to the swizzle atom");
+// behind the h1 ring of r1c chunks: the h2 ring, the merge staging buffer (4 warps x 256 maxima), the residue buffer(s)
+__host__ __device__ constexpr int s_r2(int r1c) { return S_R1 + (r1c * 16 + R1M) * 1024; }
+__host__ __device__ constexpr int s_stage(int r1c) { return s_r2(r1c) + R2G * 1024; }
+__host__ __device__ constexpr int s_idx(int r1c) { return s_stage(r1c) + 4 * 256 * 4; }
 
 // mbarriers
-constexpr int B_IDX = 0, B_H1F = 2, B_H1E = 4, B_A2F = 6, B_A2E = 8, B_H2F = 10, B_H2E = 13, B_A3F = 16, B_A3E = 18, B_N = 20;
+constexpr int B_IDX = 0, B_H1F = 2, B_H1E = 5, B_A2F = 8, B_A2E = 10, B_H2F = 12, B_H2E = 15, B_A3F = 18, B_A3E = 20;
 
 struct A20Params {
     const uint8_t *idx;        // [n][L] residues
@@ -76,6 +79,7 @@ struct A20Params {
     int64_t n, n_items;
     fx::CnnOffsets o;
     int L, T, nt3, nc2, nlive2, nc1, idx_slot;
+    int r1c, idx_nbuf;   // h1 ring chunks (3 when shared memory allows: conv2 runs a chunk further ahead), residue buffers
     long long *prof;  // FLEXS_UMMA_PROF=1: per-CTA wait counters of each role
 };
 
@@ -140,11 +144,13 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
     if (tid == 0) {
         fxd::mbar_init(&bar[B_IDX], 1); fxd::mbar_init(&bar[B_IDX + 1], 1);
         for (int i = 0; i < 2; ++i) {
-            fxd::mbar_init(&bar[B_H1F + i], 4); fxd::mbar_init(&bar[B_H1E + i], 1);
             fxd::mbar_init(&bar[B_A2F + i], 1); fxd::mbar_init(&bar[B_A2E + i], 4);
             fxd::mbar_init(&bar[B_A3F + i], 1); fxd::mbar_init(&bar[B_A3E + i], 4);
         }
-        for (int i = 0; i < 3; ++i) { fxd::mbar_init(&bar[B_H2F + i], 4); fxd::mbar_init(&bar[B_H2E + i], 1); }
+        for (int i = 0; i < 3; ++i) {
+            fxd::mbar_init(&bar[B_H1F + i], 4); fxd::mbar_init(&bar[B_H1E + i], 1);
+            fxd::mbar_init(&bar[B_H2F + i], 4); fxd::mbar_init(&bar[B_H2E + i], 1);
+        }
         fxd::fence_mbar_init();
     }
     if (wid == 0) tmem_alloc(tmem_addr_s, 256);  // conv2 accumulators at columns 0 / 64, conv3 at 128 / 192
@@ -156,7 +162,9 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
     }
     for (int i = tid; i < (K + KC3) * UWTAP / 16; i += NT)
         reinterpret_cast<uint4 *>(smem_raw + S_W2)[i] = __ldg(reinterpret_cast<const uint4 *>(p.uw + A20_OFF_UW2) + i);
-    for (int i = tid; i < (R1G + R2G) * 1024 / 16; i += NT)
+    const uint32_t r1c = (uint32_t)p.r1c;
+    const int S_R2 = s_r2(p.r1c), S_STAGE = s_stage(p.r1c), S_IDX = s_idx(p.r1c);
+    for (int i = tid; i < (S_STAGE - S_R1) / 16; i += NT)
         reinterpret_cast<uint4 *>(smem_raw + S_R1)[i] = make_uint4(0, 0, 0, 0);
     fence_async_smem();
     tc_fence_before();
@@ -186,16 +194,22 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
         if (tid == 0 && (int64_t)blockIdx.x < p.n_items) issue_idx_load(p, smem_raw + S_IDX, &bar[B_IDX], blockIdx.x);
         uint32_t g1 = 0, itc = 0;
         for (int64_t item = blockIdx.x; item < p.n_items; item += stride, ++itc) {
-            // every producer is done with the previous item: its residue buffer (the next item's) is free
+            // every producer is done with the previous item: its residue buffer is free.  Two buffers: the NEXT item's
+            // residues are fetched now; one buffer (long sequences, where the third h1 chunk is worth more): this item's.
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (tid == 0 && item + stride < p.n_items)
-                issue_idx_load(p, smem_raw + S_IDX + ((itc + 1) & 1) * p.idx_slot, &bar[B_IDX + ((itc + 1) & 1)], item + stride);
-            fxd::mbar_wait(&bar[B_IDX + (itc & 1)], (itc >> 1) & 1);
+            const uint32_t ibuf = p.idx_nbuf == 2 ? (itc & 1u) : 0u;
+            if (p.idx_nbuf == 2) {
+                if (tid == 0 && item + stride < p.n_items)
+                    issue_idx_load(p, smem_raw + S_IDX + (ibuf ^ 1u) * p.idx_slot, &bar[B_IDX + (ibuf ^ 1u)], item + stride);
+            } else if (tid == 0 && itc > 0) {
+                issue_idx_load(p, smem_raw + S_IDX, &bar[B_IDX], item);
+            }
+            fxd::mbar_wait(&bar[B_IDX + ibuf], (p.idx_nbuf == 2 ? (itc >> 1) : itc) & 1);
             const int nvalid = (int)min((int64_t)8, p.n - item * 8);
-            const uint8_t *sidx = smem_raw + S_IDX + (itc & 1) * p.idx_slot +
+            const uint8_t *sidx = smem_raw + S_IDX + ibuf * p.idx_slot +
                                   ((reinterpret_cast<uintptr_t>(p.idx) + (uintptr_t)(item * 8 * L)) & 15) + (b < nvalid ? b : 0) * L;
             for (int qc = 0; qc < p.nc1; ++qc, ++g1) {
-                const uint32_t slot = g1 & 1u;
+                const uint32_t use1 = g1 / r1c, slot = g1 - use1 * r1c;
                 float4 ta[4][2], tb[4][2];
                 bool ok[4];
 #pragma unroll
@@ -215,7 +229,7 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
                 // the gathers are in flight before the ring slot is waited for: their L2 latency is off the
                 // conv2 -> conv1 -> conv2 dependency chain of the two-chunk ring
                 const long long w0 = now();
-                if (g1 >= 2) fxd::mbar_wait(&bar[B_H1E + slot], ((g1 >> 1) - 1) & 1);
+                if (use1 > 0) fxd::mbar_wait(&bar[B_H1E + slot], (use1 - 1) & 1);
                 pt[0] += now() - w0;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -233,8 +247,8 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
                     st_shared_v4(row + first_off, first4);
                     st_shared_v4(row + second_off, second4);
                     if (gr < (uint32_t)R1M) {  // head of the ring, mirrored behind its end
-                        st_shared_v4(row + R1C * 16 * 1024 + first_off, first4);
-                        st_shared_v4(row + R1C * 16 * 1024 + second_off, second4);
+                        st_shared_v4(row + r1c * 16 * 1024 + first_off, first4);
+                        st_shared_v4(row + r1c * 16 * 1024 + second_off, second4);
                     }
                 }
                 fence_async_smem();
@@ -323,8 +337,8 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
         const int lq = wid & 3, c = 4 * lq + (lane >> 3), b = lane & 7;
         const uint32_t tlane = tmem_base + ((uint32_t)(lq * 32) << 16) + 128u;
         const bool up8 = (lane & 8) != 0, up16 = (lane & 16) != 0;
-        float *stage_s = reinterpret_cast<float *>(smem_raw + S_STAGE);  // [2 buffers][4 warps][4 fg][8 b][8 f]
-        uint32_t t3 = 0, nflush = 0;
+        float *stg = reinterpret_cast<float *>(smem_raw + S_STAGE);  // [4 warps][4 fg][8 b][8 f]
+        uint32_t t3 = 0;
         float mx[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) mx[j] = -INFINITY;
@@ -358,7 +372,6 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
             // GlobalMaxPooling1D: the 4 lanes of stream b merge with a halving butterfly (after the xor-8 step a lane keeps
             // filters 16 (lane bit 3) + 0..15, after the xor-16 step 8 of those), park them in this warp's 256-float slot
             // [fg][b][8]; the 4 warps meet in the double-buffered staging area; warp lq then reduces filters 8 lq .. 8 lq + 7.
-            float *stg = stage_s + (int)(nflush & 1) * 4 * 256;
             {
                 float k16[16];
 #pragma unroll
@@ -397,17 +410,18 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
                 dst[(size_t)f * GS] = fmaxf(fmaf(t.x, inv3, b3[f]), 0.f);
                 dst[(size_t)(f + 1) * GS] = fmaxf(fmaf(t.y, inv3, b3[f + 1]), 0.f);
             }
-            ++nflush;
+            asm volatile("bar.sync 2, 128;" ::: "memory");   // everyone has read the staging buffer: the next item may write it
         }
     } else if (wid == W_I2) {
         // =========================== conv2 MMA issue ===========================
         uint32_t g1 = 0, a2 = 0;
         for (int64_t item = blockIdx.x; item < p.n_items; item += stride) {
             for (int qc = 0; qc < p.nlive2; ++qc, ++g1, ++a2) {
-                const uint32_t s0 = g1 & 1u, a = a2 & 1u;
+                const uint32_t use1 = g1 / r1c, s0 = g1 - use1 * r1c, a = a2 & 1u;
+                const uint32_t use1n = (g1 + 1) / r1c, s1 = (g1 + 1) - use1n * r1c;
                 const long long w0 = now();
-                fxd::mbar_wait_warp(&bar[B_H1F + s0], (g1 >> 1) & 1);
-                fxd::mbar_wait_warp(&bar[B_H1F + (s0 ^ 1u)], ((g1 + 1) >> 1) & 1);  // the window ends 4 groups into the next chunk
+                fxd::mbar_wait_warp(&bar[B_H1F + s0], use1 & 1);
+                fxd::mbar_wait_warp(&bar[B_H1F + s1], use1n & 1);  // the window ends 4 groups into the next chunk
                 const long long w1 = now();
                 if (a2 >= 2) fxd::mbar_wait_warp(&bar[B_A2E + a], ((a2 >> 1) - 1) & 1);
                 const long long w2 = now();
@@ -419,7 +433,7 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
                 pt[2] += now() - w2;
             }
             // the item's last h1 chunk is only ever the 4-group tail of the last window: release it as well
-            umma_commit_elect(&bar[B_H1E + (g1 & 1u)]);
+            umma_commit_elect(&bar[B_H1E + g1 % r1c]);
             ++g1;
         }
     } else {
@@ -474,7 +488,17 @@ static bool plan(const flexs_model *m, A20Params &p) {
     p.nlive2 = (p.T + 8) / 16 + 1;      // h2 chunks with a position inside the sequence (the others are zero padding)
     p.nc1 = p.nlive2 + 1;               // h1 chunks per item: a conv2 window ends 4 groups into the next chunk
     p.idx_slot = (int)align_up((size_t)8 * m->L + 32, 16);
-    return (int64_t)S_IDX + 2 * p.idx_slot + 1024 <= m->max_smem_optin;
+    // Two h1 chunks and two residue buffers; one residue buffer for very long sequences.  A third h1 chunk (conv2 a chunk
+    // further ahead) was measured: the conv2 issuer's wait for conv1 drops from 24 % to 10 % of an item, throughput does
+    // not move (gfp237 2.945e7 vs 2.952e7) — the tensor pipe is busy either way (51 cycles per MMA, 81 % of the conv3
+    // issuer's time is spent blocked on it).  FLEXS_A20_R1C=3 selects it for experiments.
+    static const bool three = std::getenv("FLEXS_A20_R1C") && std::getenv("FLEXS_A20_R1C")[0] == '3';
+    const int opts[4][2] = {{three ? 3 : 2, 2}, {three ? 3 : 2, 1}, {2, 2}, {2, 1}};
+    for (const auto &o : opts) {
+        p.r1c = o[0]; p.idx_nbuf = o[1];
+        if ((int64_t)s_idx(p.r1c) + p.idx_nbuf * p.idx_slot + 1024 <= m->max_smem_optin) return true;
+    }
+    return false;
 }
 
 static int prepare(flexs_model *m) {
@@ -547,7 +571,7 @@ int launch_cnn_a20(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out
     if (rc != FLEXS_OK) return rc;
     p.feat = reinterpret_cast<float *>(ws->ptr);
     p.overflow_flag = ws->flag;
-    const size_t smem = (size_t)S_IDX + 2 * p.idx_slot + 1024;
+    const size_t smem = (size_t)s_idx(p.r1c) + p.idx_nbuf * p.idx_slot + 1024;
     static const bool prof = std::getenv("FLEXS_UMMA_PROF") && std::getenv("FLEXS_UMMA_PROF")[0] == '1';
     auto kernel = prof ? cnn_a20_kernel<true> : cnn_a20_kernel<false>;
     FX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
