@@ -611,7 +611,7 @@ def main():
         launches_per_fwd = -(-args.batch // (148 * 56 * 128))
         seq_per_launch = args.batch / launches_per_fwd
         roofline.update({
-            "kernel": "cnn_k9_kernel (+ cnn_k9_dense_kernel)",
+            "kernel": "cnn_k9_pair_kernel (cta_group::2 CTA pairs; + cnn_k9_dense_kernel)",
             "tensor_flop_executed_per_seq": 2 * mac_exec, "tensor_tflops_executed": exec_tf,
             "tensor_frac_executed": exec_tf / peaks["bf16_tflops"],
             "sequences_per_launch": seq_per_launch,
@@ -627,7 +627,7 @@ def main():
             cap = json.load(open(cap_path))
             per_seq = (cap["dram_bytes_per_launch"] - cap["table_bytes"]) / cap["sequences_per_launch"]
             roofline.update({"traffic": cap["table_bytes"] + per_seq * seq_per_launch,
-                             "traffic_unit": "bytes per cnn_k9_kernel launch",
+                             "traffic_unit": "bytes per conv-kernel launch",
                              "traffic_source": f"{cap_path.name}: {cap['dram_bytes_per_launch']:.4g} B measured for "
                                                f"{cap['sequences_per_launch']} sequences, scaled to this launch size",
                              "traffic_over_algorithmic": (cap["table_bytes"] + per_seq * seq_per_launch) /

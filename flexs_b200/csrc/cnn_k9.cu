@@ -189,6 +189,80 @@ __device__ __forceinline__ void issue_conv3_tile(uint32_t a_slot_addr, uint32_t 
     }
 }
 
+// ---- CTA-pair variant (cta_group::2): two CTAs of a cluster run the same tile index on their own 128 rows as ONE
+// M = 256 MMA.  The B operand of a pair MMA is split by columns: CTA rank r supplies filters [r N/2, (r+1) N/2) from
+// the SAME shared-memory offset of its own SM (tools/pair_mma_test.cu measures exactly this), so each SM reads half of
+// the weight planes per tile — the operand traffic that bounds the single-CTA kernel drops from 11 KB to 9.5 KB per tile.
+// Weight planes per CTA: W64 [tap][chunk][32 rows of this rank's half of hi|lo][16 B], W32 [tap][chunk][16 rows of
+// this rank's half of hi][16 B].
+constexpr int PW64_CH = 32 * 16, PW64_TAP = 4 * PW64_CH, PW32_CH = 16 * 16, PW32_TAP = 4 * PW32_CH;
+constexpr int PW32_OFF = K3 * PW64_TAP;
+constexpr uint32_t IDESC_P64 = (1u << 4) | ((64u >> 3) << 17) | ((256u >> 4) << 24);
+constexpr uint32_t IDESC_P32 = (1u << 4) | ((32u >> 3) << 17) | ((256u >> 4) << 24);
+static_assert(PW32_OFF + K3 * PW32_TAP <= K3 * UWTAP, "pair weight planes fit the single-CTA staging area");
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the leader CTA's copy of a shared-memory object, usable with the shared::cluster forms
+__device__ __forceinline__ uint32_t leader_addr(const void *local) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(fxd::smem_u32(local)));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    // default semantics (release at CTA scope): a cluster-scope release costs MEMBAR.ALL.GPU + two error barriers per
+    // arrival (measured: +60 % kernel time).  What the arrival publishes is this SM's own shared memory / TMEM state,
+    // complete before the arrive issues (cp.async.wait_all + proxy fence, tcgen05.wait::ld), and it is consumed by this
+    // SM's half of the pair MMA, which the leader can only start after it has seen the arrival.
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(fxd::smem_u32(dst_smem)),
+                 "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair_elect(uint32_t d_tmem, uint32_t a_lo32, uint32_t a_hi32, uint32_t b_lo32,
+                                                    uint32_t b_hi32, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "elect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo32), "r"(a_hi32), "r"(b_lo32), "r"(b_hi32), "r"(idesc), "r"(accumulate) : "memory");
+}
+// the arrival lands on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair_elect(uint64_t *bar) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+        ::"r"(fxd::smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void issue_conv3_tile_pair(uint32_t a_slot_addr, uint32_t w_addr, uint32_t d_tmem) {
+    const uint32_t a0 = desc_lo(a_slot_addr, 16);
+    const uint32_t b64 = desc_lo(w_addr, PW64_CH), b32 = desc_lo(w_addr + PW32_OFF, PW32_CH);
+#pragma unroll
+    for (int j = 0; j < K3; ++j) {
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) {
+            const uint32_t a_hi = a0 + (((uint32_t)j * 1024u + (uint32_t)kp * 32u) >> 4);
+            const uint32_t a_lo = a_hi + (64u >> 4);
+            const uint32_t bd64 = b64 + (((uint32_t)j * PW64_TAP + (uint32_t)(2 * kp) * PW64_CH) >> 4);
+            const uint32_t bd32 = b32 + (((uint32_t)j * PW32_TAP + (uint32_t)(2 * kp) * PW32_CH) >> 4);
+            umma_f16_pair_elect(d_tmem, a_hi, A_DESC_HI, bd64, DESC_HI, IDESC_P64, (j | kp) ? 1u : 0u);
+            umma_f16_pair_elect(d_tmem, a_lo, A_DESC_HI, bd32, DESC_HI, IDESC_P32, 1u);
+        }
+    }
+}
+
 __device__ __forceinline__ void issue_idx_load(const K9Params &p, uint8_t *dst, uint64_t *bar, int64_t group) {
     const int64_t first = group * GS;
     const int64_t cnt = min((int64_t)GS, p.n - first);
@@ -206,8 +280,8 @@ __device__ __forceinline__ void issue_idx_load(const K9Params &p, uint8_t *dst, 
         : "memory");
 }
 
-template <bool PROF>
-__global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
+template <bool PROF, bool PAIR>
+__device__ __forceinline__ void k9_body(const K9Params &p) {
     auto now = [] { return PROF ? clock64() : 0ll; };  // phase timers exist only in the FLEXS_UMMA_PROF=1 instantiation
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const Offs of = carve(p);
@@ -225,27 +299,55 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
     const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int L = p.L, T = p.T, nti = p.nti;
 
+    // Work units.  Single CTA: unit = CTA, one group of 128 sequences per step.  Pair: unit = cluster of two CTAs that
+    // walk the groups 2u, 2u + 1 in lockstep (same tile index at the same time); the leader's group is the earlier and
+    // therefore the fuller one, so it sets the tile count, and the peer pads with absent streams (zero rows).
+    const uint32_t rank = PAIR ? cluster_rank() : 0u;
+    const int64_t W = PAIR ? 2 : 1;
+    const int64_t gb0 = (int64_t)(PAIR ? (blockIdx.x >> 1) : blockIdx.x) * W;
+    const int64_t gstep = (int64_t)(PAIR ? (gridDim.x >> 1) : gridDim.x) * W;
+    auto mine_of = [&](int64_t gb) -> int {  // sequences of this CTA's group of the unit step at gb (0: no group)
+        const int64_t left = p.n - (gb + rank) * GS;
+        return (int)max((int64_t)0, min((int64_t)GS, left));
+    };
+    auto lead_of = [&](int64_t gb) -> int { return (int)min((int64_t)GS, p.n - gb * GS); };
+
     if (tid == 0) {
         fxd::mbar_init(mbar_idx, 1);
         for (int i = 0; i < RING; ++i) {
-            fxd::mbar_init(&full[i], 1); fxd::mbar_init(&empty[i], 1);
-            fxd::mbar_init(&tfull[i], 1); fxd::mbar_init(&tfull[8 + i], 1); fxd::mbar_init(&tempty[i], 4);
+            // pair: the leader's "operands ready" / "accumulator drained" barriers collect both CTAs' arrivals
+            fxd::mbar_init(&full[i], PAIR ? 2 : 1); fxd::mbar_init(&empty[i], 1);
+            fxd::mbar_init(&tfull[i], 1); fxd::mbar_init(&tfull[8 + i], 1); fxd::mbar_init(&tempty[i], PAIR ? 8 : 4);
         }
         fxd::fence_mbar_init();
     }
-    if (wid == 0) tmem_alloc(tmem_addr_s, 512);
+    if (wid == 0) { if (PAIR) tmem_alloc_pair(tmem_addr_s, 512); else tmem_alloc(tmem_addr_s, 512); }
     for (int i = tid; i < F * SBP; i += NT) feat_s[i] = 0.f;
     const float inv3 = __ldg(reinterpret_cast<const float *>(p.uw + OFF_SCAL) + 1);
     for (int i = tid; i < F; i += NT) b3[i] = __ldg(p.weights + p.o.b3 + i);
-    for (int i = tid; i < K3 * UWTAP / 16; i += NT)
-        reinterpret_cast<uint4 *>(uw3)[i] = __ldg(reinterpret_cast<const uint4 *>(p.uw + OFF_UW3) + i);
+    if (!PAIR) {
+        for (int i = tid; i < K3 * UWTAP / 16; i += NT)
+            reinterpret_cast<uint4 *>(uw3)[i] = __ldg(reinterpret_cast<const uint4 *>(p.uw + OFF_UW3) + i);
+    } else {
+        // this rank's column halves of the weight planes: rows 32 r .. 32 r + 31 of [hi|lo], rows 16 r .. 16 r + 15 of hi
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.uw + OFF_UW3);
+        for (int i = tid; i < K3 * 4 * 32; i += NT) {
+            const int blk = i >> 5, row = i & 31;
+            reinterpret_cast<uint4 *>(uw3)[i] = __ldg(src + blk * 64 + 32 * (int)rank + row);
+        }
+        for (int i = tid; i < K3 * 4 * 16; i += NT) {
+            const int blk = i >> 4, row = i & 15;
+            reinterpret_cast<uint4 *>(uw3 + PW32_OFF)[i] = __ldg(src + blk * 64 + 16 * (int)rank + row);
+        }
+    }
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();  // both CTAs' barriers exist before anyone arrives on the peer's
     tc_fence_after();
     const uint32_t tmem_base = *tmem_addr_s;
     const uint32_t ring_addr = fxd::smem_u32(ring), uw3_addr = fxd::smem_u32(uw3);
-    if (tid == 0) issue_idx_load(p, smem_raw + of.idx, mbar_idx, blockIdx.x);
+    if (tid == 0 && mine_of(gb0) > 0) issue_idx_load(p, smem_raw + of.idx, mbar_idx, gb0 + rank);
 
     uint32_t kt = 0;  // tiles before the current group: tile k uses slot = accumulator = k & 7
     uint32_t gi = 0;  // groups before the current one: packed-residue buffer and residue-barrier parity = gi & 1
@@ -262,12 +364,13 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
         const uint32_t dst1 = (uint32_t)((rr + 4) * 128 + ((jch ^ (rr + 4)) << 4));
         const unsigned char *tabj = p.tab + jch * 16;
         const int nwp = p.nwp;
-        for (int64_t g = blockIdx.x; g < p.n_groups; g += gridDim.x, ++gi) {
-            const int64_t first = g * GS;
-            const int s_grp = (int)min((int64_t)GS, p.n - first);
-            const uint32_t ntiles = (uint32_t)(((s_grp + 7) >> 3) * nti);
+        const uint32_t full_mine = PAIR ? leader_addr(&full[wid]) : 0u;
+        for (int64_t gb = gb0; gb < p.n_groups; gb += gstep, ++gi) {
+            const int64_t first = (gb + rank) * GS;
+            const int s_grp = mine_of(gb);
+            const uint32_t ntiles = (uint32_t)(((lead_of(gb) + 7) >> 3) * nti);
             uint32_t *pw = reinterpret_cast<uint32_t *>(smem_raw + of.pw) + (gi & 1) * GS * nwp;
-            fxd::mbar_wait(mbar_idx, gi & 1);
+            if (s_grp > 0) fxd::mbar_wait(mbar_idx, gi & 1);  // (a CTA without a group is in its last step)
             const uint8_t *sidx = smem_raw + of.idx + ((reinterpret_cast<uintptr_t>(p.idx) + (uintptr_t)(first * L)) & 15);
             // residues -> 2 bits each, 16 per word, first residue in the top bits; a zero word on either side
             for (int i = tid; i < s_grp * nwp; i += NPROD * 32) {
@@ -283,14 +386,17 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
             }
             asm volatile("bar.sync 1, %0;" ::"n"(NPROD * 32) : "memory");
             // every producer has packed: the staging buffer is free for the next group's residues
-            if (tid == 0 && g + gridDim.x < p.n_groups) issue_idx_load(p, smem_raw + of.idx, mbar_idx, g + gridDim.x);
+            if (tid == 0 && mine_of(gb + gstep) > 0) issue_idx_load(p, smem_raw + of.idx, mbar_idx, gb + gstep + rank);
             for (uint32_t tl = ((uint32_t)wid - kt) & 7u; tl < ntiles; tl += NPROD) {
                 const uint32_t use = (kt + tl) >> 3;
                 const long long q0 = now();
                 if (use > 0) fxd::mbar_wait(&empty[wid], (use - 1) & 1);  // the MMAs that read this slot retired
                 const long long q1 = now();
                 const int item = (int)tl / nti, q = (int)tl - item * nti;
-                if (PROF && (p.dbg & 2)) { if (lane == 0) mbar_arrive(&full[wid]); continue; }
+                if (PROF && (p.dbg & 2)) {
+                    if (lane == 0) { if (PAIR) mbar_arrive_remote(full_mine); else mbar_arrive(&full[wid]); }
+                    continue;
+                }
                 // residues 16(q-1) .. 16(q+2)-1 of the lane's two streams (word index + 1 in the padded array)
                 const int sl0 = item * 8 + rr, sl1 = sl0 + 4;
                 const bool ok0 = sl0 < s_grp, ok1 = sl1 < s_grp;
@@ -338,7 +444,7 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
                 asm volatile("cp.async.wait_all;" ::: "memory");
                 fence_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&full[wid]);
+                if (lane == 0) { if (PAIR) mbar_arrive_remote(full_mine); else mbar_arrive(&full[wid]); }
                 if (PROF && tid == 0) { pt[2] += q1 - q0; pt[3] += now() - q1; }
             }
             kt += ntiles;
@@ -362,14 +468,16 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
         const int et = tid - NPROD * 32;  // thread index among the 256 epilogue threads
         float *stage_s = reinterpret_cast<float *>(smem_raw + of.stage) + par * 2 * 4 * 256;  // [2 buffers][4 warps][4 fg][8 b][8 f]
         uint64_t *tfull_mine = tfull + 8 * par;
+        const uint32_t tempty_lead = PAIR ? leader_addr(&tempty[0]) : 0u;
         uint32_t nflush = 0;    // items of this set so far: staging buffer = nflush & 1
         uint32_t phase_bits = 0;  // bit a: parity of the next phase of this set's barrier for accumulator a
         float mx[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) mx[j] = -INFINITY;
-        for (int64_t g = blockIdx.x; g < p.n_groups; g += gridDim.x, ++gi) {
-            const int s_grp = (int)min((int64_t)GS, p.n - g * GS);
-            const int nitems = (s_grp + 7) >> 3;
+        for (int64_t gb = gb0; gb < p.n_groups; gb += gstep, ++gi) {
+            const int64_t g = gb + rank;
+            const int s_grp = mine_of(gb);
+            const int nitems = (lead_of(gb) + 7) >> 3;  // pair: the peer visits (and frees) every tile of the unit
             const uint32_t ntiles = (uint32_t)(nitems * nti);
             float *featT = feat_s;
             // one tile: accumulator -> registers -> running maxima
@@ -390,7 +498,9 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
                     if (hf == 1) {
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&tempty[acc]);  // the accumulator is in registers: hand it back
+                        if (lane == 0) {  // the accumulator is in registers: hand it back
+                            if (PAIR) mbar_arrive_remote(tempty_lead + acc * 8u); else mbar_arrive(&tempty[acc]);
+                        }
                     }
                     if (valid) {
 #pragma unroll
@@ -459,11 +569,13 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
             // the group's features are complete once all 8 epilogue warps are here: copy the [32][128] tile out
             // (slots past the end of the batch keep stale values; the dense kernel never reports them)
             asm volatile("bar.sync 2, %0;" ::"n"(8 * 32) : "memory");
-            float4 *dst = reinterpret_cast<float4 *>(p.feat + (size_t)g * F * GS);
+            if (s_grp > 0) {
+                float4 *dst = reinterpret_cast<float4 *>(p.feat + (size_t)g * F * GS);
 #pragma unroll
-            for (int i = et; i < F * GS / 4; i += 8 * 32) {
-                const int row = i >> 5, col = (i & 31) * 4;
-                dst[i] = *reinterpret_cast<const float4 *>(featT + row * SBP + col);
+                for (int i = et; i < F * GS / 4; i += 8 * 32) {
+                    const int row = i >> 5, col = (i & 31) * 4;
+                    dst[i] = *reinterpret_cast<const float4 *>(featT + row * SBP + col);
+                }
             }
             // the next group's first features are stored after a barrier of only one set: nobody
             // may still be reading this group's
@@ -474,10 +586,10 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
         // Two warps take alternate tiles: issuing a tile (two barrier waits, 12 MMAs, two commits) costs more issue time
         // than the tensor pipe needs to run it, and tiles are independent (own slot, own accumulator; a commit tracks
         // the MMAs of the committing thread).
+        // Pair: only the leader CTA issues; its MMAs drive both SMs' tensor cores and its commits arrive in both CTAs.
         const uint32_t me = (uint32_t)(wid - MMAW);
-        for (int64_t g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
-            const int s_grp = (int)min((int64_t)GS, p.n - g * GS);
-            const uint32_t ntiles = (uint32_t)(((s_grp + 7) >> 3) * nti);
+        for (int64_t gb = gb0; gb < p.n_groups && rank == 0; gb += gstep) {
+            const uint32_t ntiles = (uint32_t)(((lead_of(gb) + 7) >> 3) * nti);
             for (uint32_t tl = (me - kt) & (NMMA - 1); tl < ntiles; tl += NMMA) {
                 const uint32_t k = kt + tl, s = k & 7u, use = k >> 3;
                 const long long m0 = now();
@@ -486,9 +598,16 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
                 if (use > 0) fxd::mbar_wait_warp(&tempty[s], (use - 1) & 1);  // accumulator drained by the epilogue
                 if (PROF && lane == 0 && wid == MMAW) { pt[5] += m1 - m0; pt[6] += now() - m1; }
                 tc_fence_after();
-                if (!(PROF && (p.dbg & 1))) issue_conv3_tile(ring_addr + s * SLOT, uw3_addr, tmem_base + s * 64u);
-                umma_commit_elect(&tfull[8u * ((tl / (uint32_t)nti) & 1u) + s]);  // the epilogue set that owns the tile's item
-                umma_commit_elect(&empty[s]);
+                const uint32_t set_bar = 8u * ((tl / (uint32_t)nti) & 1u) + s;  // the epilogue set that owns the tile's item
+                if (PAIR) {
+                    if (!(PROF && (p.dbg & 1))) issue_conv3_tile_pair(ring_addr + s * SLOT, uw3_addr, tmem_base + s * 64u);
+                    umma_commit_pair_elect(&tfull[set_bar]);
+                    umma_commit_pair_elect(&empty[s]);
+                } else {
+                    if (!(PROF && (p.dbg & 1))) issue_conv3_tile(ring_addr + s * SLOT, uw3_addr, tmem_base + s * 64u);
+                    umma_commit_elect(&tfull[set_bar]);
+                    umma_commit_elect(&empty[s]);
+                }
             }
             kt += ntiles;
         }
@@ -500,8 +619,14 @@ __global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) {
             if (pt[i]) atomicAdd(reinterpret_cast<unsigned long long *>(&p.prof[(size_t)blockIdx.x * 8 + i]), (unsigned long long)pt[i]);
     tc_fence_before();
     __syncthreads();
-    if (wid == 0) tmem_dealloc(tmem_base, 512);
+    if (PAIR) cluster_sync_all();  // no CTA leaves (or frees TMEM) while its partner can still reach it
+    if (wid == 0) { if (PAIR) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 }
+
+template <bool PROF>
+__global__ void __launch_bounds__(NT, 1) cnn_k9_kernel(const K9Params p) { k9_body<PROF, false>(p); }
+template <bool PROF>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) cnn_k9_pair_kernel(const K9Params p) { k9_body<PROF, true>(p); }
 
 // ---- forward: dense head kernel -----------------------------------------------------------------------------
 // One [32][128] feature tile per step: Dense(H,relu) -> Dense(H,relu) -> Dense(1) -> nan_to_num -> ensemble accumulate
@@ -631,8 +756,20 @@ int launch_cnn_k9(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out,
     p.tab_ovf = m->d_k9_ovf;
     p.overflow_flag = ws->flag;
     const size_t smem = carve(p).total + 1024;
-    auto kernel = prof ? cnn_k9_kernel<true> : cnn_k9_kernel<false>;
+    // CTA pairs (cta_group::2) by default; FLEXS_K9_PAIR=0 keeps the single-CTA kernel
+    static const bool pair = !(std::getenv("FLEXS_K9_PAIR") && std::getenv("FLEXS_K9_PAIR")[0] == '0');
+    auto kernel = pair ? (prof ? cnn_k9_pair_kernel<true> : cnn_k9_pair_kernel<false>)
+                       : (prof ? cnn_k9_kernel<true> : cnn_k9_kernel<false>);
     FX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int max_units = m->sm_count;
+    if (pair) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * (unsigned)(m->sm_count / 2)); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem;
+        int ncl = 0;
+        FX_CUDA(cudaOccupancyMaxActiveClusters(&ncl, kernel, &cfg));
+        FX_REQUIRE(ncl > 0, "no room for a CTA pair of the table kernel");
+        max_units = std::min(ncl, m->sm_count / 2);
+    }
     FX_CUDA(cudaFuncSetAttribute(cnn_k9_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM));
     FX_CUDA(cudaMemsetAsync(ws->flag, 0, sizeof(int), s));
     for (int64_t g0 = 0; g0 < n_groups; g0 += chunk_groups) {
@@ -640,7 +777,9 @@ int launch_cnn_k9(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out,
         p.idx = d_idx + first * m->L;
         p.n = cnt;
         p.n_groups = (cnt + GS - 1) / GS;
-        const int grid = (int)std::min<int64_t>(p.n_groups, m->sm_count);
+        const int dgrid = (int)std::min<int64_t>(p.n_groups, m->sm_count);
+        const int grid = pair ? 2 * (int)std::min<int64_t>((p.n_groups + 1) / 2, max_units)
+                              : (int)std::min<int64_t>(p.n_groups, max_units);
         for (int mem = 0; mem < m->M; ++mem) {
             p.weights = m->d_weights + (int64_t)mem * m->member_floats;
             p.uw = reinterpret_cast<const unsigned char *>(m->d_umma2_w) + (size_t)mem * UW_MEMBER_BYTES;
@@ -653,7 +792,7 @@ int launch_cnn_k9(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out,
             kernel<<<grid, NT, smem, s>>>(p);
             FX_CUDA(cudaGetLastError());
             DenseParams dp{p.feat, d_out + first, p.uw, ws->flag, cnt, p.n_groups, mem, m->M};
-            cnn_k9_dense_kernel<<<grid, DNT, D_SMEM, s>>>(dp);
+            cnn_k9_dense_kernel<<<dgrid, DNT, D_SMEM, s>>>(dp);
             FX_CUDA(cudaGetLastError());
             m->launches += 2;
             if (prof) {

@@ -37,7 +37,7 @@ for r in rows[2:]:
     st = {h: float(d[h]) for h in hdr if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio") and d[h]}
     for h, v in sorted(st.items(), key=lambda kv: -kv[1])[:8]:
         out.append(f"    {h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', ''):28s} {v:6.2f}")
-    if k9_seqs and "cnn_k9_kernel" in d["Kernel Name"]:
+    if k9_seqs and ("cnn_k9_kernel" in d["Kernel Name"] or "cnn_k9_pair_kernel" in d["Kernel Name"]):
         def num(key):
             v = float(d[key].replace(",", ""))
             u = units[hdr.index(key)].lower()
