@@ -110,6 +110,77 @@ __device__ __forceinline__ void issue_taps(uint32_t a_win_addr, uint32_t w_addr,
     }
 }
 
+// ---- CTA-pair variant (cta_group::2; see cnn_k9.cu and tools/pair_mma_test.cu): two CTAs of a cluster run the same
+// tile of their own items as ONE M = 256 MMA.  CTA rank r supplies filters [r N/2, (r+1) N/2) of the B operand from
+// the same shared-memory offset of its own SM, so each SM fetches half of the weight planes per MMA.  Planes per CTA
+// and layer: W64 [tap][chunk][32 rows: this rank's half of hi|lo][16 B], then W32 [tap][chunk][16 rows: half of hi].
+constexpr int PW64_CH = 32 * 16, PW64_TAP = 4 * PW64_CH, PW32_CH = 16 * 16, PW32_TAP = 4 * PW32_CH;
+constexpr uint32_t IDESC_P64 = (1u << 4) | ((64u >> 3) << 17) | ((256u >> 4) << 24);
+constexpr uint32_t IDESC_P32 = (1u << 4) | ((32u >> 3) << 17) | ((256u >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t leader_addr(const void *local) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(fxd::smem_u32(local)));
+    return r;
+}
+// arrival on the leader CTA's barrier.  CTA-scope release (the default): what it publishes is this SM's own shared
+// memory / TMEM state, complete before the arrive issues and consumed by this SM's half of the pair MMA; a
+// cluster-scope release costs a MEMBAR.ALL.GPU per arrival (measured on cnn_k9: +60 % kernel time).
+template <bool PAIR>
+__device__ __forceinline__ void arrive_at_issuer(uint64_t *local_bar, uint32_t leader_bar) {
+    if (PAIR) asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(leader_bar) : "memory");
+    else mbar_arrive(local_bar);
+}
+__device__ __forceinline__ void umma_f16_pair_elect(uint32_t d_tmem, uint32_t a_lo32, uint32_t a_hi32, uint32_t b_lo32,
+                                                    uint32_t b_hi32, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "elect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo32), "r"(a_hi32), "r"(b_lo32), "r"(b_hi32), "r"(idesc), "r"(accumulate) : "memory");
+}
+// commit whose arrival lands on the barrier at this offset in BOTH CTAs of the pair
+template <bool PAIR>
+__device__ __forceinline__ void commit_to(uint64_t *bar) {
+    if (PAIR) {
+        asm volatile(
+            "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+            "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+            ::"r"(fxd::smem_u32(bar)), "h"((uint16_t)3) : "memory");
+    } else {
+        umma_commit_elect(bar);
+    }
+}
+// pair version of issue_taps: w_addr = this layer's W64 planes, w32_addr = its W32 planes
+template <int J0, int J1>
+__device__ __forceinline__ void issue_taps_pair(uint32_t a_win_addr, uint32_t w_addr, uint32_t w32_addr, uint32_t d_tmem) {
+    const uint32_t a0 = __reduce_or_sync(0xffffffffu, desc_lo(a_win_addr, 16));
+    const uint32_t b64 = __reduce_or_sync(0xffffffffu, desc_lo(w_addr, PW64_CH));
+    const uint32_t b32 = __reduce_or_sync(0xffffffffu, desc_lo(w32_addr, PW32_CH));
+    d_tmem = __reduce_or_sync(0xffffffffu, d_tmem);
+#pragma unroll
+    for (int j = J0; j < J1; ++j) {
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) {
+            const uint32_t a_hi = a0 + (((uint32_t)j * 1024u + (uint32_t)kp * 32u) >> 4);
+            const uint32_t a_lo = a_hi + (64u >> 4);
+            const uint32_t bd64 = b64 + (((uint32_t)j * PW64_TAP + (uint32_t)(2 * kp) * PW64_CH) >> 4);
+            const uint32_t bd32 = b32 + (((uint32_t)j * PW32_TAP + (uint32_t)(2 * kp) * PW32_CH) >> 4);
+            umma_f16_pair_elect(d_tmem, a_hi, A_DESC_HI, bd64, DESC_HI, IDESC_P64, (j | kp) ? 1u : 0u);
+            umma_f16_pair_elect(d_tmem, a_lo, A_DESC_HI, bd32, DESC_HI, IDESC_P32, 1u);
+        }
+    }
+}
+
 __device__ __forceinline__ void issue_idx_load(const A20Params &p, uint8_t *dst, uint64_t *bar, int64_t item) {
     const int64_t first = item * 8;
     const int64_t cnt = min((int64_t)8, p.n - first);
@@ -125,8 +196,8 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4 &v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-template <bool PROF>
-__global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
+template <bool PROF, bool PAIR>
+__device__ __forceinline__ void a20_body(const A20Params &p) {
     auto now = [] { return PROF ? clock64() : 0ll; };  // phase timers exist only in the FLEXS_UMMA_PROF=1 instantiation
     long long pt[4] = {0, 0, 0, 0};
     const long long t_begin = now();
@@ -143,25 +214,53 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
 
     if (tid == 0) {
         fxd::mbar_init(&bar[B_IDX], 1); fxd::mbar_init(&bar[B_IDX + 1], 1);
+        // pair: the barriers the issuers wait on live in the leader CTA and collect the warps of both CTAs
+        const uint32_t nw = PAIR ? 8 : 4;
         for (int i = 0; i < 2; ++i) {
-            fxd::mbar_init(&bar[B_A2F + i], 1); fxd::mbar_init(&bar[B_A2E + i], 4);
-            fxd::mbar_init(&bar[B_A3F + i], 1); fxd::mbar_init(&bar[B_A3E + i], 4);
+            fxd::mbar_init(&bar[B_A2F + i], 1); fxd::mbar_init(&bar[B_A2E + i], nw);
+            fxd::mbar_init(&bar[B_A3F + i], 1); fxd::mbar_init(&bar[B_A3E + i], nw);
         }
         for (int i = 0; i < 3; ++i) {
-            fxd::mbar_init(&bar[B_H1F + i], 4); fxd::mbar_init(&bar[B_H1E + i], 1);
-            fxd::mbar_init(&bar[B_H2F + i], 4); fxd::mbar_init(&bar[B_H2E + i], 1);
+            fxd::mbar_init(&bar[B_H1F + i], nw); fxd::mbar_init(&bar[B_H1E + i], 1);
+            fxd::mbar_init(&bar[B_H2F + i], nw); fxd::mbar_init(&bar[B_H2E + i], 1);
         }
         fxd::fence_mbar_init();
     }
-    if (wid == 0) tmem_alloc(tmem_addr_s, 256);  // conv2 accumulators at columns 0 / 64, conv3 at 128 / 192
+    // conv2 accumulators at columns 0 / 64, conv3 at 128 / 192
+    if (wid == 0) {
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(fxd::smem_u32(tmem_addr_s)), "r"(256u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            tmem_alloc(tmem_addr_s, 256);
+        }
+    }
+    // Work units.  Single CTA: unit = CTA, one item per step.  Pair: unit = cluster; its CTAs take the items 2u, 2u + 1
+    // of a step and run them tile by tile in lockstep.  An item past the end (odd item count) is all padding.
+    const uint32_t rank = PAIR ? cluster_rank() : 0u;
+    const int64_t unit0 = PAIR ? (int64_t)(blockIdx.x >> 1) * 2 : (int64_t)blockIdx.x;
+    const int64_t stride = PAIR ? (int64_t)(gridDim.x >> 1) * 2 : (int64_t)gridDim.x;
+    const uint32_t lbar = PAIR ? leader_addr(bar) : 0u;  // the leader's barrier array
     const float *scal = reinterpret_cast<const float *>(p.uw + A20_OFF_SCAL);
     const float inv2s = __ldg(scal), inv3 = __ldg(scal + 1);
     for (int i = tid; i < F; i += NT) {
         b2s[i] = __ldg(p.weights + p.o.b2 + i) * ASCALE;
         b3[i] = __ldg(p.weights + p.o.b3 + i);
     }
-    for (int i = tid; i < (K + KC3) * UWTAP / 16; i += NT)
-        reinterpret_cast<uint4 *>(smem_raw + S_W2)[i] = __ldg(reinterpret_cast<const uint4 *>(p.uw + A20_OFF_UW2) + i);
+    if (!PAIR) {
+        for (int i = tid; i < (K + KC3) * UWTAP / 16; i += NT)
+            reinterpret_cast<uint4 *>(smem_raw + S_W2)[i] = __ldg(reinterpret_cast<const uint4 *>(p.uw + A20_OFF_UW2) + i);
+    } else {
+        // this rank's column halves: rows 32 r .. 32 r + 31 of every [hi|lo] block, rows 16 r .. 16 r + 15 of its hi part
+        for (int layer = 0; layer < 2; ++layer) {
+            const int taps = layer ? KC3 : K;
+            const uint4 *src = reinterpret_cast<const uint4 *>(p.uw + (layer ? A20_OFF_UW3 : A20_OFF_UW2));
+            uint4 *d64 = reinterpret_cast<uint4 *>(smem_raw + (layer ? S_W3 : S_W2));
+            uint4 *d32 = d64 + taps * PW64_TAP / 16;
+            for (int i = tid; i < taps * 4 * 32; i += NT) d64[i] = __ldg(src + (i >> 5) * 64 + 32 * (int)rank + (i & 31));
+            for (int i = tid; i < taps * 4 * 16; i += NT) d32[i] = __ldg(src + (i >> 4) * 64 + 16 * (int)rank + (i & 15));
+        }
+    }
     const uint32_t r1c = (uint32_t)p.r1c;
     const int S_R2 = s_r2(p.r1c), S_STAGE = s_stage(p.r1c), S_IDX = s_idx(p.r1c);
     for (int i = tid; i < (S_STAGE - S_R1) / 16; i += NT)
@@ -169,11 +268,11 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();  // both CTAs' barriers exist before anyone arrives on the leader's
     tc_fence_after();
     const uint32_t tmem_base = *tmem_addr_s;
     const uint32_t r1_addr = fxd::smem_u32(smem_raw + S_R1), r2_addr = fxd::smem_u32(smem_raw + S_R2);
     const uint32_t w2_addr = fxd::smem_u32(smem_raw + S_W2), w3_addr = fxd::smem_u32(smem_raw + S_W3);
-    const int64_t stride = gridDim.x;
     float xmax = 0.f;  // largest activation written as fp16 (range guard)
 
     if (wid < W_E2) {
@@ -191,9 +290,11 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
         const uint32_t row_off = (uint32_t)(b * 128), hi_off = (uint32_t)((cc ^ b) << 4), lo_off = (uint32_t)(((4 + cc) ^ b) << 4);
         const bool odd = (b & 1) != 0;
         const uint32_t first_off = odd ? lo_off : hi_off, second_off = odd ? hi_off : lo_off;
-        if (tid == 0 && (int64_t)blockIdx.x < p.n_items) issue_idx_load(p, smem_raw + S_IDX, &bar[B_IDX], blockIdx.x);
+        if (tid == 0 && unit0 + rank < p.n_items) issue_idx_load(p, smem_raw + S_IDX, &bar[B_IDX], unit0 + rank);
         uint32_t g1 = 0, itc = 0;
-        for (int64_t item = blockIdx.x; item < p.n_items; item += stride, ++itc) {
+        for (int64_t ib = unit0; ib < p.n_items; ib += stride, ++itc) {
+            const int64_t item = ib + rank;
+            const bool real = item < p.n_items;  // (a CTA without an item is in its last step)
             // every producer is done with the previous item: its residue buffer is free.  Two buffers: the NEXT item's
             // residues are fetched now; one buffer (long sequences, where the third h1 chunk is worth more): this item's.
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -201,10 +302,10 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
             if (p.idx_nbuf == 2) {
                 if (tid == 0 && item + stride < p.n_items)
                     issue_idx_load(p, smem_raw + S_IDX + (ibuf ^ 1u) * p.idx_slot, &bar[B_IDX + (ibuf ^ 1u)], item + stride);
-            } else if (tid == 0 && itc > 0) {
+            } else if (tid == 0 && itc > 0 && real) {
                 issue_idx_load(p, smem_raw + S_IDX, &bar[B_IDX], item);
             }
-            fxd::mbar_wait(&bar[B_IDX + ibuf], (p.idx_nbuf == 2 ? (itc >> 1) : itc) & 1);
+            if (real) fxd::mbar_wait(&bar[B_IDX + ibuf], (p.idx_nbuf == 2 ? (itc >> 1) : itc) & 1);
             const int nvalid = (int)min((int64_t)8, p.n - item * 8);
             const uint8_t *sidx = smem_raw + S_IDX + ibuf * p.idx_slot +
                                   ((reinterpret_cast<uintptr_t>(p.idx) + (uintptr_t)(item * 8 * L)) & 15) + (b < nvalid ? b : 0) * L;
@@ -253,7 +354,7 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
                 }
                 fence_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bar[B_H1F + slot]);
+                if (lane == 0) arrive_at_issuer<PAIR>(&bar[B_H1F + slot], lbar + (B_H1F + slot) * 8u);
             }
         }
     } else if (wid < W_E3) {
@@ -262,7 +363,8 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
         const int lq = wid & 3, c = 4 * lq + (lane >> 3), b = lane & 7;
         const uint32_t tlane = tmem_base + ((uint32_t)(lq * 32) << 16);
         uint32_t g2 = 0, a2 = 0;
-        for (int64_t item = blockIdx.x; item < p.n_items; item += stride) {
+        for (int64_t ib = unit0; ib < p.n_items; ib += stride) {
+            const int64_t item = ib + rank;
             const int nvalid = (int)min((int64_t)8, p.n - item * 8);
             for (int qc = 0; qc < p.nc2; ++qc, ++g2) {
                 const uint32_t slot = g2 % 3u;
@@ -284,7 +386,7 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
                         if (hf == 1) {
                             tc_fence_before();
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(&bar[B_A2E + a]);  // the accumulator is in registers
+                            if (lane == 0) arrive_at_issuer<PAIR>(&bar[B_A2E + a], lbar + (B_A2E + a) * 8u);  // the accumulator is in registers
                         }
 #pragma unroll
                         for (int h8 = 0; h8 < 2; ++h8) {
@@ -327,7 +429,7 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
                 }
                 fence_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bar[B_H2F + slot]);
+                if (lane == 0) arrive_at_issuer<PAIR>(&bar[B_H2F + slot], lbar + (B_H2F + slot) * 8u);
             }
         }
     } else if (wid < W_I2) {
@@ -342,7 +444,8 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
         float mx[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) mx[j] = -INFINITY;
-        for (int64_t item = blockIdx.x; item < p.n_items; item += stride) {
+        for (int64_t ib = unit0; ib < p.n_items; ib += stride) {
+            const int64_t item = ib + rank;
             const int nvalid = (int)min((int64_t)8, p.n - item * 8);
             for (int q = 0; q < p.nt3; ++q, ++t3) {
                 const uint32_t a = t3 & 1u;
@@ -360,7 +463,7 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
                     if (hf == 1) {
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&bar[B_A3E + a]);
+                        if (lane == 0) arrive_at_issuer<PAIR>(&bar[B_A3E + a], lbar + (B_A3E + a) * 8u);
                     }
                     if (valid) {
 #pragma unroll
@@ -414,8 +517,10 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
         }
     } else if (wid == W_I2) {
         // =========================== conv2 MMA issue ===========================
+        // (pair: only the leader issues; its MMAs drive both SMs' tensor cores and its commits arrive in both CTAs)
+        const uint32_t w2b_addr = w2_addr + K * PW64_TAP;
         uint32_t g1 = 0, a2 = 0;
-        for (int64_t item = blockIdx.x; item < p.n_items; item += stride) {
+        for (int64_t ib = unit0; ib < p.n_items && rank == 0; ib += stride) {
             for (int qc = 0; qc < p.nlive2; ++qc, ++g1, ++a2) {
                 const uint32_t use1 = g1 / r1c, s0 = g1 - use1 * r1c, a = a2 & 1u;
                 const uint32_t use1n = (g1 + 1) / r1c, s1 = (g1 + 1) - use1n * r1c;
@@ -427,19 +532,21 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
                 const long long w2 = now();
                 pt[0] += w1 - w0; pt[1] += w2 - w1;
                 tc_fence_after();
-                issue_taps<0, K>(r1_addr + s0 * 16u * 1024u, w2_addr, tmem_base + a * 64u);
-                umma_commit_elect(&bar[B_A2F + a]);
-                umma_commit_elect(&bar[B_H1E + s0]);
+                if (PAIR) issue_taps_pair<0, K>(r1_addr + s0 * 16u * 1024u, w2_addr, w2b_addr, tmem_base + a * 64u);
+                else issue_taps<0, K>(r1_addr + s0 * 16u * 1024u, w2_addr, tmem_base + a * 64u);
+                commit_to<PAIR>(&bar[B_A2F + a]);
+                commit_to<PAIR>(&bar[B_H1E + s0]);
                 pt[2] += now() - w2;
             }
             // the item's last h1 chunk is only ever the 4-group tail of the last window: release it as well
-            umma_commit_elect(&bar[B_H1E + g1 % r1c]);
+            commit_to<PAIR>(&bar[B_H1E + g1 % r1c]);
             ++g1;
         }
     } else {
         // =========================== conv3 MMA issue ===========================
+        const uint32_t w3b_addr = w3_addr + KC3 * PW64_TAP;
         uint32_t g2 = 0, t3 = 0;
-        for (int64_t item = blockIdx.x; item < p.n_items; item += stride) {
+        for (int64_t ib = unit0; ib < p.n_items && rank == 0; ib += stride) {
             for (int q = 0; q < p.nt3; ++q, ++t3) {
                 const uint32_t G = g2 + (uint32_t)q, s0 = G % 3u, a = t3 & 1u;
                 const long long w0 = now();
@@ -450,20 +557,22 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
                 const long long w2 = now();
                 tc_fence_after();
                 const uint32_t win = r2_addr + s0 * 16u * 1024u, d = tmem_base + 128u + a * 64u;
-                issue_taps<0, KC3 - 2>(win, w3_addr, d);
+                if (PAIR) issue_taps_pair<0, KC3 - 2>(win, w3_addr, w3b_addr, d);
+                else issue_taps<0, KC3 - 2>(win, w3_addr, d);
                 // taps 17 and 18 reach into the third chunk of the window (its first two groups)
                 const long long w3 = now();
                 fxd::mbar_wait_warp(&bar[B_H2F + (G + 2) % 3u], ((G + 2) / 3u) & 1);
                 const long long w4 = now();
                 tc_fence_after();
-                issue_taps<KC3 - 2, KC3>(win, w3_addr, d);
-                umma_commit_elect(&bar[B_A3F + a]);
-                umma_commit_elect(&bar[B_H2E + s0]);
+                if (PAIR) issue_taps_pair<KC3 - 2, KC3>(win, w3_addr, w3b_addr, d);
+                else issue_taps<KC3 - 2, KC3>(win, w3_addr, d);
+                commit_to<PAIR>(&bar[B_A3F + a]);
+                commit_to<PAIR>(&bar[B_H2E + s0]);
                 pt[0] += w1 - w0; pt[1] += w2 - w1; pt[2] += w4 - w3; pt[3] += (w3 - w2) + (now() - w4);
             }
             // the two trailing chunks of the item were never the first chunk of a window: release them here
-            umma_commit_elect(&bar[B_H2E + (g2 + (uint32_t)p.nt3) % 3u]);
-            umma_commit_elect(&bar[B_H2E + (g2 + (uint32_t)p.nt3 + 1) % 3u]);
+            commit_to<PAIR>(&bar[B_H2E + (g2 + (uint32_t)p.nt3) % 3u]);
+            commit_to<PAIR>(&bar[B_H2E + (g2 + (uint32_t)p.nt3 + 1) % 3u]);
             g2 += (uint32_t)p.nc2;
         }
     }
@@ -476,8 +585,17 @@ __global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) {
     }
     tc_fence_before();
     __syncthreads();
-    if (wid == 0) tmem_dealloc(tmem_base, 256);
+    if (PAIR) cluster_sync_all();  // no CTA leaves (or frees TMEM) while its partner can still reach it
+    if (wid == 0) {
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+        else tmem_dealloc(tmem_base, 256);
+    }
 }
+
+template <bool PROF>
+__global__ void __launch_bounds__(NT, 1) cnn_a20_kernel(const A20Params p) { a20_body<PROF, false>(p); }
+template <bool PROF>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) cnn_a20_pair_kernel(const A20Params p) { a20_body<PROF, true>(p); }
 
 static bool plan(const flexs_model *m, A20Params &p) {
     p.o = fx::cnn_offsets(m);
@@ -573,15 +691,28 @@ int launch_cnn_a20(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out
     p.overflow_flag = ws->flag;
     const size_t smem = (size_t)s_idx(p.r1c) + p.idx_nbuf * p.idx_slot + 1024;
     static const bool prof = std::getenv("FLEXS_UMMA_PROF") && std::getenv("FLEXS_UMMA_PROF")[0] == '1';
-    auto kernel = prof ? cnn_a20_kernel<true> : cnn_a20_kernel<false>;
+    // CTA pairs (cta_group::2) by default; FLEXS_A20_PAIR=0 keeps the single-CTA kernel
+    static const bool pair = !(std::getenv("FLEXS_A20_PAIR") && std::getenv("FLEXS_A20_PAIR")[0] == '0');
+    auto kernel = pair ? (prof ? cnn_a20_pair_kernel<true> : cnn_a20_pair_kernel<false>)
+                       : (prof ? cnn_a20_kernel<true> : cnn_a20_kernel<false>);
     FX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int max_units = m->sm_count;
+    if (pair) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * (unsigned)(m->sm_count / 2)); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem;
+        int ncl = 0;
+        FX_CUDA(cudaOccupancyMaxActiveClusters(&ncl, kernel, &cfg));
+        FX_REQUIRE(ncl > 0, "no room for a CTA pair of the A = 20 kernel");
+        max_units = std::min(ncl, m->sm_count / 2);
+    }
     FX_CUDA(cudaMemsetAsync(ws->flag, 0, sizeof(int), s));
     for (int64_t t0 = 0; t0 < n_tiles; t0 += chunk_tiles) {
         const int64_t first = t0 * GS, cnt = std::min(n - first, chunk_tiles * GS);
         p.idx = d_idx + first * m->L;
         p.n = cnt;
         p.n_items = (cnt + 7) / 8;
-        const int grid = (int)std::min<int64_t>(p.n_items, m->sm_count);
+        const int grid = pair ? 2 * (int)std::min<int64_t>((p.n_items + 1) / 2, max_units)
+                              : (int)std::min<int64_t>(p.n_items, max_units);
         for (int mem = 0; mem < m->M; ++mem) {
             p.weights = m->d_weights + (int64_t)mem * m->member_floats;
             p.uw = reinterpret_cast<const unsigned char *>(m->d_a20_w) + (size_t)mem * A20_MEMBER_BYTES;
