@@ -630,47 +630,192 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) cnn_k9_pair_k
 
 // ---- forward: dense head kernel -----------------------------------------------------------------------------
 // One [32][128] feature tile per step: Dense(H,relu) -> Dense(H,relu) -> Dense(1) -> nan_to_num -> ensemble accumulate
-// (u2::dense_head_umma: two tcgen05 GEMMs with the fp16 hi/lo split).  Weights are staged once per CTA; the next tile
-// arrives by bulk async copy while this one is computed.
-constexpr int DNT = 288, DMMAW = 8;
-constexpr int D_OFF_MBAR = 0, D_OFF_TM = 64, D_OFF_FT = 1024, D_OFF_SCR = D_OFF_FT + 2 * F * GS * 4;
-constexpr int D_SMEM = D_OFF_SCR + DS_TOTAL + 1024;
-static_assert(D_OFF_SCR % 1024 == 0, "dense scratch must be 1024-byte aligned");
+// (cnn.py:49-52, keras_model.py:77-79, ensemble.py:54-59) as two tcgen05 GEMMs with the fp16 hi/lo split, weights
+// staged once per CTA.  The five stages of a tile are five warp roles that meet only through mbarriers, so two tiles
+// are in flight and the tensor pipe runs GEMM 2 of tile i while the epilogue warps turn tile i + 1 into its operand
+// (the first version ran the stages one after the other between CTA barriers: 5900 cycles per tile, 1600 of them MMA):
+//   0-3    features (global, coalesced; next tile prefetched in registers) -> fp16 hi/lo planes X1[i & 1]
+//   16     GEMM 1: X1 x B1 -> TMEM columns 0..223
+//   4-11   epilogue 1: bias, ReLU, split -> planes X2[i & 1]
+//   17     GEMM 2: X2 x B2 -> TMEM columns 256..479
+//   12-15  epilogue 2: bias, ReLU, dot with the output weights, nan_to_num, ensemble accumulate -> scores
+constexpr int DNT = 576, DW_E1 = 4, DW_E2 = 12, DW_G1 = 16, DW_G2 = 17;
+constexpr int D_OFF_MBAR = 0, D_OFF_TM = 128, D_OFF_DV = 256;
+constexpr int D_OFF_B1 = 2048, D_OFF_B2 = D_OFF_B1 + 4 * DBK, D_OFF_X1 = D_OFF_B2 + 14 * DBK;
+constexpr int D_OFF_X2 = D_OFF_X1 + 2 * 8 * DPLANE, D_SMEM = D_OFF_X2 + 2 * 28 * DPLANE + 1024;
+static_assert(D_OFF_DV + DV_FLOATS * 4 <= D_OFF_B1 && D_OFF_X1 % 1024 == 0, "dense kernel shared-memory map");
+// mbarriers
+constexpr int DB_X1F = 0, DB_X1E = 2, DB_A1F = 4, DB_A1E = 5, DB_X2F = 6, DB_X2E = 8, DB_A2F = 10, DB_A2E = 11;
 
 __global__ void __launch_bounds__(DNT, 1) cnn_k9_dense_kernel(const DenseParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + D_OFF_MBAR);  // [0], [1]: feature tiles, [2]: dense MMAs
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + D_OFF_MBAR);
     uint32_t *tmem_addr_s = reinterpret_cast<uint32_t *>(smem_raw + D_OFF_TM);
-    float *ft = reinterpret_cast<float *>(smem_raw + D_OFF_FT);
-    unsigned char *scratch = smem_raw + D_OFF_SCR;
-    const int tid = threadIdx.x, wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    float *dv = reinterpret_cast<float *>(smem_raw + D_OFF_DV);  // bd1 * ASCALE | bd2 | wd3 | inv_d1s, inv_d2, bd3
+    unsigned char *db1 = smem_raw + D_OFF_B1, *db2 = smem_raw + D_OFF_B2;
+    unsigned char *dx1 = smem_raw + D_OFF_X1, *dx2 = smem_raw + D_OFF_X2;
+    const int tid = threadIdx.x, lane = tid & 31, wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
     if (tid == 0) {
-        fxd::mbar_init(&mbar[0], 1); fxd::mbar_init(&mbar[1], 1); fxd::mbar_init(&mbar[2], 1);
+        for (int b = 0; b < 2; ++b) {
+            fxd::mbar_init(&bar[DB_X1F + b], 4); fxd::mbar_init(&bar[DB_X1E + b], 1);
+            fxd::mbar_init(&bar[DB_X2F + b], 8); fxd::mbar_init(&bar[DB_X2E + b], 1);
+        }
+        fxd::mbar_init(&bar[DB_A1F], 1); fxd::mbar_init(&bar[DB_A1E], 8);
+        fxd::mbar_init(&bar[DB_A2F], 1); fxd::mbar_init(&bar[DB_A2E], 4);
         fxd::fence_mbar_init();
     }
     if (wid == 0) tmem_alloc(tmem_addr_s, 512);
-    dense_stage_weights<DNT>(scratch, p.uw);
+    {
+        const float *gdv = reinterpret_cast<const float *>(p.uw + OFF_DV);
+        for (int i = tid; i < DV_FLOATS; i += DNT) dv[i] = __ldg(gdv + i);
+        for (int i = tid; i < 4 * DBK / 16; i += DNT)
+            reinterpret_cast<uint4 *>(db1)[i] = __ldg(reinterpret_cast<const uint4 *>(p.uw + OFF_DB1) + i);
+        for (int i = tid; i < 14 * DBK / 16; i += DNT)
+            reinterpret_cast<uint4 *>(db2)[i] = __ldg(reinterpret_cast<const uint4 *>(p.uw + OFF_DB2) + i);
+    }
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_addr_s;
-    auto load_tile = [&](int64_t g, int buf) {
-        fxd::mbar_arrive_expect_tx(&mbar[buf], F * GS * 4);
-        fxd::bulk_g2s(ft + buf * F * GS, p.feat + (size_t)g * F * GS, F * GS * 4, &mbar[buf]);
-    };
-    if (tid == 0 && (int64_t)blockIdx.x < p.n_groups) load_tile(blockIdx.x, 0);
-    uint32_t it = 0, dph = 0;
+    const int64_t g0 = blockIdx.x, gs = gridDim.x;
     float xmax = 0.f;  // largest activation written as fp16 (range guard)
-    for (int64_t g = blockIdx.x; g < p.n_groups; g += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const int64_t first = g * GS;
-        const int s_grp = (int)min((int64_t)GS, p.n - first);
-        // the other buffer's last reader was the previous step, which ended with a CTA barrier
-        if (tid == 0 && g + gridDim.x < p.n_groups) load_tile(g + gridDim.x, buf ^ 1);
-        fxd::mbar_wait(&mbar[buf], (it >> 1) & 1);
-        dense_head_umma<DNT, DMMAW, false>(scratch, ft + buf * F * GS, GS, GS, s_grp, p.uw, tmem_base, &mbar[2], dph, xmax,
-                                           p.mem, p.M, p.out, [first](int sl) { return (long long)(first + sl); });
+
+    if (wid < DW_E1) {
+        // ---- features -> X1 planes: thread = sequence slot, 32 coalesced loads per tile ----
+        const int slot = tid;
+        float cur[F], nxt[F];
+        auto load = [&](int64_t g, float (&v)[F]) {
+            const bool ok = g < p.n_groups && g * GS + slot < p.n;  // slots past the batch hold stale features
+            const float *src = p.feat + (size_t)g * F * GS + slot;
+#pragma unroll
+            for (int f = 0; f < F; ++f) v[f] = ok ? __ldg(src + f * GS) : 0.f;
+        };
+        load(g0, cur);
+        uint32_t i = 0;
+        for (int64_t g = g0; g < p.n_groups; g += gs, ++i) {
+            const uint32_t b = i & 1u;
+            load(g + gs, nxt);
+            if (i >= 2) fxd::mbar_wait(&bar[DB_X1E + b], ((i >> 1) - 1) & 1);  // GEMM 1 of tile i - 2 has read this buffer
+            unsigned char *x1 = dx1 + b * 8 * DPLANE;
+#pragma unroll
+            for (int cchunk = 0; cchunk < 4; ++cchunk) {
+                float x[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) x[q] = cur[cchunk * 8 + q] * ASCALE;
+                uint4 hi4, lo4;
+                split8(x, hi4, lo4, xmax);
+                *reinterpret_cast<uint4 *>(x1 + (size_t)cchunk * DPLANE + slot * 16) = hi4;
+                *reinterpret_cast<uint4 *>(x1 + (size_t)(4 + cchunk) * DPLANE + slot * 16) = lo4;
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar[DB_X1F + b]);
+#pragma unroll
+            for (int f = 0; f < F; ++f) cur[f] = nxt[f];
+        }
+    } else if (wid < DW_E2) {
+        // ---- epilogue 1: accumulator 1 -> bias, ReLU, split -> X2 planes ----
+        const int lq = wid & 3, half = (wid - DW_E1) >> 2, slot = 32 * lq + lane;
+        const uint32_t tl = tmem_base + ((uint32_t)(lq * 32) << 16);
+        const float inv_d1s = dv[3 * DH];
+        uint32_t i = 0;
+        for (int64_t g = g0; g < p.n_groups; g += gs, ++i) {
+            const uint32_t b = i & 1u;
+            fxd::mbar_wait(&bar[DB_A1F], i & 1);
+            if (i >= 2) fxd::mbar_wait(&bar[DB_X2E + b], ((i >> 1) - 1) & 1);  // GEMM 2 of tile i - 2 has read this buffer
+            tc_fence_after();
+            unsigned char *x2 = dx2 + b * 28 * DPLANE;
+#pragma unroll
+            for (int c7 = 0; c7 < 7; ++c7) {
+                const int cchunk = half * 7 + c7;
+                uint32_t va[8], vb[8];
+                tmem_ld8_nowait(tl + (uint32_t)(cchunk * 8), va);
+                tmem_ld8_nowait(tl + (uint32_t)(DH + cchunk * 8), vb);
+                const float4 b0 = *reinterpret_cast<const float4 *>(dv + cchunk * 8);
+                const float4 b1 = *reinterpret_cast<const float4 *>(dv + cchunk * 8 + 4);
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                tmem_ld_wait();
+                if (c7 == 6) {  // the accumulator is in registers: GEMM 1 of the next tile may overwrite it
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar[DB_A1E]);
+                }
+                float x[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    x[q] = fmaxf(fmaf(__uint_as_float(va[q]) + __uint_as_float(vb[q]), inv_d1s, bb[q]), 0.f);
+                uint4 hi4, lo4;
+                split8(x, hi4, lo4, xmax);
+                *reinterpret_cast<uint4 *>(x2 + (size_t)cchunk * DPLANE + slot * 16) = hi4;
+                *reinterpret_cast<uint4 *>(x2 + (size_t)(14 + cchunk) * DPLANE + slot * 16) = lo4;
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar[DB_X2F + b]);
+        }
+    } else if (wid < DW_G1) {
+        // ---- epilogue 2: accumulator 2 -> bias, ReLU, dot with the output weights -> score ----
+        const int lq = wid & 3, slot = 32 * lq + lane;
+        const uint32_t tl = tmem_base + ((uint32_t)(lq * 32) << 16) + 256u;
+        const float inv_d2 = dv[3 * DH + 1], bd3v = dv[3 * DH + 2];
+        uint32_t i = 0;
+        for (int64_t g = g0; g < p.n_groups; g += gs, ++i) {
+            fxd::mbar_wait(&bar[DB_A2F], i & 1);
+            tc_fence_after();
+            float sum = 0.f;
+#pragma unroll 2
+            for (int cchunk = 0; cchunk < 14; ++cchunk) {
+                uint32_t va[8], vb[8];
+                tmem_ld8_nowait(tl + (uint32_t)(cchunk * 8), va);
+                tmem_ld8_nowait(tl + (uint32_t)(DH + cchunk * 8), vb);
+                const float4 b0 = *reinterpret_cast<const float4 *>(dv + DH + cchunk * 8);
+                const float4 b1 = *reinterpret_cast<const float4 *>(dv + DH + cchunk * 8 + 4);
+                const float4 w0 = *reinterpret_cast<const float4 *>(dv + 2 * DH + cchunk * 8);
+                const float4 w1 = *reinterpret_cast<const float4 *>(dv + 2 * DH + cchunk * 8 + 4);
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float d2 = fmaxf(fmaf(__uint_as_float(va[q]) + __uint_as_float(vb[q]), inv_d2, bb[q]), 0.f);
+                    sum = fmaf(d2, ww[q], sum);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar[DB_A2E]);
+            // Dense(1) bias, nan_to_num (keras_model.py:77), ensemble mean (ensemble.py:24)
+            const int64_t seq = g * GS + slot;
+            if (seq < p.n) {
+                const float y = fxd::nan_to_num(sum + bd3v);
+                float tot = (p.mem == 0) ? y : p.out[seq] + y;
+                if (p.M > 1 && p.mem == p.M - 1) tot = tot / (float)p.M;
+                p.out[seq] = tot;
+            }
+        }
+    } else if (wid == DW_G1) {
+        uint32_t i = 0;
+        for (int64_t g = g0; g < p.n_groups; g += gs, ++i) {
+            const uint32_t b = i & 1u;
+            fxd::mbar_wait_warp(&bar[DB_X1F + b], (i >> 1) & 1);
+            if (i >= 1) fxd::mbar_wait_warp(&bar[DB_A1E], (i - 1) & 1);
+            tc_fence_after();
+            issue_dense_layer<2, 4>(fxd::smem_u32(dx1 + b * 8 * DPLANE), fxd::smem_u32(db1), tmem_base);
+            umma_commit_elect(&bar[DB_X1E + b]);
+            umma_commit_elect(&bar[DB_A1F]);
+        }
+    } else {
+        uint32_t i = 0;
+        for (int64_t g = g0; g < p.n_groups; g += gs, ++i) {
+            const uint32_t b = i & 1u;
+            fxd::mbar_wait_warp(&bar[DB_X2F + b], (i >> 1) & 1);
+            if (i >= 1) fxd::mbar_wait_warp(&bar[DB_A2E], (i - 1) & 1);
+            tc_fence_after();
+            issue_dense_layer<7, 14>(fxd::smem_u32(dx2 + b * 28 * DPLANE), fxd::smem_u32(db2), tmem_base + 256u);
+            umma_commit_elect(&bar[DB_X2E + b]);
+            umma_commit_elect(&bar[DB_A2F]);
+        }
     }
     if (xmax > 60000.f) atomicExch(p.overflow_flag, 1);
     tc_fence_before();
