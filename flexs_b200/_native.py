@@ -14,7 +14,8 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
-_LIB_PATH = Path(__file__).resolve().parent / "libflexs_b200.so"
+# FLEXS_B200_LIB: load another build of the same library (A/B timing of kernel changes on one box, tools/)
+_LIB_PATH = Path(os.environ.get("FLEXS_B200_LIB") or Path(__file__).resolve().parent / "libflexs_b200.so")
 _lib: Optional[ctypes.CDLL] = None
 
 OK, EINVAL, ECUDA, EALPHABET = 0, -1, -2, -3

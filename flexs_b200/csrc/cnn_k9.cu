@@ -42,7 +42,7 @@ constexpr int RING = 8;                 // operand slots == TMEM accumulators ==
 constexpr int CM = 16 + K3 - 1;         // 8-row groups per tile (16 positions + k3-1 behind them)
 constexpr int SLOT = CM * 1024;         // rows of 128 B = one table entry: hi ch 0-15 | hi 16-31 | lo 0-15 | lo 16-31,
                                         // K-major SWIZZLE_128B (16-byte chunk j of row r sits at chunk j ^ (r & 7))
-constexpr int GS = DSLOTS, SBP = GS + 4;  // sequences per dense-head batch, padded feature row
+constexpr int GS = DSLOTS;  // sequences per group = per feature tile of the dense head
 
 // table segments (entries of 128 B): interior | o = 0 | o = 1 | o = T-2 | o = T-1
 constexpr int N_MAIN = 1 << 18, N_E7 = 1 << 14, N_E8 = 1 << 16;
@@ -60,7 +60,7 @@ struct K9Params {
     int *overflow_flag;
     int64_t n, n_groups;
     fx::CnnOffsets o;
-    int L, T, nti, idx_slot, nwp;
+    int L, T, nti, idx_slot;
     long long *prof;
     int dbg;  // profiling knobs (FLEXS_UMMA_DBG bitmask, PROF build only): 1 skip the MMAs, 2 skip the gathers, 4 skip the epilogue math
 };
@@ -75,7 +75,7 @@ struct DenseParams {
 };
 
 struct Offs {
-    int mbar, tm, b3, uw3, idx, pw, feat, stage, ring;
+    int mbar, tm, done, b3, uw3, idx, stage, ring;
     size_t total;
 };
 
@@ -90,11 +90,9 @@ __host__ __device__ inline Offs carve(const K9Params &p) {
         off += bytes;
         return (int)r;
     };
-    o.mbar = take(64 * 8, 16); o.tm = take(16, 16); o.b3 = take(F * 4, 16);
+    o.mbar = take(64 * 8, 16); o.tm = take(16, 16); o.done = take(16, 16); o.b3 = take(F * 4, 16);
     o.uw3 = take((size_t)K3 * UWTAP, 128);
-    o.idx = take(p.idx_slot, 16);
-    o.pw = take((size_t)2 * GS * p.nwp * 4, 16);
-    o.feat = take((size_t)F * SBP * 4, 16);
+    o.idx = take((size_t)2 * p.idx_slot, 16);  // residues of two groups: this one and the next
     o.stage = take((size_t)2 * 2 * 4 * 256 * 4, 16);  // epilogue merge buffers: [set][double buffer][4 warps][256 maxima]
     o.ring = take((size_t)RING * SLOT, 1024);
     o.total = off;
@@ -290,7 +288,7 @@ __device__ __forceinline__ void k9_body(const K9Params &p) {
     uint32_t *tmem_addr_s = reinterpret_cast<uint32_t *>(smem_raw + of.tm);
     float *b3 = reinterpret_cast<float *>(smem_raw + of.b3);
     unsigned char *uw3 = smem_raw + of.uw3;
-    float *feat_s = reinterpret_cast<float *>(smem_raw + of.feat);
+    uint32_t *idx_done = reinterpret_cast<uint32_t *>(smem_raw + of.done);  // producer warps finished with residue buffer b
     unsigned char *ring = smem_raw + of.ring;
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -313,7 +311,8 @@ __device__ __forceinline__ void k9_body(const K9Params &p) {
     auto lead_of = [&](int64_t gb) -> int { return (int)min((int64_t)GS, p.n - gb * GS); };
 
     if (tid == 0) {
-        fxd::mbar_init(mbar_idx, 1);
+        fxd::mbar_init(&mbar_idx[0], 1); fxd::mbar_init(&mbar_idx[1], 1);
+        idx_done[0] = 0; idx_done[1] = 0;
         for (int i = 0; i < RING; ++i) {
             // pair: the leader's "operands ready" / "accumulator drained" barriers collect both CTAs' arrivals
             fxd::mbar_init(&full[i], PAIR ? 2 : 1); fxd::mbar_init(&empty[i], 1);
@@ -322,7 +321,6 @@ __device__ __forceinline__ void k9_body(const K9Params &p) {
         fxd::fence_mbar_init();
     }
     if (wid == 0) { if (PAIR) tmem_alloc_pair(tmem_addr_s, 512); else tmem_alloc(tmem_addr_s, 512); }
-    for (int i = tid; i < F * SBP; i += NT) feat_s[i] = 0.f;
     const float inv3 = __ldg(reinterpret_cast<const float *>(p.uw + OFF_SCAL) + 1);
     for (int i = tid; i < F; i += NT) b3[i] = __ldg(p.weights + p.o.b3 + i);
     if (!PAIR) {
@@ -347,10 +345,13 @@ __device__ __forceinline__ void k9_body(const K9Params &p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_addr_s;
     const uint32_t ring_addr = fxd::smem_u32(ring), uw3_addr = fxd::smem_u32(uw3);
-    if (tid == 0 && mine_of(gb0) > 0) issue_idx_load(p, smem_raw + of.idx, mbar_idx, gb0 + rank);
+    if (tid == 0) {
+        if (mine_of(gb0) > 0) issue_idx_load(p, smem_raw + of.idx, &mbar_idx[0], gb0 + rank);
+        if (mine_of(gb0 + gstep) > 0) issue_idx_load(p, smem_raw + of.idx + p.idx_slot, &mbar_idx[1], gb0 + gstep + rank);
+    }
 
     uint32_t kt = 0;  // tiles before the current group: tile k uses slot = accumulator = k & 7
-    uint32_t gi = 0;  // groups before the current one: packed-residue buffer and residue-barrier parity = gi & 1
+    uint32_t gi = 0;  // groups before the current one: residue buffer = gi & 1, its barrier's parity = (gi >> 1) & 1
     long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long t_begin = now();
 
@@ -363,30 +364,18 @@ __device__ __forceinline__ void k9_body(const K9Params &p) {
         const uint32_t dst0 = (uint32_t)(rr * 128 + ((jch ^ rr) << 4));
         const uint32_t dst1 = (uint32_t)((rr + 4) * 128 + ((jch ^ (rr + 4)) << 4));
         const unsigned char *tabj = p.tab + jch * 16;
-        const int nwp = p.nwp;
+        // lane 3 b + w (< 24) packs word q - 1 + w of stream b for the tile: 16 residues, 2 bits each, first residue in the
+        // top bits.  Every warp builds the 24 words of its own tile, so the producer warps never wait for each other.
+        const int wsb = lane / 3, www = lane - 3 * wsb;
         const uint32_t full_mine = PAIR ? leader_addr(&full[wid]) : 0u;
         for (int64_t gb = gb0; gb < p.n_groups; gb += gstep, ++gi) {
             const int64_t first = (gb + rank) * GS;
             const int s_grp = mine_of(gb);
             const uint32_t ntiles = (uint32_t)(((lead_of(gb) + 7) >> 3) * nti);
-            uint32_t *pw = reinterpret_cast<uint32_t *>(smem_raw + of.pw) + (gi & 1) * GS * nwp;
-            if (s_grp > 0) fxd::mbar_wait(mbar_idx, gi & 1);  // (a CTA without a group is in its last step)
-            const uint8_t *sidx = smem_raw + of.idx + ((reinterpret_cast<uintptr_t>(p.idx) + (uintptr_t)(first * L)) & 15);
-            // residues -> 2 bits each, 16 per word, first residue in the top bits; a zero word on either side
-            for (int i = tid; i < s_grp * nwp; i += NPROD * 32) {
-                const int sq = i / nwp, wv = i - sq * nwp - 1;
-                uint32_t word = 0;
-                if (wv >= 0 && wv * 16 < L) {
-                    const uint8_t *src = sidx + sq * L + wv * 16;
-                    const int cnt = min(16, L - wv * 16);
-#pragma unroll
-                    for (int r = 0; r < 16; ++r) word = (word << 2) | (r < cnt ? (uint32_t)(src[r] & 3) : 0u);
-                }
-                pw[i] = word;
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(NPROD * 32) : "memory");
-            // every producer has packed: the staging buffer is free for the next group's residues
-            if (tid == 0 && mine_of(gb + gstep) > 0) issue_idx_load(p, smem_raw + of.idx, mbar_idx, gb + gstep + rank);
+            const uint32_t buf = gi & 1u;
+            if (s_grp > 0) fxd::mbar_wait(&mbar_idx[buf], (gi >> 1) & 1);  // (a CTA without a group is in its last step)
+            const uint32_t sidx = fxd::smem_u32(smem_raw + of.idx) + buf * (uint32_t)p.idx_slot +
+                                  (uint32_t)((reinterpret_cast<uintptr_t>(p.idx) + (uintptr_t)(first * L)) & 15);
             for (uint32_t tl = ((uint32_t)wid - kt) & 7u; tl < ntiles; tl += NPROD) {
                 const uint32_t use = (kt + tl) >> 3;
                 const long long q0 = now();
@@ -400,9 +389,29 @@ __device__ __forceinline__ void k9_body(const K9Params &p) {
                 // residues 16(q-1) .. 16(q+2)-1 of the lane's two streams (word index + 1 in the padded array)
                 const int sl0 = item * 8 + rr, sl1 = sl0 + 4;
                 const bool ok0 = sl0 < s_grp, ok1 = sl1 < s_grp;
-                const uint32_t *ws0 = pw + (ok0 ? sl0 : 0) * nwp + q, *ws1 = pw + (ok1 ? sl1 : 0) * nwp + q;
-                const uint32_t u0 = ws0[0], u1 = ws0[1], u2 = ws0[2];
-                const uint32_t v0 = ws1[0], v1 = ws1[1], v2 = ws1[2];
+                uint32_t word = 0;
+                {
+                    const int sq = item * 8 + wsb, wv = q - 1 + www;
+                    if (lane < 24 && sq < s_grp && wv >= 0 && wv * 16 < L) {
+                        // 16 residue bytes at an arbitrary byte offset: five aligned words, funnel-shifted into four
+                        const uint32_t a = sidx + (uint32_t)(sq * L + wv * 16), sh = (a & 3u) * 8u;
+                        uint32_t w[5];
+#pragma unroll
+                        for (int i = 0; i < 5; ++i)
+                            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w[i]) : "r"((a & ~3u) + 4u * i));
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint32_t x = __funnelshift_r(w[i], w[i + 1], sh) & 0x03030303u;
+                            // residues at bits 0, 8, 16, 24 -> one byte r0 r1 r2 r3 (a multiply gathers them in the top byte)
+                            word = (word << 8) | ((x * 0x40100401u) >> 24);
+                        }
+                        const int cnt = min(16, L - wv * 16);  // the last word of a row: drop the next row's residues
+                        word &= 0xffffffffu << (2 * (16 - cnt));
+                    }
+                }
+                const uint32_t u0 = __shfl_sync(0xffffffffu, word, 3 * rr), u1 = __shfl_sync(0xffffffffu, word, 3 * rr + 1);
+                const uint32_t u2 = __shfl_sync(0xffffffffu, word, 3 * rr + 2), v0 = __shfl_sync(0xffffffffu, word, 3 * rr + 12);
+                const uint32_t v1 = __shfl_sync(0xffffffffu, word, 3 * rr + 13), v2 = __shfl_sync(0xffffffffu, word, 3 * rr + 14);
                 // the window of input row c (h2 position o = 16 q + c - 1) starts at residue o - 2, i.e. 2 (c + 13) bits
                 // into w0:w1:w2 — a compile-time shift
                 auto code_of = [](int c, uint32_t x0, uint32_t x1, uint32_t x2) -> uint32_t {
@@ -449,6 +458,18 @@ __device__ __forceinline__ void k9_body(const K9Params &p) {
             }
             kt += ntiles;
             if (PROF && tid == 0) pt[7] += ntiles;
+            // The last of the eight warps to finish the group hands its residue buffer to the bulk copy of the group after
+            // the next one (nobody waits: the copy has a whole group's time to land).
+            __syncwarp();
+            if (lane == 0) {
+                if (atomicAdd(&idx_done[buf], 1u) == NPROD - 1) {
+                    atomicExch(&idx_done[buf], 0u);
+                    if (mine_of(gb + 2 * gstep) > 0) {
+                        fence_async_smem();  // the warps' reads of the buffer precede the async-proxy write
+                        issue_idx_load(p, smem_raw + of.idx + buf * p.idx_slot, &mbar_idx[buf], gb + 2 * gstep + rank);
+                    }
+                }
+            }
         }
     } else if (wid < MMAW) {
         // =========================== conv3 epilogue: running max per sequence ===========================
@@ -465,7 +486,6 @@ __device__ __forceinline__ void k9_body(const K9Params &p) {
         const int c = 4 * lq + (lane >> 3), b = lane & 7;
         const uint32_t tlane = tmem_base + ((uint32_t)(lq * 32) << 16);
         const bool up8 = (lane & 8) != 0, up16 = (lane & 16) != 0;
-        const int et = tid - NPROD * 32;  // thread index among the 256 epilogue threads
         float *stage_s = reinterpret_cast<float *>(smem_raw + of.stage) + par * 2 * 4 * 256;  // [2 buffers][4 warps][4 fg][8 b][8 f]
         uint64_t *tfull_mine = tfull + 8 * par;
         const uint32_t tempty_lead = PAIR ? leader_addr(&tempty[0]) : 0u;
@@ -479,7 +499,7 @@ __device__ __forceinline__ void k9_body(const K9Params &p) {
             const int s_grp = mine_of(gb);
             const int nitems = (lead_of(gb) + 7) >> 3;  // pair: the peer visits (and frees) every tile of the unit
             const uint32_t ntiles = (uint32_t)(nitems * nti);
-            float *featT = feat_s;
+            float *featT = p.feat + (size_t)g * F * GS;  // [32][128] tile of this group, written 8 sequences at a time
             // one tile: accumulator -> registers -> running maxima
             auto visit = [&](uint32_t k, int q) {
                 const uint32_t acc = k & 7u;
@@ -559,27 +579,14 @@ __device__ __forceinline__ void k9_body(const K9Params &p) {
                     const float2 o2 = *reinterpret_cast<const float2 *>(rd + w4 * 256);
                     t.x = fmaxf(t.x, o2.x); t.y = fmaxf(t.y, o2.y);
                 }
+                // a warp writes 8 rows of 32 bytes (8 sequences of one filter): whole sectors
                 if (sl < s_grp) {
-                    featT[f * SBP + sl] = fmaxf(fmaf(t.x, inv3, b3[f]), 0.f);
-                    featT[(f + 1) * SBP + sl] = fmaxf(fmaf(t.y, inv3, b3[f + 1]), 0.f);
+                    featT[f * GS + sl] = fmaxf(fmaf(t.x, inv3, b3[f]), 0.f);
+                    featT[(f + 1) * GS + sl] = fmaxf(fmaf(t.y, inv3, b3[f + 1]), 0.f);
                 }
                 ++nflush;
             }
             kt += ntiles;
-            // the group's features are complete once all 8 epilogue warps are here: copy the [32][128] tile out
-            // (slots past the end of the batch keep stale values; the dense kernel never reports them)
-            asm volatile("bar.sync 2, %0;" ::"n"(8 * 32) : "memory");
-            if (s_grp > 0) {
-                float4 *dst = reinterpret_cast<float4 *>(p.feat + (size_t)g * F * GS);
-#pragma unroll
-                for (int i = et; i < F * GS / 4; i += 8 * 32) {
-                    const int row = i >> 5, col = (i & 31) * 4;
-                    dst[i] = *reinterpret_cast<const float4 *>(featT + row * SBP + col);
-                }
-            }
-            // the next group's first features are stored after a barrier of only one set: nobody
-            // may still be reading this group's
-            asm volatile("bar.sync 2, %0;" ::"n"(8 * 32) : "memory");
         }
     } else {
         // =========================== MMA issuers ===========================
@@ -829,7 +836,6 @@ static bool plan(const flexs_model *m, K9Params &p) {
     p.T = m->L - m->K + 1;
     p.nti = (p.T + 15) / 16;
     p.idx_slot = (int)align_up((size_t)GS * m->L + 32, 16);
-    p.nwp = (m->L + 15) / 16 + 2;  // packed residues: a zero word, ceil(L/16) words of 16 residues, a zero word
     return (int64_t)carve(p).total + 1024 <= m->max_smem_optin && D_SMEM <= m->max_smem_optin;
 }
 
