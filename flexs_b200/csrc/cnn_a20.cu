@@ -606,12 +606,11 @@ static bool plan(const flexs_model *m, A20Params &p) {
     p.nlive2 = (p.T + 8) / 16 + 1;      // h2 chunks with a position inside the sequence (the others are zero padding)
     p.nc1 = p.nlive2 + 1;               // h1 chunks per item: a conv2 window ends 4 groups into the next chunk
     p.idx_slot = (int)align_up((size_t)8 * m->L + 32, 16);
-    // Two h1 chunks and two residue buffers; one residue buffer for very long sequences.  A third h1 chunk (conv2 a chunk
-    // further ahead) was measured: the conv2 issuer's wait for conv1 drops from 24 % to 10 % of an item, throughput does
-    // not move (gfp237 2.945e7 vs 2.952e7) — the tensor pipe is busy either way (51 cycles per MMA, 81 % of the conv3
-    // issuer's time is spent blocked on it).  FLEXS_A20_R1C=3 selects it for experiments.
-    static const bool three = std::getenv("FLEXS_A20_R1C") && std::getenv("FLEXS_A20_R1C")[0] == '3';
-    const int opts[4][2] = {{three ? 3 : 2, 2}, {three ? 3 : 2, 1}, {2, 2}, {2, 1}};
+    // Three h1 chunks when shared memory allows (conv2 runs a chunk further ahead of conv1), two residue buffers (one for
+    // very long sequences).  With single-CTA MMAs the third chunk bought nothing (the operand fetch of the tensor pipe was
+    // the limit either way); with CTA pairs it is worth +3.4 % on gfp237 and +1.3 % on aav735.  FLEXS_A20_R1C=2 for A/B runs.
+    static const bool two = std::getenv("FLEXS_A20_R1C") && std::getenv("FLEXS_A20_R1C")[0] == '2';
+    const int opts[4][2] = {{two ? 2 : 3, 2}, {two ? 2 : 3, 1}, {2, 2}, {2, 1}};
     for (const auto &o : opts) {
         p.r1c = o[0]; p.idx_nbuf = o[1];
         if ((int64_t)s_idx(p.r1c) + p.idx_nbuf * p.idx_slot + 1024 <= m->max_smem_optin) return true;

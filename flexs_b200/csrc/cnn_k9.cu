@@ -352,7 +352,7 @@ __device__ __forceinline__ void k9_body(const K9Params &p) {
 
     uint32_t kt = 0;  // tiles before the current group: tile k uses slot = accumulator = k & 7
     uint32_t gi = 0;  // groups before the current one: residue buffer = gi & 1, its barrier's parity = (gi >> 1) & 1
-    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long pt[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     const long long t_begin = now();
 
     if (wid < NPROD) {
@@ -567,10 +567,13 @@ __device__ __forceinline__ void k9_body(const K9Params &p) {
             for (int item = par; item < nitems; item += 2) {
                 const uint32_t k0 = kt + (uint32_t)(item * nti);
                 for (int q = 0; q < nti; ++q) visit(k0 + (uint32_t)q, q);
+                const long long f0 = now();
                 float *stg = stage_s + (int)(nflush & 1) * 4 * 256;
                 butterfly_to(stg + lq * 256);
+                const long long f1 = now();
                 if (par == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
                 else asm volatile("bar.sync 4, 128;" ::: "memory");
+                const long long f2 = now();
                 const int pr = lane >> 3, f = 8 * lq + 2 * pr, sl = item * 8 + b;
                 const float *rd = stg + (lq * 8 + b) * 8 + ((2 * pr) ^ (((b >> 2) & 1) << 2));   // the writers' half swap
                 float2 t = *reinterpret_cast<const float2 *>(rd);
@@ -585,6 +588,7 @@ __device__ __forceinline__ void k9_body(const K9Params &p) {
                     featT[(f + 1) * GS + sl] = fmaxf(fmaf(t.y, inv3, b3[f + 1]), 0.f);
                 }
                 ++nflush;
+                if (PROF && tid == 8 * 32) { pt[8] += f1 - f0; pt[9] += f2 - f1; pt[10] += now() - f2; }
             }
             kt += ntiles;
         }
@@ -622,8 +626,8 @@ __device__ __forceinline__ void k9_body(const K9Params &p) {
     if (PROF && tid == 0) pt[0] = now() - t_begin;
     if (blockIdx.x == 0 && tid == 0 && __ldg(p.tab_ovf) != 0) atomicExch(p.overflow_flag, 1);
     if (PROF && p.prof != nullptr && (tid == 0 || tid == 8 * 32 || tid == MMAW * 32))
-        for (int i = 0; i < 8; ++i)
-            if (pt[i]) atomicAdd(reinterpret_cast<unsigned long long *>(&p.prof[(size_t)blockIdx.x * 8 + i]), (unsigned long long)pt[i]);
+        for (int i = 0; i < 12; ++i)
+            if (pt[i]) atomicAdd(reinterpret_cast<unsigned long long *>(&p.prof[(size_t)blockIdx.x * 12 + i]), (unsigned long long)pt[i]);
     tc_fence_before();
     __syncthreads();
     if (PAIR) cluster_sync_all();  // no CTA leaves (or frees TMEM) while its partner can still reach it
@@ -937,8 +941,8 @@ int launch_cnn_k9(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out,
             p.tab = reinterpret_cast<const unsigned char *>(m->d_k9_tab) + (size_t)mem * TAB_BYTES;
             p.prof = nullptr;
             if (prof) {
-                FX_CUDA(cudaMalloc(&p.prof, (size_t)grid * 8 * sizeof(long long)));
-                FX_CUDA(cudaMemset(p.prof, 0, (size_t)grid * 8 * sizeof(long long)));
+                FX_CUDA(cudaMalloc(&p.prof, (size_t)grid * 12 * sizeof(long long)));
+                FX_CUDA(cudaMemset(p.prof, 0, (size_t)grid * 12 * sizeof(long long)));
             }
             kernel<<<grid, NT, smem, s>>>(p);
             FX_CUDA(cudaGetLastError());
@@ -948,17 +952,18 @@ int launch_cnn_k9(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out,
             m->launches += 2;
             if (prof) {
                 FX_CUDA(cudaStreamSynchronize(s));
-                std::vector<long long> h((size_t)grid * 8);
+                std::vector<long long> h((size_t)grid * 12);
                 FX_CUDA(cudaMemcpy(h.data(), p.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
                 cudaFree(p.prof);
-                double a[8] = {0};
-                for (int b = 0; b < grid; ++b) for (int i = 0; i < 8; ++i) a[i] += (double)h[(size_t)b * 8 + i] / grid;
+                double a[12] = {0};
+                for (int b = 0; b < grid; ++b) for (int i = 0; i < 12; ++i) a[i] += (double)h[(size_t)b * 12 + i] / grid;
                 const double nt = a[7] > 0 ? a[7] : 1;
                 fprintf(stderr, "[k9 prof] n=%lld grid=%d tiles/CTA=%.0f | cycles per tile %.0f | producer warp 0 (per own tile = 1/8 "
                                 "of tiles): wait slot %.0f, gather %.0f | epilogue warp 8 (per own tile = 1/2 of tiles): wait MMA %.0f, "
-                                "load+max+flush %.0f | MMA warp 16 (per own tile = 1/2 of tiles): wait operands %.0f, wait accumulator %.0f\n",
+                                "load+max %.0f, per item: butterfly %.0f, set barrier %.0f, merge+store %.0f | MMA warp 16 (per own tile = 1/2 of tiles): "
+                                "wait operands %.0f, wait accumulator %.0f\n",
                         (long long)cnt, grid, a[7], a[0] / nt, a[2] / nt * 8, a[3] / nt * 8, a[4] / nt * 2, a[1] / nt * 2,
-                        a[5] / nt * 2, a[6] / nt * 2);
+                        a[8] / nt * 2 * p.nti, a[9] / nt * 2 * p.nti, a[10] / nt * 2 * p.nti, a[5] / nt * 2, a[6] / nt * 2);
             }
         }
     }
