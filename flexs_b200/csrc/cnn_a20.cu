@@ -690,20 +690,23 @@ int launch_cnn_a20(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out
     p.overflow_flag = ws->flag;
     const size_t smem = (size_t)s_idx(p.r1c) + p.idx_nbuf * p.idx_slot + 1024;
     static const bool prof = std::getenv("FLEXS_UMMA_PROF") && std::getenv("FLEXS_UMMA_PROF")[0] == '1';
-    // CTA pairs (cta_group::2) by default; FLEXS_A20_PAIR=0 keeps the single-CTA kernel
-    static const bool pair = !(std::getenv("FLEXS_A20_PAIR") && std::getenv("FLEXS_A20_PAIR")[0] == '0');
-    auto kernel = pair ? (prof ? cnn_a20_pair_kernel<true> : cnn_a20_pair_kernel<false>)
-                       : (prof ? cnn_a20_kernel<true> : cnn_a20_kernel<false>);
-    FX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int max_units = m->sm_count;
-    if (pair) {
+    // CTA pairs (cta_group::2) by default; FLEXS_A20_PAIR=0, or a device that cannot co-schedule a pair, keeps the
+    // single-CTA kernel
+    static const bool want_pair = !(std::getenv("FLEXS_A20_PAIR") && std::getenv("FLEXS_A20_PAIR")[0] == '0');
+    if (want_pair && m->a20_pair_units < 0) {
+        auto pk = prof ? cnn_a20_pair_kernel<true> : cnn_a20_pair_kernel<false>;
+        FX_CUDA(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * (unsigned)(m->sm_count / 2)); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem;
         int ncl = 0;
-        FX_CUDA(cudaOccupancyMaxActiveClusters(&ncl, kernel, &cfg));
-        FX_REQUIRE(ncl > 0, "no room for a CTA pair of the A = 20 kernel");
-        max_units = std::min(ncl, m->sm_count / 2);
+        if (cudaOccupancyMaxActiveClusters(&ncl, pk, &cfg) != cudaSuccess) { ncl = 0; (void)cudaGetLastError(); }
+        m->a20_pair_units = std::min(ncl, m->sm_count / 2);
     }
+    const bool pair = want_pair && m->a20_pair_units > 0;
+    auto kernel = pair ? (prof ? cnn_a20_pair_kernel<true> : cnn_a20_pair_kernel<false>)
+                       : (prof ? cnn_a20_kernel<true> : cnn_a20_kernel<false>);
+    FX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int max_units = pair ? m->a20_pair_units : m->sm_count;
     FX_CUDA(cudaMemsetAsync(ws->flag, 0, sizeof(int), s));
     for (int64_t t0 = 0; t0 < n_tiles; t0 += chunk_tiles) {
         const int64_t first = t0 * GS, cnt = std::min(n - first, chunk_tiles * GS);

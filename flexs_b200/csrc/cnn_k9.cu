@@ -702,10 +702,19 @@ __global__ void __launch_bounds__(DNT, 1) cnn_k9_dense_kernel(const DenseParams 
 #pragma unroll
             for (int f = 0; f < F; ++f) v[f] = ok ? __ldg(src + f * GS) : 0.f;
         };
+        // The tiles were written by the conv kernel up to a chunk (136 MB > L2) ago: they come from DRAM.  One bulk prefetch
+        // per tile pulls it into L2 three tiles ahead; the register prefetch one tile ahead then only pays the L2 latency
+        // (measured without: the whole pipeline waited ~2000 cycles per tile for this warp's loads).
+        auto prefetch_l2 = [&](int64_t g) {
+            if (tid == 0 && g < p.n_groups)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.feat + (size_t)g * F * GS), "r"(F * GS * 4) : "memory");
+        };
+        prefetch_l2(g0 + gs); prefetch_l2(g0 + 2 * gs);
         load(g0, cur);
         uint32_t i = 0;
         for (int64_t g = g0; g < p.n_groups; g += gs, ++i) {
             const uint32_t b = i & 1u;
+            prefetch_l2(g + 3 * gs);
             load(g + gs, nxt);
             if (i >= 2) fxd::mbar_wait(&bar[DB_X1E + b], ((i >> 1) - 1) & 1);  // GEMM 1 of tile i - 2 has read this buffer
             unsigned char *x1 = dx1 + b * 8 * DPLANE;
@@ -911,20 +920,23 @@ int launch_cnn_k9(flexs_model *m, const uint8_t *d_idx, int64_t n, float *d_out,
     p.tab_ovf = m->d_k9_ovf;
     p.overflow_flag = ws->flag;
     const size_t smem = carve(p).total + 1024;
-    // CTA pairs (cta_group::2) by default; FLEXS_K9_PAIR=0 keeps the single-CTA kernel
-    static const bool pair = !(std::getenv("FLEXS_K9_PAIR") && std::getenv("FLEXS_K9_PAIR")[0] == '0');
-    auto kernel = pair ? (prof ? cnn_k9_pair_kernel<true> : cnn_k9_pair_kernel<false>)
-                       : (prof ? cnn_k9_kernel<true> : cnn_k9_kernel<false>);
-    FX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int max_units = m->sm_count;
-    if (pair) {
+    // CTA pairs (cta_group::2) by default; FLEXS_K9_PAIR=0, or a device that cannot co-schedule a pair, keeps the
+    // single-CTA kernel
+    static const bool want_pair = !(std::getenv("FLEXS_K9_PAIR") && std::getenv("FLEXS_K9_PAIR")[0] == '0');
+    if (want_pair && m->k9_pair_units < 0) {
+        auto pk = prof ? cnn_k9_pair_kernel<true> : cnn_k9_pair_kernel<false>;
+        FX_CUDA(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * (unsigned)(m->sm_count / 2)); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem;
         int ncl = 0;
-        FX_CUDA(cudaOccupancyMaxActiveClusters(&ncl, kernel, &cfg));
-        FX_REQUIRE(ncl > 0, "no room for a CTA pair of the table kernel");
-        max_units = std::min(ncl, m->sm_count / 2);
+        if (cudaOccupancyMaxActiveClusters(&ncl, pk, &cfg) != cudaSuccess) { ncl = 0; (void)cudaGetLastError(); }
+        m->k9_pair_units = std::min(ncl, m->sm_count / 2);
     }
+    const bool pair = want_pair && m->k9_pair_units > 0;
+    auto kernel = pair ? (prof ? cnn_k9_pair_kernel<true> : cnn_k9_pair_kernel<false>)
+                       : (prof ? cnn_k9_kernel<true> : cnn_k9_kernel<false>);
+    FX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int max_units = pair ? m->k9_pair_units : m->sm_count;
     FX_CUDA(cudaFuncSetAttribute(cnn_k9_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM));
     FX_CUDA(cudaMemsetAsync(ws->flag, 0, sizeof(int), s));
     for (int64_t g0 = 0; g0 < n_groups; g0 += chunk_groups) {

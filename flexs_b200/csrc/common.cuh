@@ -66,6 +66,7 @@ struct flexs_model {
     void *d_k9_tab = nullptr;        // cnn_k9.cu: conv1 o conv2 as a table over 9 residues, [M][425984][128 B]
     int *d_k9_ovf = nullptr;         // raised by the table builder when an entry left the fp16 window
     bool k9_ready = false;
+    int k9_pair_units = -1;   // CTA pairs of cnn_k9_pair_kernel the device can hold at once (-1: not asked yet, 0: none)
     float *d_enum_tab = nullptr;     // enum_table.cu: scores of all A^L sequences (A^L <= 2^20)
     bool enum_ready = false;
     // Per-stream scratch of the tcgen05 kernels: the fp16-overflow flag (raised by a kernel, read by the gated FP32
@@ -75,6 +76,7 @@ struct flexs_model {
     std::vector<StreamWs> stream_ws;
     void *d_a20_w = nullptr;         // cnn_a20.cu: operand blob (dense planes, conv planes, conv1 gather tables), all members
     bool a20_ready = false;
+    int a20_pair_units = -1;  // the same for cnn_a20_pair_kernel
     void *d_mlp_w = nullptr;         // mlp_umma.cu: operand blob, all members
     bool mlp_ready = false;
 

@@ -211,6 +211,33 @@ def test_cnn_table_kernel_lengths_and_ragged_groups(L, n):
     m.close()
 
 
+@pytest.mark.parametrize("L,n", [(19, 333), (24, 1), (90, 9), (90, 1001), (237, 17), (238, 130), (300, 47), (735, 25)])
+def test_cnn_protein_kernel_ragged_items_and_pairs(L, n):
+    """cnn_a20.cu runs as CTA pairs (cta_group::2) on items of 8 sequences: batches with an odd number of items (one CTA
+    of the last pair has no item), items with fewer than 8 sequences, a single sequence, the shortest supported
+    sequence; prefixes of a batch score exactly like the batch (no cross-item state), unaligned pointers."""
+    A = 20
+    ws = fo.trained_like_weights(fo.CNNShape(L, A, 32, 100, 5).weight_shapes(), L)
+    idx = np.random.default_rng(L * 7 + n).integers(0, A, size=(n, L), dtype=np.uint8)
+    ref = co.cnn_forward(idx, [ws])
+    m = _native.NativeModel("cnn", seq_len=L, alphabet_size=A, num_filters=32, hidden_size=100, kernel_size=5)
+    m.set_weights(ws)
+    m.set_variant(_native.VARIANT_UMMA)
+    got = _device_forward(m, idx)
+    assert rel_err(got, ref, _floor(ref)) < TOL
+    assert elem_rel_err(got, ref)[0] < TOL
+    for cut in (1, 7, 8, 9, 16, 17, 129):
+        if cut < n:
+            np.testing.assert_array_equal(_device_forward(m, idx[:cut]), got[:cut])
+    buf = torch.zeros(n * L + 64, dtype=torch.uint8, device="cuda")
+    buf[3: 3 + n * L] = torch.from_numpy(idx.reshape(-1)).cuda()
+    out = torch.empty(n, dtype=torch.float32, device="cuda")
+    m.forward_dev(buf.data_ptr() + 3, n, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy(), got)
+    m.close()
+
+
 def test_cnn_table_kernel_selection_rebuild_and_ensemble():
     """AUTO picks the table kernel for large batches only; new weights rebuild the table; an ensemble keeps one
     table per member; residues outside [0, A) cannot index outside the table."""

@@ -43,7 +43,7 @@ for r in rows[2:]:
             u = units[hdr.index(key)].lower()
             return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
         total = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
-        js = {"kernel": "cnn_k9_kernel", "capture": Path(rep).name, "sequences_per_launch": k9_seqs, "dram_bytes_per_launch": total,
+        js = {"kernel": d["Kernel Name"].split("(")[0].split("::")[-1].strip(), "capture": Path(rep).name, "sequences_per_launch": k9_seqs, "dram_bytes_per_launch": total,
               "dram_bytes_read": num("dram__bytes_read.sum"), "dram_bytes_write": num("dram__bytes_write.sum"),
               "table_bytes": 425984 * 128, "algorithmic_bytes_per_launch": 104 * k9_seqs,
               "tensor_pipe_active_pct": float(d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "nan") or "nan"),
