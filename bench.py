@@ -323,7 +323,8 @@ class Screen:
         gen.manual_seed(1234 + rank)
         self.idx = torch.randint(0, A, (batch, L), dtype=torch.uint8, device=device, generator=gen)
         self.k = TOPK
-        self.vs = VirtualScreen(self.surrogate, k=self.k, unique=True)
+        # N > 1: the all-gather + merge of step i run on a side stream under the forward of step i + 1 (VirtualScreen overlap mode)
+        self.vs = VirtualScreen(self.surrogate, k=self.k, unique=True, overlap=world > 1)
         self.fwd_ms = []
         self.status_sum = torch.zeros(1, dtype=torch.int32, device=device)
         self.scores = None
@@ -369,6 +370,7 @@ def timed_steps(screen, steps, warmup, world, device):
     start.record()
     for _ in range(steps):
         screen.step()
+    screen.vs.wait()   # overlap mode: the last steps' all-gather + merge launches are inside the timed region
     end.record()
     torch.cuda.synchronize(device)
     if world > 1:
@@ -640,7 +642,7 @@ def main():
                    "hidden": H_NS, "kernel_size": K_NS, "per_gpu_batch": args.batch, "topk": TOPK,
                    "parallelism": f"candidate-shard x{world}, one all-gather of per-shard top-k" if world > 1 else "single GPU",
                    "screen": "flexs_b200.screen.VirtualScreen(unique=True): forward + one selection launch"
-                             + (" + one all-gather + one merge launch" if world > 1 else ""),
+                             + (" + one all-gather + one merge launch (side stream, overlapping the next step's forward)" if world > 1 else ""),
                    "l2_policy": f"inputs larger than L2 ({args.batch * L_NS / 1e6:.0f} MB of uint8 per GPU per step)"},
         "clocks": clocks, "roofline": roofline, "gpu_launches": int(screen.launches),
     }

@@ -35,6 +35,31 @@ for L, n, B in ((8, 300_001, 100), (100, 40_000, 50)):
     same = np.array_equal(top_i, order) and np.array_equal(top_s, scores[order])
     print(f"rank {rank}: L={L} n={n} k={B - 1}: {'OK' if same else 'MISMATCH'}", flush=True)
     ok = ok and same
+# overlap mode: the all-gather + merge of screen i run on a side stream under the forward of screen i + 1; results are
+# read one screen late (double-buffered messages) and must equal the synchronous screen's
+L, n, B = 100, 60_000, 100
+cnn = flexs.baselines.models.CNN(L, 32, 100, su.DNAA, seed=7, device=torch.cuda.current_device())
+rng = np.random.default_rng(3)
+batches = [rng.integers(0, 4, size=(n, L), dtype=np.uint8) for _ in range(5)]
+lo, hi = rank * n // world, (rank + 1) * n // world
+shards = [torch.from_numpy(b[lo:hi]).cuda() for b in batches]
+sync_vs, pipe_vs = VirtualScreen(cnn, k=B - 1), VirtualScreen(cnn, k=B - 1, overlap=True)
+want = []
+for sh in shards:
+    s_, i_ = sync_vs.screen_indices(sh, lo)
+    want.append((s_.cpu().numpy().copy(), i_.cpu().numpy().copy()))
+pending, same = None, True
+for j, sh in enumerate(shards + [None]):
+    if sh is not None:
+        pipe_vs.local_topk(sh, lo, check=False)
+        res = pipe_vs.merge(L, sh.device)
+    if pending is not None:
+        pipe_vs.wait()
+        pj, (ps, pi) = pending
+        same = same and np.array_equal(ps.cpu().numpy(), want[pj][0]) and np.array_equal(pi.cpu().numpy(), want[pj][1])
+    pending = (j, res) if sh is not None else None
+print(f"rank {rank}: overlap mode, 5 pipelined screens: {'OK' if same else 'MISMATCH'}", flush=True)
+ok = ok and same
 flag = torch.tensor([0 if ok else 1], device="cuda")
 dist.all_reduce(flag)
 dist.destroy_process_group()
