@@ -38,6 +38,7 @@ UNIT = "sequences/s"
 L_NS, A_NS, F_NS, H_NS, K_NS = 100, 4, 32, 100, 5
 PER_GPU_BATCH = 1 << 22          # 4,194,304 candidates per GPU per step (419 MB of uint8 > 126 MB L2)
 TOPK = 99                        # sequences_batch_size=100 -> the [: -B : -1] slice keeps B-1
+EXCHANGE = "peer"                # N > 1: how the per-shard top-k messages travel (--exchange); falls back to nccl by itself
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}   # B200_PROFILING.md fallback
 
 
@@ -188,6 +189,22 @@ def landscape_timings(device):
                                    "hbm_gbs_alg": n * (land.seq_len + 8) / (ms / 1e3) / 1e9, "dtype": "f64"}}
 
 
+def gather_rank_stats(stats, world):
+    """Every rank's small dict of timings -> list on every rank (N > 1: explains `ms_per_step`, which follows the slowest
+    rank).  Never fails the bench: returns None if the collective does."""
+    if world <= 1:
+        return [stats]
+    try:
+        import torch.distributed as dist
+
+        out = [None] * world
+        dist.all_gather_object(out, stats)
+        return out
+    except Exception as exc:  # noqa: BLE001
+        sys.stderr.write(f"per-rank statistics unavailable: {exc}\n")
+        return None
+
+
 def load_peaks():
     path = REPO / "MEASURED_PEAKS.json"
     if path.exists():
@@ -323,8 +340,10 @@ class Screen:
         gen.manual_seed(1234 + rank)
         self.idx = torch.randint(0, A, (batch, L), dtype=torch.uint8, device=device, generator=gen)
         self.k = TOPK
-        # N > 1: the all-gather + merge of step i run on a side stream under the forward of step i + 1 (VirtualScreen overlap mode)
-        self.vs = VirtualScreen(self.surrogate, k=self.k, unique=True, overlap=world > 1)
+        # N > 1: EXCHANGE = "peer": one-sided message stores over NVLink peer memory, the merge of step i issued with step
+        # i + 1 (csrc/peer.cu); "nccl": one all_gather per step; "nccl-overlap": that all_gather on a side stream
+        self.vs = VirtualScreen(self.surrogate, k=self.k, unique=True, overlap=(world > 1 and EXCHANGE == "nccl-overlap"),
+                                exchange="peer" if (world > 1 and EXCHANGE == "peer") else "nccl")
         self.fwd_ms = []
         self.status_sum = torch.zeros(1, dtype=torch.int32, device=device)
         self.scores = None
@@ -380,6 +399,7 @@ def timed_steps(screen, steps, warmup, world, device):
     torch.cuda.synchronize(device)
     clocks = sampler.stop()
     ms = start.elapsed_time(end)
+    screen.own_ms = ms   # this rank's own device time (the reported one is the max over ranks)
     screen.fwd_ms = [a.elapsed_time(b) for a, b in screen.vs.forward_events]
     screen.vs.forward_events = None
     assert int(screen.status_sum.item()) == 0, "selection fell short of k distinct sequences: the step must use check=True"
@@ -539,15 +559,19 @@ _JSON_OUT = sys.stdout
 
 
 def main():
+    global EXCHANGE
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--exchange", choices=["peer", "nccl", "nccl-overlap"], default=EXCHANGE,
+                    help="N > 1: how the per-shard top-k messages travel (see flexs_b200/screen.py)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="candidates per GPU per step")
     ap.add_argument("--variant", default="auto", choices=["auto", "simple", "tiled", "umma", "lut"])
     ap.add_argument("--skip-extras", action="store_true", help="skip cpu_baseline / e2e / other workloads")
     args = ap.parse_args()
+    EXCHANGE = args.exchange
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -640,12 +664,24 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "north_star_cnn_100x4", "seq_len": L_NS, "alphabet": A_NS, "num_filters": F_NS,
                    "hidden": H_NS, "kernel_size": K_NS, "per_gpu_batch": args.batch, "topk": TOPK,
-                   "parallelism": f"candidate-shard x{world}, one all-gather of per-shard top-k" if world > 1 else "single GPU",
+                   "parallelism": f"candidate-shard x{world}, one exchange of the per-shard top-k messages per step" if world > 1 else "single GPU",
                    "screen": "flexs_b200.screen.VirtualScreen(unique=True): forward + one selection launch"
-                             + (" + one all-gather + one merge launch (side stream, overlapping the next step's forward)" if world > 1 else ""),
+                             + ({"peer": " + one push launch (stores into every rank's mailbox over NVLink peer memory) + wait + merge launches, issued one step late",
+                                 "nccl": " + one all-gather + one merge launch",
+                                 "nccl-overlap": " + one all-gather + one merge launch on a side stream"}[EXCHANGE] if world > 1 else ""),
                    "l2_policy": f"inputs larger than L2 ({args.batch * L_NS / 1e6:.0f} MB of uint8 per GPU per step)"},
         "clocks": clocks, "roofline": roofline, "gpu_launches": int(screen.launches),
     }
+    if world > 1:
+        # ranks are coupled once per step (the exchange of the per-shard winners): the step follows the slowest GPU of the box
+        per_rank = gather_rank_stats({"rank": rank, "forward_ms": round(float(np.mean(screen.fwd_ms)), 4),
+                                      "forward_ms_max": round(float(np.max(screen.fwd_ms)), 4),
+                                      "own_step_ms": round(screen.own_ms / args.steps, 4),
+                                      "sm_mhz": clocks.get("sm_mhz"), "reasons": clocks.get("reasons")}, world)
+        if per_rank is not None:
+            line["per_rank"] = per_rank
+            line["slowest_rank_forward_ms"] = max(r["forward_ms"] for r in per_rank)
+        line["config"]["exchange"] = getattr(screen.vs, "exchange", EXCHANGE)
     if not args.skip_extras:
         line["e2e"] = measure_e2e(screen, L_NS, A_NS, max(2, min(args.steps, 4)), world, device)
         if rank == 0:

@@ -16,7 +16,7 @@ CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libflexs_b200.so"
 
 SOURCES = ["api.cu", "encode.cu", "cnn_simple.cu", "cnn_tiled.cu", "cnn_umma.cu", "cnn_umma2.cu", "cnn_k9.cu", "cnn_a20.cu", "mlp.cu", "mlp_umma.cu",
-           "topk.cu", "select.cu", "dedup.cu", "gen.cu", "density.cu", "train.cu", "vae.cu", "landscape.cu", "enum_table.cu"]
+           "topk.cu", "select.cu", "peer.cu", "dedup.cu", "gen.cu", "density.cu", "train.cu", "vae.cu", "landscape.cu", "enum_table.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

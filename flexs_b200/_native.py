@@ -52,6 +52,13 @@ _SIGNATURES = [
                                       c_void_p, c_void_p, c_void_p]),
     ("flexs_screen_message_bytes", c_int64, [c_int, c_int]),
     ("flexs_screen_merge_dev", c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    ("flexs_peer_mailbox_bytes", c_int64, [c_int64, c_int, c_int]),
+    ("flexs_peer_alloc", c_int, [c_int64, ctypes.POINTER(c_void_p), c_char_p]),
+    ("flexs_peer_open", c_int, [c_char_p, ctypes.POINTER(c_void_p)]),
+    ("flexs_peer_close", c_int, [c_void_p]),
+    ("flexs_peer_free", c_int, [c_void_p]),
+    ("flexs_screen_push_dev", c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, ctypes.c_uint32, c_void_p, c_void_p]),
+    ("flexs_screen_wait_dev", c_int, [c_void_p, c_int64, c_int, c_int, c_int, ctypes.c_uint32, c_void_p, c_void_p]),
     ("flexs_dedup_workspace_bytes", c_int64, [c_int64]),
     ("flexs_dedup_scores_dev", c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("flexs_dedup_representatives_dev", c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
@@ -402,6 +409,47 @@ def screen_merge_dev(d_gathered: int, world: int, k: int, seq_len: int, d_top_sc
                      d_top_rows: int, stream: int = 0) -> None:
     check(lib().flexs_screen_merge_dev(c_void_p(d_gathered), world, k, seq_len, c_void_p(d_top_scores), c_void_p(d_top_idx),
                                        c_void_p(d_top_rows), c_void_p(stream)), "screen_merge")
+
+
+def peer_mailbox_bytes(msg_bytes: int, world: int, depth: int) -> int:
+    b = int(lib().flexs_peer_mailbox_bytes(msg_bytes, world, depth))
+    if b < 0:
+        raise ValueError("msg_bytes must be a positive multiple of 16, world and depth >= 1")
+    return b
+
+
+def peer_alloc(nbytes: int):
+    """cudaMalloc'ed, zeroed device buffer + its 64-byte cudaIpc handle: ``(device pointer, handle bytes)``."""
+    ptr, handle = c_void_p(), ctypes.create_string_buffer(64)
+    check(lib().flexs_peer_alloc(nbytes, ctypes.byref(ptr), handle), "peer_alloc")
+    return int(ptr.value), handle.raw
+
+
+def peer_open(handle: bytes) -> int:
+    """Map another process's buffer (same node) into this process; returns the device pointer."""
+    ptr = c_void_p()
+    check(lib().flexs_peer_open(ctypes.create_string_buffer(handle, 64), ctypes.byref(ptr)), "peer_open")
+    return int(ptr.value)
+
+
+def peer_close(ptr: int) -> None:
+    check(lib().flexs_peer_close(c_void_p(ptr)), "peer_close")
+
+
+def peer_free(ptr: int) -> None:
+    check(lib().flexs_peer_free(c_void_p(ptr)), "peer_free")
+
+
+def screen_push_dev(d_msg: int, msg_bytes: int, rank: int, world: int, slot: int, depth: int, seq: int, d_peer_bases: int,
+                    stream: int = 0) -> None:
+    check(lib().flexs_screen_push_dev(c_void_p(d_msg), msg_bytes, rank, world, slot, depth, seq, c_void_p(d_peer_bases),
+                                      c_void_p(stream)), "screen_push")
+
+
+def screen_wait_dev(d_mailbox: int, msg_bytes: int, world: int, slot: int, depth: int, seq: int, d_status: int = 0,
+                    stream: int = 0) -> None:
+    check(lib().flexs_screen_wait_dev(c_void_p(d_mailbox), msg_bytes, world, slot, depth, seq, c_void_p(d_status),
+                                      c_void_p(stream)), "screen_wait")
 
 
 def dedup_workspace_bytes(n: int) -> int:

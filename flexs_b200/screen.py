@@ -96,10 +96,20 @@ class VirtualScreen:
     double-buffered messages, so they overlap the NEXT screen's forward pass and the ranks stop meeting in a collective
     between two forwards (at 8 GPUs the exposed gather + the wait for the slowest rank cost 1.6 ms of an 8.8 ms step).
     The tensors ``merge`` returns are then complete after :meth:`wait` (or a device synchronize) and are overwritten
-    by the second screen after theirs.
+    by the second screen after theirs.  (Measured: fine at 2 GPUs; at 8 the NCCL kernel, spinning on a side stream until the
+    slowest rank arrives, keeps SMs from the persistent forward kernel: 7.2 -> 8.5 ms.)
+
+    ``exchange="peer"`` (world > 1, one node): no collective at all.  After its selection launch a rank writes its message
+    into a slot of every rank's mailbox over NVLink peer memory (``flexs_screen_push_dev``: plain stores + a release store of
+    the step number; it never waits), and the merge of screen i is issued when screen i + 1 is (or at :meth:`wait`): a
+    ``flexs_screen_wait_dev`` launch that holds the stream until the slot's flags show step i, then the same merge launch.
+    Ranks drift by up to one screen instead of meeting after every forward.  Results as in overlap mode: complete after
+    :meth:`wait`.  Every rank must issue the same sequence of screens.
     """
 
-    def __init__(self, model, k: int, group=None, unique: bool = True, overlap: bool = False):
+    PEER_DEPTH = 4   # mailbox slots (csrc/peer.cu: why 4 is enough for a lag of one screen)
+
+    def __init__(self, model, k: int, group=None, unique: bool = True, overlap: bool = False, exchange: str = "nccl"):
         """``unique``: rank distinct sequences, a repeated candidate competing once through its first occurrence —
         what the reference's explorers do by keeping scores in a dict (adalead.py:157, cmaes.py:112-115,
         dyna_ppo.py:310-314).  ``unique=False`` ranks rows."""
@@ -107,6 +117,11 @@ class VirtualScreen:
             raise TypeError("VirtualScreen needs a B200 surrogate (CNN, MLP or an Ensemble of identical ones)")
         self.model, self.k, self.group, self.unique = model, int(k), group, bool(unique)
         self.overlap = bool(overlap)
+        if exchange not in ("nccl", "peer"):
+            raise ValueError("exchange must be 'nccl' or 'peer'")
+        self.exchange = exchange
+        self._peer = {}      # peer mode: (device, seq_len, world) -> mailbox state
+        self._pending = None  # peer mode: the screen whose merge has not been issued yet
         self._calls = 0      # screens started: message slot of the current one = (_calls - 1) & 1 in overlap mode
         self._side = None    # side stream of the overlap mode
         self._buf = {}
@@ -143,8 +158,90 @@ class VirtualScreen:
         """Overlap mode: make the current stream wait for every all-gather + merge issued so far."""
         import torch
 
+        if self._pending is not None:
+            self._issue_peer_merge()
         if self._side is not None:
             torch.cuda.current_stream().wait_stream(self._side)
+
+    def _peer_state(self, device, seq_len: int, rank: int, world: int):
+        """Mailbox of this rank + the mapped mailboxes of its peers (cudaIpc handles exchanged once per shape)."""
+        import torch
+        import torch.distributed as dist
+
+        from flexs_b200 import _native
+
+        key = (device, seq_len, world)
+        if key not in self._peer:
+            mb = message_bytes(self.k, seq_len)
+            own, bases, err = None, [], None
+            with torch.cuda.device(device):
+                # Any rank may fail to allocate / map (no peer access, IPC not permitted in this container): all ranks
+                # must then agree to use the collective instead, so failures are exchanged, not raised.
+                try:
+                    own, handle = _native.peer_alloc(_native.peer_mailbox_bytes(mb, world, self.PEER_DEPTH))
+                except Exception as exc:  # noqa: BLE001
+                    handle, err = None, exc
+                handles = [None] * world
+                dist.all_gather_object(handles, handle, group=self.group)
+                if all(h is not None for h in handles):
+                    try:
+                        bases = [own if r == rank else _native.peer_open(handles[r]) for r in range(world)]
+                    except Exception as exc:  # noqa: BLE001
+                        err = exc
+                else:
+                    err = err or RuntimeError("a peer could not allocate its mailbox")
+                oks = [None] * world
+                dist.all_gather_object(oks, err is None, group=self.group)
+            if not all(oks):
+                for b in bases:
+                    if b != own:
+                        _native.peer_close(b)
+                if own is not None:
+                    _native.peer_free(own)
+                import warnings
+
+                warnings.warn(f"VirtualScreen: peer-memory exchange unavailable ({err}); using the NCCL all_gather")
+                self.exchange = "nccl"
+                return None
+            self._peer[key] = dict(own=own, bases=bases, seq=0, mb=mb,
+                                   d_bases=torch.tensor(bases, dtype=torch.int64, device=device),
+                                   status=torch.zeros(1, dtype=torch.int32, device=device),
+                                   fin=[torch.zeros(mb, dtype=torch.uint8, device=device) for _ in range(2)])
+        return self._peer[key]
+
+    def _issue_peer_merge(self):
+        import torch
+
+        from flexs_b200 import _native
+
+        st, seq, seq_len, device, world = self._pending
+        self._pending = None
+        slot = seq % self.PEER_DEPTH
+        fin_i, fin_s, fin_rows = message_views(st["fin"][seq & 1], self.k, seq_len)
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _native.screen_wait_dev(st["own"], st["mb"], world, slot, self.PEER_DEPTH, seq, st["status"].data_ptr(), stream)
+            _native.screen_merge_dev(st["own"] + slot * world * st["mb"], world, self.k, seq_len if self.unique else 0,
+                                     fin_s.data_ptr(), fin_i.data_ptr(), fin_rows.data_ptr() if self.unique else 0, stream)
+        self.launches += 2
+
+    def close(self):
+        """Peer mode: unmap the peers' mailboxes and free this rank's (collective: every rank calls it)."""
+        import torch
+        import torch.distributed as dist
+
+        from flexs_b200 import _native
+
+        self.wait()
+        for (device, _, world), st in self._peer.items():
+            torch.cuda.synchronize(device)
+            dist.barrier(group=self.group)
+            for b in st["bases"]:
+                if b != st["own"]:
+                    _native.peer_close(b)
+            dist.barrier(group=self.group)
+            _native.peer_free(st["own"])
+        self._peer = {}
 
     def local_topk(self, idx, index_offset: int = 0, check: bool = True):
         """Score ``uint8[n, L]`` residue indices resident on this GPU and select the local top-k.
@@ -206,6 +303,19 @@ class VirtualScreen:
             return top_s, top_i
         import torch.distributed as dist
 
+        st = self._peer_state(device, seq_len, rank, world) if self.exchange == "peer" else None
+        if st is not None:
+            if self._pending is not None:
+                self._issue_peer_merge()   # the previous screen's messages have had a whole forward to arrive
+            st["seq"] += 1
+            seq = st["seq"]
+            with torch.cuda.device(device):
+                _native.screen_push_dev(buf["msg"].data_ptr(), st["mb"], rank, world, seq % self.PEER_DEPTH, self.PEER_DEPTH, seq,
+                                        st["d_bases"].data_ptr(), torch.cuda.current_stream().cuda_stream)
+            self.launches += 1
+            self._pending = (st, seq, seq_len, device, world)
+            fin_i, fin_s, _ = message_views(st["fin"][seq & 1], self.k, seq_len)
+            return fin_s, fin_i
         fin_i, fin_s, fin_rows = message_views(buf["fin"], self.k, seq_len)
         with torch.cuda.device(device):
             if self.overlap:

@@ -204,6 +204,29 @@ int flexs_screen_merge_dev(const void *d_gathered, int world, int k, int seq_len
                            float *d_top_scores, int64_t *d_top_idx, uint8_t *d_top_rows,
                            void *stream);
 
+/* ---- K3d: the screen's exchange step as one-sided stores over NVLink peer memory ----------
+ * Alternative to the all_gather of screen.py for one-process-per-GPU jobs on one node (the
+ * reference has no counterpart: adalead.py:171-175 ranks one in-process list).  Every rank owns
+ * a mailbox  data [depth][world][msg_bytes] | flags [depth][world] uint32  allocated with
+ * flexs_peer_alloc (cudaMalloc + a 64-byte cudaIpc handle the host side passes to the other
+ * ranks, which map it with flexs_peer_open).  flexs_screen_push_dev writes this rank's message
+ * into slot `slot` of EVERY mailbox (d_peer_bases: device array of `world` mailbox pointers, own
+ * one included) and then stores the step number `seq` (> 0, increasing) into the slot's flag
+ * with release semantics at system scope; it never waits.  flexs_screen_wait_dev blocks the
+ * STREAM (not the host) until all `world` flags of `slot` in this rank's own mailbox have
+ * reached `seq` (4 s watchdog: *d_status = 2 and a trapped launch instead of a hung GPU); the
+ * slot's data block is then the rank-major layout flexs_screen_merge_dev takes.
+ * msg_bytes: a multiple of 16 (flexs_screen_message_bytes is).                              */
+int64_t flexs_peer_mailbox_bytes(int64_t msg_bytes, int world, int depth);
+int flexs_peer_alloc(int64_t bytes, void **d_ptr, unsigned char *handle64);
+int flexs_peer_open(const unsigned char *handle64, void **d_ptr);
+int flexs_peer_close(void *d_ptr);
+int flexs_peer_free(void *d_ptr);
+int flexs_screen_push_dev(const void *d_msg, int64_t msg_bytes, int rank, int world, int slot,
+                          int depth, uint32_t seq, const void *d_peer_bases, void *stream);
+int flexs_screen_wait_dev(const void *d_mailbox, int64_t msg_bytes, int world, int slot,
+                          int depth, uint32_t seq, int *d_status, void *stream);
+
 /* ---- K5: candidate generation helpers -------------------------------------------------
  * flexs_mutate_dev replaces generate_random_mutant (sequence_utils.py:87-108) applied to
  * n parents at once: every residue is, with probability mu, replaced by a uniform draw

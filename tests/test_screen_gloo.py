@@ -101,3 +101,33 @@ def test_all_gather_of_shard_topk_world2(tmp_path, n, k):
     want = np.lexsort((np.arange(n), -scores_all.astype(np.float64)))[: min(k, n)]
     np.testing.assert_array_equal(r0["i"], want)
     np.testing.assert_array_equal(r0["s"], scores_all[want])
+
+
+def _stats_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import json
+        import sys
+        from pathlib import Path
+
+        sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+        import bench
+
+        got = bench.gather_rank_stats({"rank": rank, "forward_ms": 7.0 + rank}, world)
+        with open(os.path.join(out_dir, f"s{rank}.json"), "w") as f:
+            json.dump(got, f)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bench_per_rank_statistics_world2(tmp_path):
+    """bench.py's N > 1 line carries every rank's forward time (the step follows the slowest GPU): the gather helper."""
+    import json
+
+    world = 2
+    mp.spawn(_stats_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        got = json.load(open(tmp_path / f"s{r}.json"))
+        assert got == [{"rank": 0, "forward_ms": 7.0}, {"rank": 1, "forward_ms": 8.0}]

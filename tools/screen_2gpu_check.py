@@ -60,6 +60,25 @@ for j, sh in enumerate(shards + [None]):
     pending = (j, res) if sh is not None else None
 print(f"rank {rank}: overlap mode, 5 pipelined screens: {'OK' if same else 'MISMATCH'}", flush=True)
 ok = ok and same
+# peer mode: no collective; every rank stores its message into every mailbox over NVLink, merges one screen late
+peer_vs = VirtualScreen(cnn, k=B - 1, exchange="peer")
+results = []
+for sh in shards + shards:            # 10 screens: the 4 mailbox slots are reused
+    peer_vs.local_topk(sh, lo, check=False)
+    s_, i_ = peer_vs.merge(L, sh.device)
+    if results:                       # the previous screen's merge was issued by this call: its buffers are final after a sync
+        torch.cuda.synchronize()
+        results[-1] = (results[-1][0].cpu().numpy().copy(), results[-1][1].cpu().numpy().copy())
+    results.append((s_, i_))
+peer_vs.wait()
+torch.cuda.synchronize()
+results[-1] = (results[-1][0].cpu().numpy().copy(), results[-1][1].cpu().numpy().copy())
+same = all(np.array_equal(results[j][0], want[j % 5][0]) and np.array_equal(results[j][1], want[j % 5][1]) for j in range(10))
+s_, i_ = peer_vs.screen_indices(shards[2], lo)          # the synchronous entry in peer mode
+same = same and np.array_equal(s_.cpu().numpy(), want[2][0]) and np.array_equal(i_.cpu().numpy(), want[2][1])
+peer_vs.close()
+print(f"rank {rank}: peer-memory exchange, 10 pipelined screens + 1 synchronous: {'OK' if same else 'MISMATCH'}", flush=True)
+ok = ok and same
 flag = torch.tensor([0 if ok else 1], device="cuda")
 dist.all_reduce(flag)
 dist.destroy_process_group()
