@@ -928,6 +928,60 @@ def test_screen_merge_kernel_matches_reference_merge(world, k, L):
     assert np.all(fi.cpu().numpy()[m:] == -1)
 
 
+def test_peer_mailbox_push_wait_merge_on_one_gpu():
+    """csrc/peer.cu without a second process: the `world` ranks' pushes all target this GPU's own mailbox (the peer table
+    lists it `world` times), over 9 steps so the 4 slots are reused; after the stream-side wait the slot holds the
+    rank-major block flexs_screen_merge_dev takes, and the merge equals screen.merge_reference."""
+    from flexs_b200 import screen
+
+    world, k, L, depth = 4, 50, 37, 4
+    mb = screen.message_bytes(k, L)
+    own, handle = _native.peer_alloc(_native.peer_mailbox_bytes(mb, world, depth))
+    assert len(handle) == 64
+    bases = torch.tensor([own] * world, dtype=torch.int64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    side = torch.cuda.Stream()
+    rng = np.random.default_rng(5)
+    try:
+        for step in range(1, 10):
+            slot = step % depth
+            msgs = torch.zeros(world, mb, dtype=torch.uint8)
+            for r in range(world):
+                idx_v, sc_v, rows_v = screen.message_views(msgs[r], k, L)
+                sc = np.sort((rng.integers(0, 300, size=k) / 4).astype(np.float32))[::-1].copy()
+                sc_v.copy_(torch.from_numpy(sc))
+                idx_v.copy_(torch.from_numpy(np.sort(rng.choice(1 << 16, size=k, replace=False)) + (r << 16)))
+                rows_v.copy_(torch.from_numpy(rng.integers(0, 3, size=(k, L), dtype=np.uint8)))   # few letters: repeats across ranks
+            d_msgs = msgs.cuda()
+            # step 5: one rank's message arrives late (its push sits behind a ~10 ms spin on another stream; everything is
+            # enqueued before anything waits, so the host never blocks on the spinning wait): the merge below can only be
+            # right if flexs_screen_wait_dev really held the stream until that message was in
+            last = world - 1 if step == 5 else None
+            for r in range(world):
+                if r != last:
+                    _native.screen_push_dev(d_msgs[r].data_ptr(), mb, r, world, slot, depth, step, bases.data_ptr(), stream)
+            if last is not None:
+                with torch.cuda.stream(side):
+                    torch.cuda._sleep(20_000_000)
+                    _native.screen_push_dev(d_msgs[last].data_ptr(), mb, last, world, slot, depth, step, bases.data_ptr(),
+                                            side.cuda_stream)
+            status = torch.zeros(1, dtype=torch.int32, device="cuda")
+            _native.screen_wait_dev(own, mb, world, slot, depth, step, status.data_ptr(), stream)
+            out = torch.zeros(mb, dtype=torch.uint8, device="cuda")
+            fi, fs, fr = screen.message_views(out, k, L)
+            _native.screen_merge_dev(own + slot * world * mb, world, k, L, fs.data_ptr(), fi.data_ptr(), fr.data_ptr(), stream)
+            torch.cuda.synchronize()
+            assert int(status.item()) == 0
+            want_s, want_i, want_rows = screen.merge_reference(msgs.reshape(-1).numpy(), world, k, L)
+            m = len(want_i)
+            np.testing.assert_array_equal(fi.cpu().numpy()[:m], want_i)
+            np.testing.assert_array_equal(fs.cpu().numpy()[:m], want_s)
+            np.testing.assert_array_equal(fr.cpu().numpy()[:m], want_rows)
+    finally:
+        torch.cuda.synchronize()
+        _native.peer_free(own)
+
+
 def test_mlp_fp16_range_guard_falls_back_to_fp32_kernel():
     """The tcgen05 MLP carries hidden activations as scaled fp16 hi/lo pairs: values above 60000/8 raise the per-stream
     flag and the gated FP32 kernel recomputes the batch — same contract as the CNN kernels."""
