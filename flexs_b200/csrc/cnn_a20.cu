@@ -27,6 +27,11 @@
 // The pooled features leave as [32][128] fp32 tiles; the dense head is cnn_k9_dense_kernel (launch_dense_tiles).
 // The rings keep rolling across items, so the tensor pipe only drains at the end of the launch.
 //
+// CTA pairs (the shipped form, cnn_a20_pair_kernel): the two CTAs of a cluster take items 2u and 2u + 1 and run them tile
+// by tile as M = 256 tcgen05.mma.cta_group::2 MMAs issued by the leader's warps 12 / 13; every barrier an issuer waits on
+// lives in the leader and collects the warps of both CTAs, every barrier an issuer signals is a multicast commit.  Each SM
+// fetches half of the weight columns per MMA (+15-19 % throughput).
+//
 // Precision: the fp16 hi/lo split of cnn_umma.cu (three products per MAC, FP32 accumulation in TMEM); activations above
 // 60000/8 raise the per-stream flag and the gated FP32 kernel recomputes the batch.
 #include <cuda_fp16.h>

@@ -16,12 +16,18 @@
 // registers (bias, scale and ReLU once per item; the warps merge an item through a staged reduction, no atomics)
 // instead of a REDUX round per tile and sequence.
 //
-// Roles (18 warps): 0-7 producers (warp w owns ring slot w: packed residues -> table index -> 128-byte gathers into a
-// SWIZZLE_128B operand slot), 8-15 conv3 epilogue (two sets of 4 warps on alternate items, running max in registers),
-// 16-17 issue the MMAs of alternate tiles.  Eight operand slots and eight TMEM accumulators (64 columns each); the roles only meet through
-// mbarriers, there is no CTA-wide barrier inside the kernel.  The pooled features of every 128 sequences leave as a
-// [32][128] fp32 tile (16 KB); cnn_k9_dense_kernel turns those tiles into scores with two tcgen05 GEMMs per tile,
-// its weights staged once per CTA.
+// Roles (18 warps): 0-7 producers (warp w owns ring slot w: it packs the 24 residue words of its own tile -> table index
+// -> 128-byte gathers into a SWIZZLE_128B operand slot), 8-15 conv3 epilogue (two sets of 4 warps on alternate items,
+// running max in registers), 16-17 issue the MMAs of alternate tiles.  Eight operand slots and eight TMEM accumulators
+// (64 columns each); the roles only meet through mbarriers: there is no CTA-wide barrier inside the kernel and no
+// barrier at a group boundary either (the residue buffers are double-buffered and re-armed by whichever producer warp
+// leaves a group last).  The pooled features leave 8 sequences at a time into a [32][128] fp32 tile per group in global
+// memory; cnn_k9_dense_kernel turns those tiles into scores with two tcgen05 GEMMs per tile, its five stages as five
+// warp roles with two tiles in flight.
+//
+// CTA pairs (the shipped form, cnn_k9_pair_kernel): two CTAs of a cluster run the same tile index of two groups as ONE
+// M = 256 tcgen05.mma.cta_group::2 — each SM feeds its own 128 rows and HALF of the weight columns, which takes 14 % off
+// the operand traffic that bounds the kernel (see issue_conv3_tile_pair and DESIGN.md 5.1).
 #include <cuda_fp16.h>
 
 #include <algorithm>
