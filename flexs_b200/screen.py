@@ -290,8 +290,10 @@ class VirtualScreen:
         return top_s, top_i, scores
 
     def merge(self, seq_len: int, device):
-        """All-gather this rank's message and reduce the ``world`` lists to the global top-k (identical on every
-        rank): returns ``(scores[k], indices[k])`` views of the merged message."""
+        """Exchange this rank's message with the other ranks (one all_gather, or the peer-memory mailboxes of
+        ``exchange="peer"``) and reduce the ``world`` lists to the global top-k (identical on every rank): returns
+        ``(scores[k], indices[k])`` views of the merged message — complete on return of the launches in the default
+        mode, after :meth:`wait` in the overlap and peer modes."""
         import torch
 
         from flexs_b200 import _native

@@ -305,3 +305,20 @@ def test_packed_wire_format_host_packers_agree():
         su.pack_sequences(big[:-1] + [7], su.DNAA)
     with pytest.raises(ValueError):
         su.pack_indices(np.full((2, 5), 4, dtype=np.uint8), 4)
+
+
+def test_virtual_screen_argument_validation():
+    """screen.py: the exchange mode is validated before any GPU work; a model without a device path is refused."""
+    from flexs_b200.screen import VirtualScreen
+
+    class _Dev:
+        def get_fitness_device(self, idx):
+            raise AssertionError("not reached")
+
+    with pytest.raises(ValueError):
+        VirtualScreen(_Dev(), k=9, exchange="carrier-pigeon")
+    with pytest.raises(TypeError):
+        VirtualScreen(object(), k=9)
+    vs = VirtualScreen(_Dev(), k=9, exchange="peer", overlap=False)
+    assert vs.exchange == "peer" and vs.PEER_DEPTH == 4 and vs.launches == 0
+    vs.wait()   # nothing pending, no stream: a no-op without a GPU
