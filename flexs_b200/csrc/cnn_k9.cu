@@ -752,17 +752,22 @@ __global__ void __launch_bounds__(DNT, 1) cnn_k9_dense_kernel(const DenseParams 
             if (i >= 2) fxd::mbar_wait(&bar[DB_X2E + b], ((i >> 1) - 1) & 1);  // GEMM 2 of tile i - 2 has read this buffer
             tc_fence_after();
             unsigned char *x2 = dx2 + b * 28 * DPLANE;
+            // the TMEM loads of chunk c + 1 are in flight while chunk c is converted (the stages of a tile form one
+            // dependency chain G1 -> E1 -> G2 -> E2 with two tiles in flight: its latency, not its issue slots, sets the rate)
+            uint32_t va[2][8], vb[2][8];
+            tmem_ld8_nowait(tl + (uint32_t)(half * 7 * 8), va[0]);
+            tmem_ld8_nowait(tl + (uint32_t)(DH + half * 7 * 8), vb[0]);
 #pragma unroll
             for (int c7 = 0; c7 < 7; ++c7) {
-                const int cchunk = half * 7 + c7;
-                uint32_t va[8], vb[8];
-                tmem_ld8_nowait(tl + (uint32_t)(cchunk * 8), va);
-                tmem_ld8_nowait(tl + (uint32_t)(DH + cchunk * 8), vb);
+                const int cchunk = half * 7 + c7, cur = c7 & 1;
                 const float4 b0 = *reinterpret_cast<const float4 *>(dv + cchunk * 8);
                 const float4 b1 = *reinterpret_cast<const float4 *>(dv + cchunk * 8 + 4);
                 const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                 tmem_ld_wait();
-                if (c7 == 6) {  // the accumulator is in registers: GEMM 1 of the next tile may overwrite it
+                if (c7 < 6) {
+                    tmem_ld8_nowait(tl + (uint32_t)((cchunk + 1) * 8), va[cur ^ 1]);
+                    tmem_ld8_nowait(tl + (uint32_t)(DH + (cchunk + 1) * 8), vb[cur ^ 1]);
+                } else {  // the accumulator is in registers: GEMM 1 of the next tile may overwrite it
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bar[DB_A1E]);
@@ -770,7 +775,7 @@ __global__ void __launch_bounds__(DNT, 1) cnn_k9_dense_kernel(const DenseParams 
                 float x[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q)
-                    x[q] = fmaxf(fmaf(__uint_as_float(va[q]) + __uint_as_float(vb[q]), inv_d1s, bb[q]), 0.f);
+                    x[q] = fmaxf(fmaf(__uint_as_float(va[cur][q]) + __uint_as_float(vb[cur][q]), inv_d1s, bb[q]), 0.f);
                 uint4 hi4, lo4;
                 split8(x, hi4, lo4, xmax);
                 *reinterpret_cast<uint4 *>(x2 + (size_t)cchunk * DPLANE + slot * 16) = hi4;
@@ -790,11 +795,12 @@ __global__ void __launch_bounds__(DNT, 1) cnn_k9_dense_kernel(const DenseParams 
             fxd::mbar_wait(&bar[DB_A2F], i & 1);
             tc_fence_after();
             float sum = 0.f;
-#pragma unroll 2
+            uint32_t va[2][8], vb[2][8];
+            tmem_ld8_nowait(tl, va[0]);
+            tmem_ld8_nowait(tl + (uint32_t)DH, vb[0]);
+#pragma unroll
             for (int cchunk = 0; cchunk < 14; ++cchunk) {
-                uint32_t va[8], vb[8];
-                tmem_ld8_nowait(tl + (uint32_t)(cchunk * 8), va);
-                tmem_ld8_nowait(tl + (uint32_t)(DH + cchunk * 8), vb);
+                const int cur = cchunk & 1;
                 const float4 b0 = *reinterpret_cast<const float4 *>(dv + DH + cchunk * 8);
                 const float4 b1 = *reinterpret_cast<const float4 *>(dv + DH + cchunk * 8 + 4);
                 const float4 w0 = *reinterpret_cast<const float4 *>(dv + 2 * DH + cchunk * 8);
@@ -802,9 +808,13 @@ __global__ void __launch_bounds__(DNT, 1) cnn_k9_dense_kernel(const DenseParams 
                 const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                 const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
                 tmem_ld_wait();
+                if (cchunk < 13) {   // next chunk's loads fly while this one is reduced
+                    tmem_ld8_nowait(tl + (uint32_t)((cchunk + 1) * 8), va[cur ^ 1]);
+                    tmem_ld8_nowait(tl + (uint32_t)(DH + (cchunk + 1) * 8), vb[cur ^ 1]);
+                }
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const float d2 = fmaxf(fmaf(__uint_as_float(va[q]) + __uint_as_float(vb[q]), inv_d2, bb[q]), 0.f);
+                    const float d2 = fmaxf(fmaf(__uint_as_float(va[cur][q]) + __uint_as_float(vb[cur][q]), inv_d2, bb[q]), 0.f);
                     sum = fmaf(d2, ww[q], sum);
                 }
             }
