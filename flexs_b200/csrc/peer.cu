@@ -6,7 +6,7 @@
 // the 16 us the collective itself takes.  Here the exchange never blocks the sender: after its selection launch a rank
 // WRITES its message into a slot of every peer's mailbox (cudaIpc-mapped peer memory, 16-byte stores over NVLink, then a
 // release store of the step number at system scope); the merge of step i is issued one step later and spins (acquire loads,
-// with the 4 s watchdog of the other kernels) only until the messages of step i are all in — by then they normally are.
+// with a 20 s watchdog) only until the messages of step i are all in — by then they normally are.
 // Ranks drift by up to a step instead of meeting after every forward.
 //
 // Mailbox of a rank: data [depth][world][msg_bytes] | flags [depth][world] uint32 (last step written into the slot).
@@ -53,7 +53,8 @@ __global__ void screen_wait_kernel(const unsigned int *flags, int world, unsigne
         if ((++spins & 63u) == 0) {
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
             if (t0 == 0) t0 = t1;
-            else if (t1 - t0 > 4000000000ull) {   // a peer died: surface it instead of hanging the stream
+            else if (t1 - t0 > 20000000000ull) {  // 20 s: a peer died — surface it instead of hanging the stream (ranks that
+                                                   // are merely late, e.g. a first launch that loads modules, must not trip it)
                 if (status) atomicExch(status, 2);
                 __trap();
             }

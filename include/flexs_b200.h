@@ -214,7 +214,7 @@ int flexs_screen_merge_dev(const void *d_gathered, int world, int k, int seq_len
  * one included) and then stores the step number `seq` (> 0, increasing) into the slot's flag
  * with release semantics at system scope; it never waits.  flexs_screen_wait_dev blocks the
  * STREAM (not the host) until all `world` flags of `slot` in this rank's own mailbox have
- * reached `seq` (4 s watchdog: *d_status = 2 and a trapped launch instead of a hung GPU); the
+ * reached `seq` (20 s watchdog: *d_status = 2 and a trapped launch instead of a hung GPU); the
  * slot's data block is then the rank-major layout flexs_screen_merge_dev takes.
  * msg_bytes: a multiple of 16 (flexs_screen_message_bytes is).                              */
 int64_t flexs_peer_mailbox_bytes(int64_t msg_bytes, int world, int depth);
