@@ -322,3 +322,21 @@ def test_virtual_screen_argument_validation():
     vs = VirtualScreen(_Dev(), k=9, exchange="peer", overlap=False)
     assert vs.exchange == "peer" and vs.PEER_DEPTH == 4 and vs.launches == 0
     vs.wait()   # nothing pending, no stream: a no-op without a GPU
+
+
+def test_peer_mailbox_layout_arithmetic():
+    """csrc/peer.cu: size of a rank's mailbox (pure host arithmetic, no GPU): data [depth][world][msg] rounded to 128 bytes,
+    then depth * world flags; bad arguments are refused."""
+    from flexs_b200 import _native
+    from flexs_b200.screen import message_bytes
+
+    mb = message_bytes(99, 100)
+    assert mb % 16 == 0 and mb == _native.screen_message_bytes(99, 100)
+    for world in (1, 2, 8):
+        for depth in (1, 4):
+            total = _native.peer_mailbox_bytes(mb, world, depth)
+            data = -(-depth * world * mb // 128) * 128
+            assert total >= data + depth * world * 4 and total - data - depth * world * 4 <= 128
+    for bad in ((0, 2, 4), (24, 2, 4), (mb, 0, 4), (mb, 2, 0)):
+        with pytest.raises(ValueError):
+            _native.peer_mailbox_bytes(*bad)
