@@ -90,20 +90,45 @@ static void *pack_rows(void *arg) {
             continue;
         }
         const unsigned char *src = PyUnicode_1BYTE_DATA(s);
+        const unsigned char *lut = j->lut;
         unsigned char *out = j->dst + r * j->row_bytes;
-        uint64_t acc = 0;
-        int have = 0;
-        for (Py_ssize_t i = 0; i < j->width; ++i) {
-            unsigned code = j->lut[src[i]];
-            if (code == 0xFF) {
-                if (!j->err) { j->err = 4; j->bad_row = r; j->bad_col = i; }
-                code = 0;
+        const Py_ssize_t width = j->width;
+        unsigned bad = 0;   /* OR of the codes: a character outside the alphabet (0xFF) sets bit 7; looked at once per row */
+        if (j->bits == 2) {
+            /* DNA / RNA: four residues per output byte, no shifts by a variable, no branch per character */
+            Py_ssize_t i = 0;
+            for (; i + 4 <= width; i += 4) {
+                const unsigned c0 = lut[src[i]], c1 = lut[src[i + 1]], c2 = lut[src[i + 2]], c3 = lut[src[i + 3]];
+                bad |= c0 | c1 | c2 | c3;
+                *out++ = (unsigned char)(c0 | (c1 << 2) | (c2 << 4) | (c3 << 6));
             }
-            acc |= (uint64_t)code << have;
-            have += j->bits;
-            if (have >= 32) { memcpy(out, &acc, 4); out += 4; acc >>= 32; have -= 32; }
+            if (i < width) {
+                unsigned byte = 0;
+                for (int sh = 0; i < width; ++i, sh += 2) {
+                    const unsigned c = lut[src[i]];
+                    bad |= c;
+                    byte |= (c & 3u) << sh;
+                }
+                *out++ = (unsigned char)byte;
+            }
+        } else {
+            uint64_t acc = 0;
+            int have = 0;
+            const int bits = j->bits;
+            for (Py_ssize_t i = 0; i < width; ++i) {
+                const unsigned code = lut[src[i]];
+                bad |= code;
+                acc |= (uint64_t)(code & 0x7Fu) << have;
+                have += bits;
+                if (have >= 32) { memcpy(out, &acc, 4); out += 4; acc >>= 32; have -= 32; }
+            }
+            while (have > 0) { *out++ = (unsigned char)acc; acc >>= 8; have -= 8; }
         }
-        while (have > 0) { *out++ = (unsigned char)acc; acc >>= 8; have -= 8; }
+        if ((bad & 0x80u) && !j->err) {   /* the row's bytes are meaningless now; the caller raises ValueError */
+            Py_ssize_t i = 0;
+            while (i < width && lut[src[i]] != 0xFF) ++i;
+            j->err = 4; j->bad_row = r; j->bad_col = i;
+        }
     }
     return NULL;
 }
@@ -121,7 +146,8 @@ static PyObject *pack_bits(PyObject *self, PyObject *args) {
     PyObject *result = NULL;
     unsigned char lut[256];
     memset(lut, 0xFF, sizeof lut);
-    if (alpha.len < 2 || alpha.len > 255) { PyErr_SetString(PyExc_ValueError, "alphabet must have 2..255 characters"); goto done; }
+    /* codes stay below 128: bit 7 of a looked-up code marks a character outside the alphabet (pack_rows ORs the codes) */
+    if (alpha.len < 2 || alpha.len > 127) { PyErr_SetString(PyExc_ValueError, "alphabet must have 2..127 characters"); goto done; }
     for (Py_ssize_t i = alpha.len - 1; i >= 0; --i) lut[((const unsigned char *)alpha.buf)[i]] = (unsigned char)i;
     int bits = 1;
     while ((1 << bits) < alpha.len) ++bits;

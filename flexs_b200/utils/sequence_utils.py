@@ -96,7 +96,7 @@ def pack_sequences(sequences: Union[Sequence[str], np.ndarray], alphabet: str) -
     n = len(sequences)
     bits = bits_per_residue(len(alphabet))
     pack_bits = _packstr("pack_bits")
-    if pack_bits is not None and n and isinstance(sequences, (list, tuple)) and isinstance(sequences[0], str):
+    if pack_bits is not None and n and len(alphabet) <= 127 and isinstance(sequences, (list, tuple)) and isinstance(sequences[0], str):
         width = len(sequences[0])
         out = np.empty((n, (width * bits + 7) // 8), dtype=np.uint8)
         pack_bits(sequences, alphabet.encode("latin-1"), out, host_threads())
