@@ -80,7 +80,12 @@ static void *pack_rows(void *arg) {
     j->err = 0; j->bad_row = -1; j->bad_col = -1;
     for (Py_ssize_t r = j->begin; r < j->end; ++r) {
         PyObject *s = j->items[r];
-        if (r + 8 < j->end) __builtin_prefetch(j->items[r + 8]);
+        if (r + 8 < j->end) {   /* header + characters of a compact str: up to 40 + width bytes */
+            const char *nx = (const char *)j->items[r + 8];
+            __builtin_prefetch(nx);
+            __builtin_prefetch(nx + 64);
+            if (j->width > 88) __builtin_prefetch(nx + 128);
+        }
         int err = 0;
         if (!PyUnicode_Check(s)) err = 1;
         else if (PyUnicode_GET_LENGTH(s) != j->width) err = 2;
